@@ -1,0 +1,186 @@
+/* fleetrec.h -- C ABI of the B200-native FleetRec inference hot path.
+ *
+ * One call chain replaces three reference boundaries:
+ *   B1  FPGA lookup kernel launch   embedding_47_krnl(...)            FPGA/kernel/user_krnl/embedding_47_krnl/src/hls/embedding_47_krnl.hpp:32-71
+ *       + its host bring-up         host.cpp setArg/enqueueTask        FPGA/host/embedding_47_krnl/host.cpp:691-761
+ *   B2  wire format                 item-major LE fp32, INPUT_SIZE/item embedding_47_krnl.cpp:774, GPU/.../constant.h:37-38
+ *   B3  GPU MLP worker              thread_consume(CUDA_thread_info*)  GPU/final_network_cublasLt_1_node_no_FIFO_scatter/cuda_server.c:91-101
+ *
+ * Conventions: plain C types only (no CUDA/torch types in signatures); every call
+ * returns an fr_status (0 = ok) and leaves a message retrievable through
+ * fr_last_error(); nothing ever calls exit().  The engine owns all device memory.
+ * One engine drives ONE GPU (one process per GPU); table sharding across
+ * processes is configured with the fr_shard_* calls.  There is no CPU fallback:
+ * fr_create fails with FR_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef FLEETREC_H
+#define FLEETREC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int fr_status;
+enum {
+  FR_OK = 0,
+  FR_ERR_INVALID = 1,     /* bad argument / descriptor                       */
+  FR_ERR_CUDA = 2,        /* CUDA runtime or driver error (message has it)   */
+  FR_ERR_OOM = 3,         /* device or host allocation failed                */
+  FR_ERR_STATE = 4,       /* call order: table/layer not loaded, not sharded */
+  FR_ERR_UNSUPPORTED = 5  /* shape the kernels do not cover                  */
+};
+
+/* Memory tier a table had in the reference (constants.hpp); informational on B200
+ * (everything is HBM3e) except that FR_TIER_PLRAM tables are replicated when sharding. */
+enum { FR_TIER_HBM = 0, FR_TIER_DDR = 1, FR_TIER_PLRAM = 2, FR_TIER_CPU = 3 };
+
+/* MLP semantics.  LINEAR is what cuda_server.c:468-491 executes (4 GEMMs, alpha=1,
+ * beta=0, no bias, no activation).  BIAS_RELU_SIGMOID is what constant.h:1-17
+ * documents (W*x+B) plus ReLU between layers and a final sigmoid (north star). */
+enum { FR_MLP_LINEAR = 0, FR_MLP_BIAS_RELU_SIGMOID = 1 };
+
+/* Arithmetic of the three hidden GEMMs.
+ *   TF32   tcgen05.mma kind::tf32, operands rounded to TF32 (rna), FP32 accumulate in TMEM
+ *   FP32   SIMT FFMA kernels, FP32 operands and accumulate (reference's CUBLAS_COMPUTE_32F) */
+enum { FR_PREC_TF32 = 0, FR_PREC_FP32 = 1 };
+
+typedef struct fr_table_desc {
+  int tier;          /* FR_TIER_*                                              */
+  int tier_index;    /* i of TABLE_SIZE_<tier>_<i>                             */
+  int bank;          /* i mod <tier>_BANK_NUM                                  */
+  int round;         /* i div <tier>_BANK_NUM                                  */
+  int64_t rows;      /* TABLE_SIZE_<tier>_<i>                                  */
+  int dim;           /* DATA_SIZE_<tier>_<i> == 4*AXI_PADDED_SIZE (floats)     */
+} fr_table_desc;
+
+/* One contiguous piece of the per-item concat vector: floats
+ * [dst, dst+len) = table[idx[table]][col, col+len).  The list restates
+ * gather_embeddings() of each kernel, including the medium model's duplicate pad. */
+typedef struct fr_segment_desc {
+  int dst, table, col, len;
+} fr_segment_desc;
+
+typedef struct fr_model_desc {
+  const char* name;
+  int n_tables;
+  const fr_table_desc* tables;      /* idx[b][t] addresses tables[t]           */
+  int n_segments;
+  const fr_segment_desc* segments;
+  int concat_floats;                /* INPUT_SIZE (multiple of 16)             */
+  int hidden[4];                    /* HIDDEN_SIZE1..3, OUTPUT_SIZE (=1)       */
+  int mlp_mode;                     /* FR_MLP_*                                */
+  int precision;                    /* FR_PREC_*                               */
+  int max_batch;                    /* largest B a stream will be given        */
+} fr_model_desc;
+
+typedef struct fr_engine fr_engine;
+/* A worker context: one CUDA stream plus the activation workspaces for one batch
+ * in flight.  Mirrors one thread_consume() worker (cuda_server.c:101-183). */
+typedef struct fr_stream_s* fr_stream;
+
+/* ---- catalogue ---------------------------------------------------------- */
+/* Fill *out with a built-in catalogue: "small" (47 tables, 352), "medium" (98,
+ * 880), "large_half" (188, 1952), "large" (377, 3968).  Pointers inside stay
+ * valid for the life of the library.  mlp_mode/precision/max_batch get defaults
+ * (BIAS_RELU_SIGMOID, TF32, 16384) the caller may overwrite. */
+fr_status fr_model_builtin(const char* name, fr_model_desc* out);
+
+/* ---- engine ------------------------------------------------------------- */
+/* n_gpus must be 1 (one process per GPU); device_ids[0] is the CUDA ordinal. */
+fr_status fr_create(const fr_model_desc* desc, int n_gpus, const int* device_ids, fr_engine** out);
+void fr_destroy(fr_engine* e);
+/* Message of the last failing call on this engine (or of the last failing
+ * fr_create / fr_model_builtin on this thread when e == NULL). */
+const char* fr_last_error(const fr_engine* e);
+
+/* Override the row count of a table before it is loaded/filled (tests and
+ * memory-capped runs use the real dims with fewer rows). */
+fr_status fr_set_table_rows(fr_engine* e, int table_id, int64_t rows);
+
+/* Copy a host table image [rows][dim] fp32 into HBM; caller keeps ownership.
+ * Replaces host.cpp:324-423,592-750 (vector alloc + init + migrate). */
+fr_status fr_load_table(fr_engine* e, int table_id, const float* host_rows, int64_t rows, int dim);
+/* Device-side fills, bit-identical to the oracle's:
+ *   reference: even rows 1.0f, odd rows 0.0f (host.cpp:66-88, embedding_47_krnl.cpp:871-897);
+ *              debug_rows > 0 reproduces the `#define DEBUG` truncation (first debug_rows rows).
+ *   hash:      every float a distinct finite normal derived from (seed, table, row, col). */
+fr_status fr_fill_table_reference(fr_engine* e, int table_id, int64_t debug_rows);
+fr_status fr_fill_table_hash(fr_engine* e, int table_id, uint32_t seed);
+/* Read rows back (tests): copies [n_rows][dim] starting at first_row to host. */
+fr_status fr_read_table(fr_engine* e, int table_id, int64_t first_row, int64_t n_rows, float* host_out);
+
+/* Layer k in 0..3.  W is the reference's layout: column-major out_k x in_k with
+ * ld = out_k (cuda_server.c:215,253,291,329), i.e. row-major [in_k][out_k].
+ * bias [out_k] may be NULL (treated as zeros; ignored in LINEAR mode). */
+fr_status fr_load_mlp(fr_engine* e, int layer, const float* W_in_major, const float* bias);
+fr_status fr_set_mlp_mode(fr_engine* e, int mlp_mode);
+fr_status fr_set_precision(fr_engine* e, int precision);
+
+/* ---- worker streams ----------------------------------------------------- */
+fr_status fr_stream_create(fr_engine* e, fr_stream* out);
+void fr_stream_destroy(fr_engine* e, fr_stream s);
+/* Raw cudaStream_t of a worker (so callers holding CUDA code can order against it). */
+void* fr_stream_cuda(fr_stream s);
+
+/* ---- hot path ----------------------------------------------------------- */
+/* idx: [B][n_tables] int32, row index per table per item; scores: [B] fp32.
+ * Both may be host or device pointers (detected); host buffers are copied
+ * inside the call chain on the worker's stream (pin them for true async).
+ * stream == NULL uses the engine's default worker.  Asynchronous: results are
+ * valid after fr_sync().  Out-of-range indices are a caller error (checked only
+ * when the engine was built with FR_CHECK_INDICES; the reference never checks). */
+fr_status fr_infer(fr_engine* e, const int32_t* idx, int B, float* scores, fr_stream s);
+/* Parity hook: the concat vectors [B][concat_floats] exactly as the FPGA would
+ * put them on the wire (embedding_47_krnl.cpp:774 byte stream, item-major). */
+fr_status fr_gather_only(fr_engine* e, const int32_t* idx, int B, float* concat, fr_stream s);
+/* B3 alone: x is what cuda_server.c:425-461 receives, [B][concat_floats] fp32. */
+fr_status fr_mlp_only(fr_engine* e, const float* x, int B, float* scores, fr_stream s);
+fr_status fr_sync(fr_engine* e, fr_stream s);
+
+/* ---- introspection ------------------------------------------------------ */
+/* Number of kernels this library has launched on this engine so far. */
+int64_t fr_launch_count(const fr_engine* e);
+/* Device bytes currently held by tables / by everything. */
+int64_t fr_table_bytes(const fr_engine* e);
+/* Device time (ms) between two marks on a worker stream: fr_mark(s, 0) ...
+ * fr_mark(s, 1); fr_elapsed_ms() syncs on mark 1.  CUDA events on the stream the
+ * kernels are launched on. */
+fr_status fr_mark(fr_engine* e, fr_stream s, int which);
+fr_status fr_elapsed_ms(fr_engine* e, fr_stream s, float* ms);
+
+/* ---- table sharding across processes (one engine per GPU) ---------------- */
+/* owner[t] in [0, world) = rank holding table t, or -1 = replicated on every
+ * rank.  Must be called before tables are loaded; non-owned tables then take
+ * no memory and fr_load_table / fr_fill_* on them are no-ops returning FR_OK. */
+fr_status fr_shard_init(fr_engine* e, int rank, int world, const int* owner);
+/* Exchange buffers: each rank exports one CUDA-IPC handle (64 bytes) for its
+ * receive buffer, the host gathers all of them (any transport) and hands the
+ * [world][64] array to every rank. */
+fr_status fr_shard_export(fr_engine* e, void* handle64);
+fr_status fr_shard_import(fr_engine* e, const void* handles /* [world][64] */);
+/* In-process variant (tests, single-process multi-GPU): peers[r] = engine of rank r. */
+fr_status fr_shard_attach_local(fr_engine* e, fr_engine* const* peers);
+/* Sharded step, phase 1: gather the locally owned tables for the GLOBAL batch
+ * idx [B_global][n_tables] and push every row piece straight into the concat
+ * buffer of the rank that owns the item (rank r owns items [r*B_global/world,
+ * (r+1)*B_global/world)) through NVLink peer stores.  Phase 2 (after the host
+ * has barriered all ranks): MLP over the local items, scores [B_global/world]. */
+fr_status fr_shard_gather_push(fr_engine* e, const int32_t* idx, int B_global, fr_stream s);
+fr_status fr_shard_mlp(fr_engine* e, int B_global, float* scores_local, fr_stream s);
+/* Local concat buffer after the exchange (parity hook), [B_global/world][concat_floats]. */
+fr_status fr_shard_read_concat(fr_engine* e, int B_global, float* concat_local, fr_stream s);
+
+/* ---- Cartesian-merged tables (MicroRec), SURVEY.md section 8c(b) ---------- */
+/* merged[iA*rowsB + iB] = A[iA] || B[iB]; index of the merged row, in int64. */
+int64_t fr_merge_index(int64_t iA, int64_t iB, int64_t rowsB);
+/* Build the merged table on the device from two loaded tables and install it
+ * as table `dst_table` (whose desc must have rows = rowsA*rowsB, dim = dimA+dimB). */
+fr_status fr_merge_tables(fr_engine* e, int table_a, int table_b, int dst_table);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLEETREC_H */

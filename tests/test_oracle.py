@@ -1,0 +1,169 @@
+"""The oracle against the reference's golden vectors and known answers (CPU).
+
+Golden vectors (tests/golden/ref_*.npz) were produced by executing the
+reference's own HLS lookup kernels (tests/golden/make_golden.py); the MLP
+known answers are the reference README's (GPU/final_network_cublasLt_1_node_
+no_FIFO_scatter/README.md:7-11).
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from fleetrec import catalogue
+from oracle import oracle, ref
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+MODELS3 = ("small", "medium", "large_half")
+
+
+def golden_tables(cat, seed):
+    return [oracle.fill_reference(t.rows, t.dim) if t.tier == "PLRAM"
+            else oracle.fill_hash(seed, t.id, t.rows, t.dim) for t in cat.tables]
+
+
+@pytest.mark.parametrize("model", MODELS3)
+def test_gather_matches_reference_wire_golden(model):
+    g = np.load(os.path.join(GOLD, f"ref_{model}.npz"))
+    cat = catalogue.load(model).with_row_cap(int(g["row_cap"]))
+    tables = golden_tables(cat, int(g["seed"]))
+    out = oracle.gather(cat, tables, oracle.idx_reference(96, cat.n_tables))
+    assert np.array_equal(out[:32].view(np.uint32), g["wire_first32"].view(np.uint32))
+    assert hashlib.sha256(out.tobytes()).hexdigest() == str(g["wire96_sha256"])
+
+
+@pytest.mark.parametrize("model", MODELS3)
+def test_segments_match_reference_stream_order(model):
+    """Catalogue segments vs the reference's gather_embeddings() fed tagged words:
+    float f of stream s of item i carries i*65536 + s*256 + f."""
+    g = np.load(os.path.join(GOLD, f"ref_{model}.npz"))
+    cat = catalogue.load(model)
+    n_pl = max(t.bank for t in cat.tables if t.tier == "PLRAM") + 1
+    where = {}
+    for tier, base, nb in (("HBM", 0, 28), ("DDR", 28, 2), ("PLRAM", 30, n_pl)):
+        for b in range(nb):
+            off = 0
+            for t in [t for t in cat.tables if t.tier == tier and t.bank == b]:
+                where[t.id] = (base + b, off)
+                off += t.dim
+    for item, key in ((0, "tagged_item0"), (31, "tagged_item31")):
+        exp = np.zeros(cat.concat_floats, np.float32)
+        for s in cat.segments:
+            st, off = where[s.table]
+            exp[s.dst:s.dst + s.len] = item * 65536 + st * 256 + off + s.col + np.arange(s.len)
+        assert np.array_equal(exp, g[key])
+
+
+@pytest.mark.parametrize("model", MODELS3)
+@pytest.mark.skipif(not all(ref.available(m) for m in MODELS3), reason="oracle/_ref not built")
+def test_live_reference_kernel_matches_oracle(model):
+    """Run the compiled reference kernel now (oracle/_ref) with a different seed."""
+    cat = catalogue.load(model).with_row_cap(128)
+    tables = golden_tables(cat, 0xBEEF)
+    out, _ = ref.run_top(model, cat, tables, batch_num=2)
+    exp = oracle.gather(cat, tables, oracle.idx_reference(64, cat.n_tables))
+    assert out.shape == exp.shape
+    assert np.array_equal(out.view(np.uint32), exp.view(np.uint32))
+
+
+def test_reference_fill_and_lookup_kat():
+    """SURVEY 8(c) lookup KAT: with the reference fill and index list, item j's whole
+    concat vector is 1.0 when idx_random[j] is even, else 0.0 (incl. the medium pad)."""
+    for model in MODELS3:
+        cat = catalogue.load(model).with_row_cap(200)
+        tables = oracle.make_tables(cat, "reference")
+        out = oracle.gather(cat, tables, oracle.idx_reference(32, cat.n_tables))
+        for j, r in enumerate(catalogue.IDX_RANDOM):
+            assert np.all(out[j] == (1.0 if r % 2 == 0 else 0.0)), (model, j)
+    ones = [j for j, r in enumerate(catalogue.IDX_RANDOM) if r % 2 == 0]
+    assert ones == [2, 3, 7, 8, 9, 11, 15, 16, 17, 20, 21, 22, 23, 25, 27, 28, 29, 30, 31]
+
+
+def test_fill_reference_debug_truncation():
+    t = oracle.fill_reference(1000, 8, debug_rows=200)      # host.cpp:75 `#define DEBUG`
+    assert np.all(t[0:200:2] == 1.0) and np.all(t[1:200:2] == 0.0) and np.all(t[200:] == 0.0)
+    t = oracle.fill_reference(7, 4)                          # odd row count: last row untouched
+    assert t[:, 0].tolist() == [1, 0, 1, 0, 1, 0, 0]
+
+
+def test_hash_fill_is_finite_normal_and_distinct():
+    t = oracle.fill_hash(7, 3, 4096, 16)
+    bits = t.view(np.uint32)
+    expo = (bits >> 23) & 0xFF
+    assert expo.min() >= 118 and expo.max() <= 126
+    assert np.isfinite(t).all() and np.abs(t).max() < 1.0 and np.abs(t).min() >= 2.0 ** -9
+    assert len(np.unique(bits)) > 0.999 * bits.size
+    assert oracle.hash_bits(7, 3, 5, 2) == int(bits[5, 2])
+
+
+@pytest.mark.parametrize("inp,h1,expect", [(352, 1024, 47244640256.0), (512, 1024, 68719476736.0),
+                                           (880, 1024, 118111600640.0), (1024, 1024, 137438953472.0),
+                                           (3968, 2048, 1065151889408.0)])
+def test_mlp_all_ones_known_answer(inp, h1, expect):
+    """README.md:9,11: all-ones input and weights -> IN*H1*H2*H3 (exact in fp32)."""
+    dims = [inp, h1, 512, 256, 1]
+    W = [np.ones((dims[k], dims[k + 1]), np.float32) for k in range(4)]
+    x = np.ones((5, inp), np.float32)
+    out = oracle.mlp(x, dims, W, None, mode=0)
+    assert np.all(out == np.float32(expect))
+    assert np.all(oracle.mlp(x, dims, W, None, mode=0, acc64=True) == np.float32(expect))
+
+
+def test_mlp_matches_numpy_float64():
+    dims = [352, 1024, 512, 256, 1]
+    W, b = oracle.make_weights(dims, seed=1)
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-1, 1, (64, 352)).astype(np.float32)
+    h = x.astype(np.float64)
+    for k in range(4):
+        h = h @ W[k].astype(np.float64) + b[k]
+        if k < 3:
+            h = np.maximum(h, 0)
+    exp = 1 / (1 + np.exp(-h[:, 0]))
+    got = oracle.mlp(x, dims, W, b, mode=1)
+    assert np.max(np.abs(got - exp) / exp) < 1e-5
+    h = x.astype(np.float64)
+    for k in range(4):
+        h = h @ W[k].astype(np.float64)
+    got = oracle.mlp(x, dims, W, None, mode=0, acc64=True)
+    assert np.allclose(got, h[:, 0], rtol=1e-5, atol=1e-6)
+
+
+def test_gather_edge_cases():
+    cat = catalogue.load("small").with_row_cap(64)
+    tables = oracle.make_tables(cat, "hash")
+    assert oracle.gather(cat, tables, np.zeros((0, 47), np.int32)).shape == (0, 352)   # empty batch
+    idx = np.stack([np.array([t.rows - 1 for t in cat.tables], np.int32),                # last rows
+                    np.zeros(47, np.int32)])                                              # first rows
+    out = oracle.gather(cat, tables, idx)
+    for s in cat.segments:
+        assert np.array_equal(out[0, s.dst:s.dst + s.len], tables[s.table][-1, s.col:s.col + s.len])
+        assert np.array_equal(out[1, s.dst:s.dst + s.len], tables[s.table][0, s.col:s.col + s.len])
+
+
+def test_large_model_is_cpu_block_then_two_halves():
+    big, half = catalogue.load("large"), catalogue.load("large_half")
+    assert big.n_tables == 377 and big.concat_floats == 3968 and big.hidden[0] == 2048
+    assert big.segments[0].len == 64 and big.tables[0].tier == "CPU"
+    for s_h, s_a, s_b in zip(half.segments, big.segments[1:189], big.segments[189:]):
+        assert (s_a.dst, s_a.table, s_a.len) == (64 + s_h.dst, 1 + s_h.table, s_h.len)
+        assert (s_b.dst, s_b.table, s_b.len) == (64 + 1952 + s_h.dst, 189 + s_h.table, s_h.len)
+
+
+def test_cartesian_merge_self_consistency():
+    """gather(M, remap(iA,iB)) == gather(A,iA) || gather(B,iB)."""
+    A, B = oracle.fill_hash(1, 0, 37, 4), oracle.fill_hash(1, 1, 11, 8)
+    M = oracle.merge_tables(A, B)
+    assert M.shape == (37 * 11, 12)
+    for ia, ib in ((0, 0), (36, 10), (0, 10), (36, 0), (17, 5)):
+        r = oracle.merge_index(ia, ib, 11)
+        assert np.array_equal(M[r], np.concatenate([A[ia], B[ib]]))
+    assert oracle.merge_index(99_999_999, 9_999_999, 10_000_000) == 99_999_999 * 10_000_000 + 9_999_999
+
+
+def test_catalogue_bytes_and_flops():
+    m = {n: catalogue.load(n) for n in catalogue.MODEL_NAMES}
+    assert [m[n].gather_bytes_per_item() for n in ("small", "medium", "large")] == [1596, 3896, 17380]
+    assert [m[n].mlp_flops_per_item() for n in ("small", "medium", "large")] == [2032128, 3113472, 18612736]
+    assert abs(m["small"].table_bytes() / 1e9 - 1.415) < 1e-3
