@@ -1,0 +1,332 @@
+#!/usr/bin/env python3
+"""bench.py -- inferences/s of the FleetRec hot path (lookup+concat -> MLP) on B200.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on host cores
+
+A step = one batch of 2048 items of the small (47-table, 352-1024-512-256-1)
+model -- BASELINE.json configs[1] -- through gather+MLP.  Steps are dealt
+round-robin to `--streams` worker streams (the reference's THREAD_NUM workers,
+cuda_server.c:554-556), so several batches are in flight; the timed region is
+bracketed by barrier + synchronize and timed with CUDA events that fork from /
+join into the worker streams.
+
+  value  indices already resident in HBM, scores left in HBM
+  e2e    the public call (Engine.infer_async == fr_infer) on pinned HOST index and
+         score buffers: the H2D of every batch's indices and the D2H of its scores
+         are inside the timed region
+  roofline      the step's slowest kernel, timed alone with CUDA events on its stream
+  cpu_baseline  the oracle's C port of the same workload on this box's host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "gpu-fpga-recommendation-system_b200"))
+
+METRIC = "inferences/sec (gather+MLP)"
+UNIT = "inferences/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm=j["hbm_gbs"], bf16=j["bf16_tflops"], bf16_sustained=j.get("bf16_tflops_sustained"),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- reference arm (host cores)
+def cpu_port_run(args, steps, warmup, budget_s=None, total_budget_s=None):
+    """The reference's algorithm (oracle C port, OpenMP) on the host: lookup+concat in
+    wire order, then the 4-layer MLP.  A step is one batch of args.batch items, or -- when
+    `total_budget_s` would be exceeded by `steps` full batches -- a bounded sample of it
+    (the first `items` items of the batch)."""
+    from fleetrec import catalogue
+    from oracle import oracle
+    cat = catalogue.load(args.model)
+    dims = cat.layer_dims
+    cores = oracle.max_threads()
+    tables = oracle.make_tables(cat, "hash", seed=0x5EED)
+    W, b = oracle.make_weights(dims, seed=42)
+    batches = [oracle.zipf_indices(cat, args.batch, seed=1234 + i) for i in range(4)]
+    items = args.batch
+    for i in range(max(warmup, 2)):
+        t0 = time.perf_counter()
+        oracle.mlp(oracle.gather(cat, tables, batches[i % 4]), dims, W, b, mode=1)
+        t_batch = time.perf_counter() - t0
+    if total_budget_s and steps * t_batch > total_budget_s:
+        items = max(64, int(args.batch * total_budget_s / (steps * t_batch)) // 64 * 64)
+        batches = [bt[:items] for bt in batches]
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(steps):
+        oracle.mlp(oracle.gather(cat, tables, batches[i % 4]), dims, W, b, mode=1)
+        done += 1
+        if budget_s and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return dict(value=done * items / dt, unit=UNIT, cores=cores, kind="port",
+                sample=f"{done} steps of {items} items (batch {args.batch}), {args.model} model full-size tables "
+                       f"({cat.table_bytes() / 1e9:.2f} GB, hash fill), Zipf(1.05) indices, "
+                       f"oracle/fr_oracle.c gather + fp32 MLP, OpenMP {cores} threads"), dt / max(done, 1)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, per_step = cpu_port_run(args, args.steps, args.warmup, total_budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, 1), "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "reference algorithm on host cores: the FPGA lookup cannot run here and the reference has no CPU "
+                    "MLP, so this is the oracle's C port (cpu_baseline.kind = port)"}
+    print(json.dumps(line))
+
+
+def workload_config(args, n):
+    return {"workload": f"FleetRec {args.model} model (BASELINE.json configs[1]): all tables HBM-resident, "
+                        f"gather+MLP at batch {args.batch}, Zipf(1.05) indices",
+            "model_tables": args.model, "batch": args.batch, "global_batch": args.batch * n,
+            "streams": args.streams, "mlp_mode": "bias_relu_sigmoid", "precision": args.precision,
+            "sharding": "replicated" if n == 1 else args.shard,
+            "l2": "tables (1.4 GB) exceed L2; a pool of distinct index batches is rotated so no step repeats "
+                  "the previous step's inputs"}
+
+
+# --------------------------------------------------------------------------- CUDA arm
+def run_ours(args):
+    import torch
+
+    import fleetrec
+    from fleetrec import catalogue
+    from oracle import oracle  # index/weight generators + the cpu_baseline leg only
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cat = catalogue.load(args.model)
+    dims = cat.layer_dims
+    B, T = args.batch, cat.n_tables
+    prec = fleetrec.FR_PREC_TF32 if args.precision == "tf32" else fleetrec.FR_PREC_FP32
+    eng = fleetrec.Engine(cat, device=local, precision=prec, max_batch=max(B, args.gather_batch))
+    eng.fill_hash(seed=0x5EED)
+    W, b = oracle.make_weights(dims, seed=42)
+    eng.load_mlp(W, b)
+    workers = [fleetrec.Worker(eng) for _ in range(args.streams)]
+    wstreams = [torch.cuda.ExternalStream(w.cuda_stream) for w in workers]
+    main = torch.cuda.current_stream()
+
+    pool = 32
+    idx_host = [torch.from_numpy(oracle.zipf_indices(cat, B, seed=1234 + 1000 * rank + i)).pin_memory()
+                for i in range(pool)]
+    idx_dev = [t.cuda(non_blocking=True) for t in idx_host]
+    sc_dev = [torch.empty(B, dtype=torch.float32, device="cuda") for _ in range(args.streams)]
+    sc_host = [torch.empty(B, dtype=torch.float32).pin_memory() for _ in range(args.streams)]
+    torch.cuda.synchronize()
+
+    # correctness gate before timing anything: one batch against the oracle's hash
+    got = eng.gather_only(idx_host[0].numpy())
+    assert np.array_equal(got.view(np.uint32), oracle.gather_hashed(cat, 0x5EED, idx_host[0].numpy()).view(np.uint32))
+
+    def timed(step_fn, steps, warmup):
+        for i in range(warmup):
+            step_fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = eng.launch_count()
+        e0.record(main)
+        for s in wstreams:
+            s.wait_event(e0)
+        for i in range(steps):
+            step_fn(i)
+        for s in wstreams:
+            ev = torch.cuda.Event()
+            ev.record(s)
+            main.wait_event(ev)
+        e1.record(main)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, eng.launch_count() - l0
+
+    def step_dev(i):
+        w = i % args.streams
+        eng.infer_async(idx_dev[i % pool], sc_dev[w], B, workers[w])
+
+    def step_e2e(i):
+        w = i % args.streams
+        eng.infer_async(idx_host[i % pool].numpy(), sc_host[w].numpy(), B, workers[w])
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches = timed(step_dev, args.steps, args.warmup)
+    ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        eng.close()
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    value = world * args.steps * B / (ms_dev * 1e-3)
+    e2e = world * args.steps * B / (ms_e2e * 1e-3)
+
+    # ---- per-kernel times (each kernel alone, CUDA events on its own stream) and rooflines
+    pk = peaks()
+    kms = eng.time_kernels(idx_dev[1], B, reps=args.kernel_reps, worker=workers[0])
+    names = ["gather_concat", "mlp_layer1", "mlp_layer2", "mlp_layer3+out", "mlp_out"]
+    flops = [0, 2.0 * B * dims[0] * dims[1], 2.0 * B * dims[1] * dims[2],
+             2.0 * B * (dims[2] * dims[3] + (dims[3] if args.precision == "tf32" else 0)), 2.0 * B * dims[3]]
+    gather_bytes = B * cat.gather_bytes_per_item(materialised=True)
+    tensor_peak = pk["bf16"] / 2 if args.precision == "tf32" else 2 * 148 * 128 * 1.965e-3   # TF/s
+    kernels = []
+    for n, ms, fl in zip(names, kms, flops):
+        if ms <= 0:
+            continue
+        if n == "gather_concat":
+            a = gather_bytes / (ms * 1e-3) / 1e9
+            kernels.append(dict(name=n, ms=ms, bound="hbm", achieved=a, peak=pk["hbm"], unit="GB/s", frac=a / pk["hbm"]))
+        else:
+            a = fl / (ms * 1e-3) / 1e12
+            kernels.append(dict(name=n, ms=ms, bound="tensor", achieved=a, peak=tensor_peak, unit="TFLOP/s",
+                                frac=a / tensor_peak))
+    dom = max(kernels, key=lambda k: k["ms"])
+    roofline = dict(bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"], unit=dom["unit"], frac=dom["frac"],
+                    traffic=None, kernel=dom["name"], ms_per_launch=dom["ms"],
+                    peak_source=pk["src"] + ("; tf32 tensor peak taken as half the measured dense bf16 rate"
+                                             if dom["bound"] == "tensor" and args.precision == "tf32" else ""),
+                    share_of_step=dom["ms"] / sum(k["ms"] for k in kernels))
+
+    # ---- stand-alone gather at a large batch, uniform indices (the HBM-roofline test of the lookup)
+    GB = args.gather_batch
+    gidx = torch.from_numpy(oracle.uniform_indices(cat, GB, seed=4321)).cuda()
+    gout = torch.empty(GB, cat.concat_floats, dtype=torch.float32, device="cuda")
+    for _ in range(3):
+        eng.gather_only_async(gidx, gout, GB, workers[0])
+    eng.sync(workers[0])
+    eng.mark(0, workers[0])
+    for _ in range(20):
+        eng.gather_only_async(gidx, gout, GB, workers[0])
+    eng.mark(1, workers[0])
+    gms = eng.elapsed_ms(workers[0]) / 20
+    g_alg = GB * cat.gather_bytes_per_item(materialised=True)
+    gather = dict(batch=GB, indices="uniform", ms=gms, achieved=g_alg / (gms * 1e-3) / 1e9, peak=pk["hbm"], unit="GB/s",
+                  frac=g_alg / (gms * 1e-3) / 1e9 / pk["hbm"], bytes_per_item=cat.gather_bytes_per_item(True))
+
+    eng.close()
+    cpu, _ = cpu_port_run(args, 10 ** 9, 1, budget_s=args.cpu_seconds) if args.cpu_seconds > 0 else (None, None)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32 (fp32 storage, fp32 accumulate)" if args.precision == "tf32" else "f32",
+            "data": "synthetic", "config": workload_config(args, world),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * T * 4, "d2h_bytes_per_step": B * 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
+            "gather_standalone": gather, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="small")
+    ap.add_argument("--batch", type=int, default=2048)
+    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--shard", default="replicated", choices=["replicated", "tables"])
+    ap.add_argument("--gather-batch", type=int, default=16384)
+    ap.add_argument("--kernel-reps", type=int, default=50)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

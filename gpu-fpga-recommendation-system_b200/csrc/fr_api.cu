@@ -1,0 +1,672 @@
+// fr_api.cu -- the C ABI of include/fleetrec.h: engine lifetime, table and weight
+// residency in HBM, worker streams, and the hot-path entry points.
+//
+// Host-side shape of the reference this replaces:
+//   FPGA/host/embedding_47_krnl/host.cpp:324-761  (allocate + init tables, migrate, launch)
+//   GPU/final_network_cublasLt_1_node_no_FIFO_scatter/cuda_server.c:101-183,346-354,406-495
+//                                                  (per-worker buffers + stream, weights H2D, batch loop)
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "fr_common.h"
+
+// ---------------------------------------------------------------------------
+// built-in catalogues (generated from the reference's constants.hpp)
+struct fr_builtin_model {
+  const char* name;
+  int n_tables;
+  const fr_table_desc* tables;
+  int n_segments;
+  const fr_segment_desc* segments;
+  int concat_floats;
+  int hidden[4];
+};
+#include "fr_catalogue_data.inc"
+
+static thread_local std::string g_tls_err;
+
+fr_status fr_fail(const fr_engine* e, fr_status code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf;
+  g_tls_err = buf;
+  return code;
+}
+
+extern "C" const char* fr_last_error(const fr_engine* e) { return e ? e->err.c_str() : g_tls_err.c_str(); }
+
+extern "C" fr_status fr_model_builtin(const char* name, fr_model_desc* out) {
+  if (!name || !out) return fr_fail(nullptr, FR_ERR_INVALID, "fr_model_builtin: null argument");
+  for (const fr_builtin_model& m : k_builtin_models)
+    if (strcmp(m.name, name) == 0) {
+      out->name = m.name;
+      out->n_tables = m.n_tables;
+      out->tables = m.tables;
+      out->n_segments = m.n_segments;
+      out->segments = m.segments;
+      out->concat_floats = m.concat_floats;
+      for (int k = 0; k < 4; k++) out->hidden[k] = m.hidden[k];
+      out->mlp_mode = FR_MLP_BIAS_RELU_SIGMOID;
+      out->precision = FR_PREC_TF32;
+      out->max_batch = 16384;
+      return FR_OK;
+    }
+  return fr_fail(nullptr, FR_ERR_INVALID, "fr_model_builtin: unknown model '%s' (small|medium|large_half|large)", name);
+}
+
+// ---------------------------------------------------------------------------
+static fr_status validate_desc(const fr_model_desc* d) {
+  if (!d || !d->tables || !d->segments) return fr_fail(nullptr, FR_ERR_INVALID, "fr_create: null descriptor");
+  if (d->n_tables <= 0 || d->n_segments <= 0) return fr_fail(nullptr, FR_ERR_INVALID, "fr_create: empty model");
+  if (d->concat_floats <= 0 || d->concat_floats % 16)
+    return fr_fail(nullptr, FR_ERR_INVALID, "fr_create: concat_floats=%d must be a positive multiple of 16 (one 512-bit "
+                   "network word, constants.hpp:9)", d->concat_floats);
+  if (d->max_batch <= 0) return fr_fail(nullptr, FR_ERR_INVALID, "fr_create: max_batch must be > 0");
+  for (int t = 0; t < d->n_tables; t++) {
+    const fr_table_desc& td = d->tables[t];
+    if (td.dim <= 0 || td.dim % 4) return fr_fail(nullptr, FR_ERR_INVALID, "table %d: dim=%d must be a multiple of 4 "
+                                                  "floats (one 128-bit axi word)", t, td.dim);
+    if (td.rows <= 0) return fr_fail(nullptr, FR_ERR_INVALID, "table %d: rows must be > 0", t);
+  }
+  for (int s = 0; s < d->n_segments; s++) {
+    const fr_segment_desc& sg = d->segments[s];
+    if (sg.table < 0 || sg.table >= d->n_tables) return fr_fail(nullptr, FR_ERR_INVALID, "segment %d: bad table", s);
+    if (sg.len <= 0 || sg.len % 4 || sg.col % 4 || sg.dst % 4 || sg.col < 0 || sg.dst < 0 ||
+        sg.col + sg.len > d->tables[sg.table].dim || sg.dst + sg.len > d->concat_floats)
+      return fr_fail(nullptr, FR_ERR_INVALID, "segment %d: (dst=%d col=%d len=%d) not 4-float aligned or out of range", s,
+                     sg.dst, sg.col, sg.len);
+  }
+  if (d->hidden[3] != 1) return fr_fail(nullptr, FR_ERR_UNSUPPORTED, "output layer must be 1 wide (OUTPUT_SIZE)");
+  for (int k = 0; k < 3; k++)
+    if (d->hidden[k] <= 0 || d->hidden[k] % 128)
+      return fr_fail(nullptr, FR_ERR_UNSUPPORTED, "hidden[%d]=%d must be a multiple of 128", k, d->hidden[k]);
+  return FR_OK;
+}
+
+static fr_status alloc_stream(fr_engine* e, fr_stream_s** out) {
+  fr_stream_s* s = new fr_stream_s();
+  const size_t mb = (size_t)e->max_batch;
+  FR_CUDA(e, cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  FR_CUDA(e, cudaMalloc(&s->d_idx, mb * e->tables.size() * sizeof(int32_t)));
+  FR_CUDA(e, cudaMalloc(&s->d_x, mb * e->D * sizeof(float)));
+  for (int k = 0; k < 3; k++) FR_CUDA(e, cudaMalloc(&s->d_h[k], mb * e->dims[k + 1] * sizeof(float)));
+  FR_CUDA(e, cudaMalloc(&s->d_scores, mb * sizeof(float)));
+  FR_CUDA(e, cudaEventCreate(&s->ev[0]));
+  FR_CUDA(e, cudaEventCreate(&s->ev[1]));
+  *out = s;
+  return FR_OK;
+}
+
+static void free_stream(fr_stream_s* s) {
+  if (!s) return;
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  cudaFree(s->d_idx);
+  cudaFree(s->d_x);
+  for (int k = 0; k < 3; k++) cudaFree(s->d_h[k]);
+  cudaFree(s->d_scores);
+  if (s->ev[0]) cudaEventDestroy(s->ev[0]);
+  if (s->ev[1]) cudaEventDestroy(s->ev[1]);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+extern "C" fr_status fr_create(const fr_model_desc* desc, int n_gpus, const int* device_ids, fr_engine** out) {
+  if (!out) return fr_fail(nullptr, FR_ERR_INVALID, "fr_create: out is null");
+  *out = nullptr;
+  fr_status st = validate_desc(desc);
+  if (st != FR_OK) return st;
+  if (n_gpus != 1 || !device_ids)
+    return fr_fail(nullptr, FR_ERR_INVALID, "fr_create: one engine drives one GPU (n_gpus must be 1); shard across "
+                   "processes with fr_shard_init");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fr_fail(nullptr, FR_ERR_CUDA, "fr_create: no CUDA device (%s); there is no CPU fallback",
+                   ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0");
+  const int dev = device_ids[0];
+  if (dev < 0 || dev >= ndev) return fr_fail(nullptr, FR_ERR_INVALID, "fr_create: device %d of %d", dev, ndev);
+  cudaDeviceProp prop;
+  if ((ce = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess)
+    return fr_fail(nullptr, FR_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(ce));
+  if (prop.major != 10)
+    return fr_fail(nullptr, FR_ERR_CUDA, "fr_create: device %d is sm_%d%d; this library is built for sm_100a only", dev,
+                   prop.major, prop.minor);
+  if ((ce = cudaSetDevice(dev)) != cudaSuccess)
+    return fr_fail(nullptr, FR_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(ce));
+
+  fr_engine* e = new fr_engine();
+  e->device = dev;
+  e->sm_count = prop.multiProcessorCount;
+  e->name = desc->name ? desc->name : "custom";
+  e->tdesc.assign(desc->tables, desc->tables + desc->n_tables);
+  e->segs.assign(desc->segments, desc->segments + desc->n_segments);
+  e->D = desc->concat_floats;
+  e->dims[0] = e->D;
+  for (int k = 0; k < 4; k++) e->dims[k + 1] = desc->hidden[k];
+  e->mlp_mode = desc->mlp_mode;
+  e->precision = desc->precision;
+  e->max_batch = desc->max_batch;
+  e->tables.resize(desc->n_tables);
+  for (int t = 0; t < desc->n_tables; t++) {
+    e->tables[t].rows = desc->tables[t].rows;
+    e->tables[t].dim = desc->tables[t].dim;
+    e->tables[t].tier = desc->tables[t].tier;
+  }
+  st = alloc_stream(e, &e->default_stream);
+  if (st != FR_OK) {
+    g_tls_err = e->err;
+    fr_destroy(e);
+    return st;
+  }
+  *out = e;
+  return FR_OK;
+}
+
+extern "C" void fr_destroy(fr_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  frtc_destroy(e);
+  for (fr_stream_s* s : e->streams) free_stream(s);
+  free_stream(e->default_stream);
+  for (FrTable& t : e->tables) cudaFree(t.d);
+  for (int k = 0; k < FR_MAX_LAYERS; k++) {
+    cudaFree(e->d_W[k]);
+    cudaFree(e->d_Wt[k]);
+    cudaFree(e->d_bias[k]);
+  }
+  cudaFree(e->d_chunks);
+  cudaFree(e->d_owned_ids);
+  cudaFree(e->d_repl_ids);
+  for (int r = 0; r < (int)e->peers.size(); r++)
+    if (e->peers[r].ipc && e->peers[r].concat) cudaIpcCloseMemHandle(e->peers[r].concat);
+  cudaFree(e->d_peer_ptrs);
+  cudaFree(e->d_xchg);
+  delete e;
+}
+
+// ---------------------------------------------------------------------------
+static fr_status check_table(fr_engine* e, int t) {
+  if (!e) return fr_fail(nullptr, FR_ERR_INVALID, "null engine");
+  if (t < 0 || t >= (int)e->tables.size()) return fr_fail(e, FR_ERR_INVALID, "table id %d out of range", t);
+  return FR_OK;
+}
+
+static fr_status ensure_table_mem(fr_engine* e, int t) {
+  FrTable& tb = e->tables[t];
+  if (tb.d) return FR_OK;
+  FR_CUDA(e, cudaSetDevice(e->device));
+  FR_CUDA(e, cudaMalloc(&tb.d, (size_t)tb.rows * tb.dim * sizeof(float)));
+  e->chunks_dirty = true;
+  return FR_OK;
+}
+
+extern "C" fr_status fr_set_table_rows(fr_engine* e, int table_id, int64_t rows) {
+  fr_status st = check_table(e, table_id);
+  if (st != FR_OK) return st;
+  if (rows <= 0) return fr_fail(e, FR_ERR_INVALID, "rows must be > 0");
+  if (e->tables[table_id].d) return fr_fail(e, FR_ERR_STATE, "table %d already resident; set rows before loading", table_id);
+  e->tables[table_id].rows = rows;
+  return FR_OK;
+}
+
+extern "C" fr_status fr_load_table(fr_engine* e, int table_id, const float* host_rows, int64_t rows, int dim) {
+  fr_status st = check_table(e, table_id);
+  if (st != FR_OK) return st;
+  FrTable& tb = e->tables[table_id];
+  if (!host_rows) return fr_fail(e, FR_ERR_INVALID, "fr_load_table: null rows");
+  if (dim != tb.dim) return fr_fail(e, FR_ERR_INVALID, "table %d: dim %d given, catalogue says %d", table_id, dim, tb.dim);
+  if (!tb.resident) return FR_OK;
+  if (tb.d && rows != tb.rows) return fr_fail(e, FR_ERR_STATE, "table %d: resident with %lld rows", table_id, (long long)tb.rows);
+  if (rows <= 0) return fr_fail(e, FR_ERR_INVALID, "rows must be > 0");
+  tb.rows = rows;
+  if ((st = ensure_table_mem(e, table_id)) != FR_OK) return st;
+  FR_CUDA(e, cudaMemcpy(tb.d, host_rows, (size_t)rows * dim * sizeof(float), cudaMemcpyHostToDevice));
+  tb.loaded = true;
+  return FR_OK;
+}
+
+extern "C" fr_status fr_fill_table_reference(fr_engine* e, int table_id, int64_t debug_rows) {
+  fr_status st = check_table(e, table_id);
+  if (st != FR_OK) return st;
+  FrTable& tb = e->tables[table_id];
+  if (!tb.resident) return FR_OK;
+  if ((st = ensure_table_mem(e, table_id)) != FR_OK) return st;
+  if ((st = frk_fill_reference(e, tb.d, tb.rows, tb.dim, debug_rows, e->default_stream->stream)) != FR_OK) return st;
+  FR_CUDA(e, cudaStreamSynchronize(e->default_stream->stream));
+  tb.loaded = true;
+  return FR_OK;
+}
+
+extern "C" fr_status fr_fill_table_hash(fr_engine* e, int table_id, uint32_t seed) {
+  fr_status st = check_table(e, table_id);
+  if (st != FR_OK) return st;
+  FrTable& tb = e->tables[table_id];
+  if (!tb.resident) return FR_OK;
+  if ((st = ensure_table_mem(e, table_id)) != FR_OK) return st;
+  if ((st = frk_fill_hash(e, tb.d, seed, table_id, tb.rows, tb.dim, e->default_stream->stream)) != FR_OK) return st;
+  FR_CUDA(e, cudaStreamSynchronize(e->default_stream->stream));
+  tb.loaded = true;
+  return FR_OK;
+}
+
+extern "C" fr_status fr_read_table(fr_engine* e, int table_id, int64_t first_row, int64_t n_rows, float* host_out) {
+  fr_status st = check_table(e, table_id);
+  if (st != FR_OK) return st;
+  FrTable& tb = e->tables[table_id];
+  if (!tb.d || !tb.loaded) return fr_fail(e, FR_ERR_STATE, "table %d not loaded", table_id);
+  if (first_row < 0 || n_rows < 0 || first_row + n_rows > tb.rows) return fr_fail(e, FR_ERR_INVALID, "row range");
+  FR_CUDA(e, cudaMemcpy(host_out, tb.d + first_row * tb.dim, (size_t)n_rows * tb.dim * sizeof(float),
+                        cudaMemcpyDeviceToHost));
+  return FR_OK;
+}
+
+extern "C" fr_status fr_load_mlp(fr_engine* e, int layer, const float* W, const float* bias) {
+  if (!e) return fr_fail(nullptr, FR_ERR_INVALID, "null engine");
+  if (layer < 0 || layer >= FR_MAX_LAYERS) return fr_fail(e, FR_ERR_INVALID, "layer %d out of range", layer);
+  if (!W) return fr_fail(e, FR_ERR_INVALID, "fr_load_mlp: null weights");
+  const int in = e->dims[layer], out = e->dims[layer + 1];
+  const size_t nw = (size_t)in * out;
+  FR_CUDA(e, cudaSetDevice(e->device));
+  if (!e->d_W[layer]) FR_CUDA(e, cudaMalloc(&e->d_W[layer], nw * sizeof(float)));
+  if (!e->d_Wt[layer]) FR_CUDA(e, cudaMalloc(&e->d_Wt[layer], nw * sizeof(float)));
+  if (!e->d_bias[layer]) FR_CUDA(e, cudaMalloc(&e->d_bias[layer], (size_t)out * sizeof(float)));
+  FR_CUDA(e, cudaMemcpy(e->d_W[layer], W, nw * sizeof(float), cudaMemcpyHostToDevice));
+  if (bias) FR_CUDA(e, cudaMemcpy(e->d_bias[layer], bias, (size_t)out * sizeof(float), cudaMemcpyHostToDevice));
+  else FR_CUDA(e, cudaMemset(e->d_bias[layer], 0, (size_t)out * sizeof(float)));
+  fr_status st = frk_transpose_round_tf32(e, e->d_W[layer], in, out, e->d_Wt[layer], e->default_stream->stream);
+  if (st != FR_OK) return st;
+  FR_CUDA(e, cudaStreamSynchronize(e->default_stream->stream));
+  e->layer_loaded[layer] = true;
+  return FR_OK;
+}
+
+extern "C" fr_status fr_set_mlp_mode(fr_engine* e, int mode) {
+  if (!e) return fr_fail(nullptr, FR_ERR_INVALID, "null engine");
+  if (mode != FR_MLP_LINEAR && mode != FR_MLP_BIAS_RELU_SIGMOID) return fr_fail(e, FR_ERR_INVALID, "bad mlp_mode %d", mode);
+  e->mlp_mode = mode;
+  return FR_OK;
+}
+
+extern "C" fr_status fr_set_precision(fr_engine* e, int p) {
+  if (!e) return fr_fail(nullptr, FR_ERR_INVALID, "null engine");
+  if (p != FR_PREC_TF32 && p != FR_PREC_FP32) return fr_fail(e, FR_ERR_INVALID, "bad precision %d", p);
+  e->precision = p;
+  return FR_OK;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" fr_status fr_stream_create(fr_engine* e, fr_stream* out) {
+  if (!e || !out) return fr_fail(e, FR_ERR_INVALID, "fr_stream_create: null argument");
+  FR_CUDA(e, cudaSetDevice(e->device));
+  fr_stream_s* s = nullptr;
+  fr_status st = alloc_stream(e, &s);
+  if (st != FR_OK) return st;
+  std::lock_guard<std::mutex> g(e->mu);
+  e->streams.push_back(s);
+  *out = s;
+  return FR_OK;
+}
+
+extern "C" void fr_stream_destroy(fr_engine* e, fr_stream s) {
+  if (!e || !s) return;
+  {
+    std::lock_guard<std::mutex> g(e->mu);
+    for (size_t i = 0; i < e->streams.size(); i++)
+      if (e->streams[i] == s) { e->streams.erase(e->streams.begin() + i); break; }
+  }
+  cudaSetDevice(e->device);
+  free_stream(s);
+}
+
+extern "C" void* fr_stream_cuda(fr_stream s) { return s ? (void*)s->stream : nullptr; }
+
+static bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static fr_status prep(fr_engine* e, fr_stream* s, int B, bool need_tables, bool need_mlp) {
+  if (!e) return fr_fail(nullptr, FR_ERR_INVALID, "null engine");
+  if (B < 0 || B > e->max_batch) return fr_fail(e, FR_ERR_INVALID, "B=%d outside [0, max_batch=%d]", B, e->max_batch);
+  if (!*s) *s = e->default_stream;
+  FR_CUDA(e, cudaSetDevice(e->device));
+  if (need_tables) {
+    for (size_t t = 0; t < e->tables.size(); t++)
+      if (e->tables[t].resident && !e->tables[t].loaded)
+        return fr_fail(e, FR_ERR_STATE, "table %d not loaded (fr_load_table / fr_fill_table_*)", (int)t);
+    if (e->chunks_dirty) {
+      std::lock_guard<std::mutex> g(e->mu);
+      if (e->chunks_dirty) {
+        fr_status st = frk_upload_chunks(e);
+        if (st != FR_OK) return st;
+      }
+    }
+  }
+  if (need_mlp) {
+    for (int k = 0; k < FR_MAX_LAYERS; k++)
+      if (!e->layer_loaded[k]) return fr_fail(e, FR_ERR_STATE, "MLP layer %d not loaded (fr_load_mlp)", k);
+    if (e->precision == FR_PREC_TF32) {
+      fr_status st = frtc_prepare(e);
+      if (st != FR_OK) return st;
+    }
+  }
+  return FR_OK;
+}
+
+static fr_status stage_idx(fr_engine* e, fr_stream_s* s, const int32_t* idx, int B, const int32_t** d_idx) {
+  if (!idx && B > 0) return fr_fail(e, FR_ERR_INVALID, "null idx");
+  if (B == 0 || is_device_ptr(idx)) {
+    *d_idx = idx;
+    return FR_OK;
+  }
+  FR_CUDA(e, cudaMemcpyAsync(s->d_idx, idx, (size_t)B * e->tables.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
+                             s->stream));
+  *d_idx = s->d_idx;
+  return FR_OK;
+}
+
+// Launch `step` of the MLP chain on a worker stream (cuda_server.c:468-491).  TF32: 3 launches
+// (layer 3 carries the output layer); FP32: 4 launches.  Returns the step's output buffer in *out.
+static int mlp_steps(const fr_engine* e) { return e->precision == FR_PREC_TF32 ? 3 : 4; }
+
+static fr_status run_mlp_step(fr_engine* e, fr_stream_s* s, int step, const float* in, int B, float* d_scores,
+                              const float** out) {
+  const bool act = (e->mlp_mode == FR_MLP_BIAS_RELU_SIGMOID);
+  if (e->precision == FR_PREC_TF32) {
+    *out = step < 2 ? s->d_h[step] : d_scores;
+    return frtc_layer(e, s, step, in, B, d_scores);
+  }
+  if (step < 3) {
+    *out = s->d_h[step];
+    return frk_sgemm_bias_act(e, in, e->d_W[step], act ? e->d_bias[step] : nullptr, s->d_h[step], B, e->dims[step],
+                              e->dims[step + 1], act, s->stream);
+  }
+  *out = d_scores;
+  return frk_final_dot(e, in, e->d_W[3], act ? e->d_bias[3] : nullptr, d_scores, B, e->dims[3], act, s->stream);
+}
+
+static fr_status run_mlp(fr_engine* e, fr_stream_s* s, const float* d_x, int B, float* d_scores) {
+  if (B == 0) return FR_OK;
+  const float* in = d_x;
+  for (int k = 0; k < mlp_steps(e); k++) {
+    const float* out = nullptr;
+    fr_status st = run_mlp_step(e, s, k, in, B, d_scores, &out);
+    if (st != FR_OK) return st;
+    in = out;
+  }
+  return FR_OK;
+}
+
+static fr_status emit_scores(fr_engine* e, fr_stream_s* s, float* scores, int B, float* d_scores) {
+  if (d_scores != scores && B > 0)
+    FR_CUDA(e, cudaMemcpyAsync(scores, d_scores, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+  return FR_OK;
+}
+
+extern "C" fr_status fr_infer(fr_engine* e, const int32_t* idx, int B, float* scores, fr_stream s) {
+  fr_status st = prep(e, &s, B, true, true);
+  if (st != FR_OK) return st;
+  if (B > 0 && !scores) return fr_fail(e, FR_ERR_INVALID, "null scores");
+  const int32_t* d_idx = nullptr;
+  if ((st = stage_idx(e, s, idx, B, &d_idx)) != FR_OK) return st;
+  if ((st = frk_gather(e, d_idx, B, s->d_x, e->precision == FR_PREC_TF32, s->stream)) != FR_OK) return st;
+  float* d_scores = (B > 0 && is_device_ptr(scores)) ? scores : s->d_scores;
+  if ((st = run_mlp(e, s, s->d_x, B, d_scores)) != FR_OK) return st;
+  return emit_scores(e, s, scores, B, d_scores);
+}
+
+extern "C" fr_status fr_gather_only(fr_engine* e, const int32_t* idx, int B, float* concat, fr_stream s) {
+  fr_status st = prep(e, &s, B, true, false);
+  if (st != FR_OK) return st;
+  if (B > 0 && !concat) return fr_fail(e, FR_ERR_INVALID, "null concat");
+  const int32_t* d_idx = nullptr;
+  if ((st = stage_idx(e, s, idx, B, &d_idx)) != FR_OK) return st;
+  if (B == 0) return FR_OK;
+  const bool dev = is_device_ptr(concat);
+  float* d_out = dev ? concat : s->d_x;
+  if ((st = frk_gather(e, d_idx, B, d_out, false, s->stream)) != FR_OK) return st;
+  if (!dev)
+    FR_CUDA(e, cudaMemcpyAsync(concat, d_out, (size_t)B * e->D * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+  return FR_OK;
+}
+
+extern "C" fr_status fr_mlp_only(fr_engine* e, const float* x, int B, float* scores, fr_stream s) {
+  fr_status st = prep(e, &s, B, false, true);
+  if (st != FR_OK) return st;
+  if (B == 0) return FR_OK;
+  if (!x || !scores) return fr_fail(e, FR_ERR_INVALID, "null x/scores");
+  const float* d_x = x;
+  if (!is_device_ptr(x)) {
+    FR_CUDA(e, cudaMemcpyAsync(s->d_x, x, (size_t)B * e->D * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    d_x = s->d_x;
+  }
+  float* d_scores = is_device_ptr(scores) ? scores : s->d_scores;
+  if ((st = run_mlp(e, s, d_x, B, d_scores)) != FR_OK) return st;
+  return emit_scores(e, s, scores, B, d_scores);
+}
+
+extern "C" fr_status fr_layer_only(fr_engine* e, int k, const float* x, int B, float* y, fr_stream s) {
+  fr_status st = prep(e, &s, B, false, true);
+  if (st != FR_OK) return st;
+  if (k < 0 || k >= mlp_steps(e)) return fr_fail(e, FR_ERR_INVALID, "fr_layer_only: step %d of %d", k, mlp_steps(e));
+  if (B == 0) return FR_OK;
+  if (!x || !y) return fr_fail(e, FR_ERR_INVALID, "null x/y");
+  const bool last = (k == mlp_steps(e) - 1);
+  const int in_w = (e->precision == FR_PREC_FP32 && k == 3) ? e->dims[3] : e->dims[k];
+  // stage the input in the buffer the previous step would have written
+  float* d_in = (k == 0) ? s->d_x : s->d_h[k - 1];
+  FR_CUDA(e, cudaMemcpyAsync(d_in, x, (size_t)B * in_w * sizeof(float), cudaMemcpyDefault, s->stream));
+  const float* out = nullptr;
+  if ((st = run_mlp_step(e, s, k, d_in, B, s->d_scores, &out)) != FR_OK) return st;
+  const size_t n = last ? (size_t)B : (size_t)B * e->dims[k + 1];
+  FR_CUDA(e, cudaMemcpyAsync(y, out, n * sizeof(float), cudaMemcpyDefault, s->stream));
+  return FR_OK;
+}
+
+extern "C" fr_status fr_sync(fr_engine* e, fr_stream s) {
+  if (!e) return fr_fail(nullptr, FR_ERR_INVALID, "null engine");
+  if (!s) s = e->default_stream;
+  FR_CUDA(e, cudaStreamSynchronize(s->stream));
+  return FR_OK;
+}
+
+extern "C" int64_t fr_launch_count(const fr_engine* e) { return e ? e->launches.load() : 0; }
+
+extern "C" int64_t fr_table_bytes(const fr_engine* e) {
+  if (!e) return 0;
+  int64_t n = 0;
+  for (const FrTable& t : e->tables)
+    if (t.d) n += t.rows * t.dim * (int64_t)sizeof(float);
+  return n;
+}
+
+extern "C" fr_status fr_mark(fr_engine* e, fr_stream s, int which) {
+  if (!e || which < 0 || which > 1) return fr_fail(e, FR_ERR_INVALID, "fr_mark: bad argument");
+  if (!s) s = e->default_stream;
+  FR_CUDA(e, cudaEventRecord(s->ev[which], s->stream));
+  return FR_OK;
+}
+
+extern "C" fr_status fr_elapsed_ms(fr_engine* e, fr_stream s, float* ms) {
+  if (!e || !ms) return fr_fail(e, FR_ERR_INVALID, "fr_elapsed_ms: bad argument");
+  if (!s) s = e->default_stream;
+  FR_CUDA(e, cudaEventSynchronize(s->ev[1]));
+  FR_CUDA(e, cudaEventElapsedTime(ms, s->ev[0], s->ev[1]));
+  return FR_OK;
+}
+
+extern "C" fr_status fr_time_kernels(fr_engine* e, const int32_t* idx, int B, int reps, fr_stream s, float* ms5) {
+  fr_status st = prep(e, &s, B, true, true);
+  if (st != FR_OK) return st;
+  if (!ms5 || reps <= 0 || B <= 0) return fr_fail(e, FR_ERR_INVALID, "fr_time_kernels: bad argument");
+  const int32_t* d_idx = nullptr;
+  if ((st = stage_idx(e, s, idx, B, &d_idx)) != FR_OK) return st;
+  for (int i = 0; i < 5; i++) ms5[i] = 0.f;
+  cudaEvent_t e0 = s->ev[0], e1 = s->ev[1];
+  const bool round = e->precision == FR_PREC_TF32;
+  // every kernel is timed alone, back to back `reps` times, events on its own stream
+  for (int pass = 0; pass < 2; pass++) {  // pass 0 = warm-up
+    FR_CUDA(e, cudaEventRecord(e0, s->stream));
+    for (int r = 0; r < reps; r++)
+      if ((st = frk_gather(e, d_idx, B, s->d_x, round, s->stream)) != FR_OK) return st;
+    FR_CUDA(e, cudaEventRecord(e1, s->stream));
+    FR_CUDA(e, cudaEventSynchronize(e1));
+    FR_CUDA(e, cudaEventElapsedTime(&ms5[0], e0, e1));
+    const float* in = s->d_x;
+    for (int k = 0; k < mlp_steps(e); k++) {
+      const float* out = nullptr;
+      FR_CUDA(e, cudaEventRecord(e0, s->stream));
+      for (int r = 0; r < reps; r++)
+        if ((st = run_mlp_step(e, s, k, in, B, s->d_scores, &out)) != FR_OK) return st;
+      FR_CUDA(e, cudaEventRecord(e1, s->stream));
+      FR_CUDA(e, cudaEventSynchronize(e1));
+      FR_CUDA(e, cudaEventElapsedTime(&ms5[1 + k], e0, e1));
+      in = out;
+    }
+  }
+  for (int i = 0; i < 5; i++) ms5[i] /= (float)reps;
+  return FR_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Sharding: table-wise model parallel, push all-to-all over NVLink.
+extern "C" fr_status fr_shard_init(fr_engine* e, int rank, int world, const int* owner) {
+  if (!e) return fr_fail(nullptr, FR_ERR_INVALID, "null engine");
+  if (world < 1 || rank < 0 || rank >= world || !owner) return fr_fail(e, FR_ERR_INVALID, "fr_shard_init: rank/world/owner");
+  for (const FrTable& t : e->tables)
+    if (t.d) return fr_fail(e, FR_ERR_STATE, "fr_shard_init must precede table loading");
+  if (e->max_batch % world) return fr_fail(e, FR_ERR_INVALID, "max_batch %d not divisible by world %d", e->max_batch, world);
+  e->rank = rank;
+  e->world = world;
+  e->owner.assign(owner, owner + e->tables.size());
+  for (size_t t = 0; t < e->tables.size(); t++) {
+    if (owner[t] < -1 || owner[t] >= world) return fr_fail(e, FR_ERR_INVALID, "owner[%d]=%d", (int)t, owner[t]);
+    e->tables[t].resident = (owner[t] == -1 || owner[t] == rank);
+  }
+  FR_CUDA(e, cudaSetDevice(e->device));
+  if (!e->d_xchg) FR_CUDA(e, cudaMalloc(&e->d_xchg, (size_t)(e->max_batch / world) * e->D * sizeof(float)));
+  e->peers.assign(world, FrPeer());
+  e->peers[rank].concat = e->d_xchg;
+  e->chunks_dirty = true;
+  return FR_OK;
+}
+
+static fr_status upload_peers(fr_engine* e) {
+  std::vector<float*> p(e->world);
+  for (int r = 0; r < e->world; r++) {
+    if (!e->peers[r].concat) return fr_fail(e, FR_ERR_STATE, "peer %d not attached", r);
+    p[r] = e->peers[r].concat;
+  }
+  if (!e->d_peer_ptrs) FR_CUDA(e, cudaMalloc(&e->d_peer_ptrs, sizeof(float*) * e->world));
+  FR_CUDA(e, cudaMemcpy(e->d_peer_ptrs, p.data(), sizeof(float*) * e->world, cudaMemcpyHostToDevice));
+  return FR_OK;
+}
+
+extern "C" fr_status fr_shard_export(fr_engine* e, void* handle64) {
+  if (!e || !handle64) return fr_fail(e, FR_ERR_INVALID, "fr_shard_export: null argument");
+  if (!e->d_xchg) return fr_fail(e, FR_ERR_STATE, "fr_shard_init first");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+  FR_CUDA(e, cudaSetDevice(e->device));
+  cudaIpcMemHandle_t h;
+  FR_CUDA(e, cudaIpcGetMemHandle(&h, e->d_xchg));
+  memcpy(handle64, &h, 64);
+  return FR_OK;
+}
+
+extern "C" fr_status fr_shard_import(fr_engine* e, const void* handles) {
+  if (!e || !handles) return fr_fail(e, FR_ERR_INVALID, "fr_shard_import: null argument");
+  if (!e->d_xchg) return fr_fail(e, FR_ERR_STATE, "fr_shard_init first");
+  FR_CUDA(e, cudaSetDevice(e->device));
+  for (int r = 0; r < e->world; r++) {
+    if (r == e->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + 64 * r, 64);
+    void* p = nullptr;
+    FR_CUDA(e, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    e->peers[r].concat = (float*)p;
+    e->peers[r].ipc = true;
+  }
+  return upload_peers(e);
+}
+
+extern "C" fr_status fr_shard_attach_local(fr_engine* e, fr_engine* const* peers) {
+  if (!e || !peers) return fr_fail(e, FR_ERR_INVALID, "fr_shard_attach_local: null argument");
+  if (!e->d_xchg) return fr_fail(e, FR_ERR_STATE, "fr_shard_init first");
+  FR_CUDA(e, cudaSetDevice(e->device));
+  for (int r = 0; r < e->world; r++) {
+    if (r == e->rank) continue;
+    if (!peers[r] || !peers[r]->d_xchg) return fr_fail(e, FR_ERR_STATE, "peer %d has no exchange buffer", r);
+    if (peers[r]->device != e->device) {
+      int can = 0;
+      FR_CUDA(e, cudaDeviceCanAccessPeer(&can, e->device, peers[r]->device));
+      if (!can) return fr_fail(e, FR_ERR_CUDA, "device %d cannot access peer %d", e->device, peers[r]->device);
+      cudaError_t ce = cudaDeviceEnablePeerAccess(peers[r]->device, 0);
+      if (ce != cudaSuccess && ce != cudaErrorPeerAccessAlreadyEnabled)
+        return fr_fail(e, FR_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(ce));
+      cudaGetLastError();
+    }
+    e->peers[r].concat = peers[r]->d_xchg;
+  }
+  return upload_peers(e);
+}
+
+extern "C" fr_status fr_shard_gather_push(fr_engine* e, const int32_t* idx, int B_global, fr_stream s) {
+  fr_status st = prep(e, &s, B_global, true, false);
+  if (st != FR_OK) return st;
+  if (!e->d_peer_ptrs) return fr_fail(e, FR_ERR_STATE, "exchange buffers not attached (fr_shard_import)");
+  if (B_global % e->world) return fr_fail(e, FR_ERR_INVALID, "B_global %d not divisible by world %d", B_global, e->world);
+  const int32_t* d_idx = nullptr;
+  if ((st = stage_idx(e, s, idx, B_global, &d_idx)) != FR_OK) return st;
+  if (B_global == 0) return FR_OK;
+  return frk_gather_push(e, d_idx, B_global, s->stream);
+}
+
+extern "C" fr_status fr_shard_mlp(fr_engine* e, int B_global, float* scores_local, fr_stream s) {
+  fr_status st = prep(e, &s, B_global, false, true);
+  if (st != FR_OK) return st;
+  if (!e->d_xchg) return fr_fail(e, FR_ERR_STATE, "fr_shard_init first");
+  const int Bl = B_global / e->world;
+  if (Bl == 0) return FR_OK;
+  if (!scores_local) return fr_fail(e, FR_ERR_INVALID, "null scores");
+  float* d_scores = is_device_ptr(scores_local) ? scores_local : s->d_scores;
+  if ((st = run_mlp(e, s, e->d_xchg, Bl, d_scores)) != FR_OK) return st;
+  return emit_scores(e, s, scores_local, Bl, d_scores);
+}
+
+extern "C" fr_status fr_shard_read_concat(fr_engine* e, int B_global, float* concat_local, fr_stream s) {
+  if (!e || !concat_local) return fr_fail(e, FR_ERR_INVALID, "fr_shard_read_concat: null argument");
+  if (!e->d_xchg) return fr_fail(e, FR_ERR_STATE, "fr_shard_init first");
+  if (!s) s = e->default_stream;
+  FR_CUDA(e, cudaSetDevice(e->device));
+  const int Bl = B_global / e->world;
+  FR_CUDA(e, cudaMemcpyAsync(concat_local, e->d_xchg, (size_t)Bl * e->D * sizeof(float), cudaMemcpyDefault, s->stream));
+  return FR_OK;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" int64_t fr_merge_index(int64_t iA, int64_t iB, int64_t rowsB) { return iA * rowsB + iB; }
+
+extern "C" fr_status fr_merge_tables(fr_engine* e, int a, int b, int dst) {
+  fr_status st;
+  if ((st = check_table(e, a)) != FR_OK || (st = check_table(e, b)) != FR_OK || (st = check_table(e, dst)) != FR_OK)
+    return st;
+  FrTable &A = e->tables[a], &B = e->tables[b], &M = e->tables[dst];
+  if (!A.loaded || !B.loaded) return fr_fail(e, FR_ERR_STATE, "merge sources not loaded");
+  if (M.dim != A.dim + B.dim || M.rows != A.rows * B.rows)
+    return fr_fail(e, FR_ERR_INVALID, "merged table %d must be (%lld rows, dim %d)", dst, (long long)(A.rows * B.rows),
+                   A.dim + B.dim);
+  if ((st = ensure_table_mem(e, dst)) != FR_OK) return st;
+  if ((st = frk_merge(e, A.d, A.rows, A.dim, B.d, B.rows, B.dim, M.d, e->default_stream->stream)) != FR_OK) return st;
+  FR_CUDA(e, cudaStreamSynchronize(e->default_stream->stream));
+  M.loaded = true;
+  return FR_OK;
+}

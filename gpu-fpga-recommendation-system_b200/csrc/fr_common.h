@@ -1,0 +1,119 @@
+// fr_common.h -- internal engine structures shared by the CUDA translation units.
+// Nothing here is part of the ABI (include/fleetrec.h is).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/fleetrec.h"
+
+#define FR_MAX_LAYERS 4
+
+// One 16-byte piece of an item's concat vector: out4[b][c] = base[idx[b][table]*stride4 + col4].
+struct FrChunk {
+  const float4* base;  // table base (device), NULL when the table is not resident on this rank
+  int table;           // column of idx[][] to read
+  int stride4;         // row pitch in float4 (= dim/4)
+  int col4;            // float4 offset inside the row
+  int pad_;
+};
+
+struct FrTable {
+  float* d = nullptr;
+  int64_t rows = 0;
+  int dim = 0;
+  int tier = 0;
+  bool resident = true;  // false: owned by another rank
+  bool loaded = false;
+};
+
+struct fr_stream_s {
+  cudaStream_t stream = nullptr;
+  int32_t* d_idx = nullptr;   // [max_batch][T]
+  float* d_x = nullptr;       // [max_batch][D]      concat activations
+  float* d_h[3] = {nullptr, nullptr, nullptr};  // [max_batch][hidden k]
+  float* d_scores = nullptr;  // [max_batch]
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+};
+
+struct FrPeer {
+  float* concat = nullptr;  // peer's exchange buffer (mapped into this process)
+  bool ipc = false;
+};
+
+struct fr_engine {
+  int device = 0;
+  int sm_count = 0;
+  std::string name;
+  std::vector<fr_table_desc> tdesc;
+  std::vector<fr_segment_desc> segs;
+  int D = 0;  // concat floats
+  int dims[FR_MAX_LAYERS + 1] = {0, 0, 0, 0, 0};
+  int mlp_mode = FR_MLP_BIAS_RELU_SIGMOID;
+  int precision = FR_PREC_TF32;
+  int max_batch = 0;
+
+  std::vector<FrTable> tables;
+  FrChunk* d_chunks = nullptr;  // [D/4]
+  bool chunks_dirty = true;
+
+  float* d_W[FR_MAX_LAYERS] = {nullptr, nullptr, nullptr, nullptr};    // [in][out] fp32 (reference layout)
+  float* d_Wt[FR_MAX_LAYERS] = {nullptr, nullptr, nullptr, nullptr};   // [out][in] tf32-rounded (tcgen05 B operand)
+  float* d_bias[FR_MAX_LAYERS] = {nullptr, nullptr, nullptr, nullptr};
+  bool layer_loaded[FR_MAX_LAYERS] = {false, false, false, false};
+  void* tc_state = nullptr;  // tensor maps etc., owned by fr_mlp_tc.cu
+
+  fr_stream_s* default_stream = nullptr;
+  std::vector<fr_stream_s*> streams;
+  std::mutex mu;
+
+  // sharding
+  int rank = 0, world = 1;
+  std::vector<int> owner;        // [T], -1 replicated
+  float* d_xchg = nullptr;       // [max_batch/world... sized max_batch][D] receive buffer
+  std::vector<FrPeer> peers;     // [world]
+  float** d_peer_ptrs = nullptr; // device copy of peers[].concat
+  int* d_owned_ids = nullptr;    // concat pieces this rank produces for every item
+  int n_owned = 0;
+  int* d_repl_ids = nullptr;     // pieces of replicated tables (local items only)
+  int n_repl = 0;
+  bool shard_lists_built = false;
+
+  std::atomic<int64_t> launches{0};
+  mutable std::string err;
+};
+
+fr_status fr_fail(const fr_engine* e, fr_status code, const char* fmt, ...);
+#define FR_CUDA(e, call)                                                                          \
+  do {                                                                                            \
+    cudaError_t err__ = (call);                                                                   \
+    if (err__ != cudaSuccess)                                                                     \
+      return fr_fail((e), err__ == cudaErrorMemoryAllocation ? FR_ERR_OOM : FR_ERR_CUDA,          \
+                     "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+  } while (0)
+
+// ---- kernels (each returns after enqueueing; bumps e->launches) -----------
+fr_status frk_upload_chunks(fr_engine* e);
+fr_status frk_gather(fr_engine* e, const int32_t* d_idx, int B, float* d_out, bool round_tf32, cudaStream_t st);
+fr_status frk_gather_push(fr_engine* e, const int32_t* d_idx, int B_global, cudaStream_t st);
+fr_status frk_fill_reference(fr_engine* e, float* d, int64_t rows, int dim, int64_t debug_rows, cudaStream_t st);
+fr_status frk_fill_hash(fr_engine* e, float* d, uint32_t seed, int table, int64_t rows, int dim, cudaStream_t st);
+fr_status frk_merge(fr_engine* e, const float* A, int64_t rowsA, int dimA, const float* B, int64_t rowsB, int dimB,
+                    float* M, cudaStream_t st);
+fr_status frk_transpose_round_tf32(fr_engine* e, const float* W, int in, int out, float* Wt, cudaStream_t st);
+
+// FP32 SIMT path: Y[B][N] = act(X[B][K] . W[K][N] + bias)
+fr_status frk_sgemm_bias_act(fr_engine* e, const float* X, const float* W, const float* bias, float* Y, int B, int K,
+                             int N, bool relu, cudaStream_t st);
+// final 1-wide layer: scores[b] = (sigmoid?)(dot(H[b][0..K), w) + bias0)
+fr_status frk_final_dot(fr_engine* e, const float* H, const float* w, const float* bias, float* scores, int B, int K,
+                        bool sigmoid, cudaStream_t st);
+
+// TF32 tcgen05 path (fr_mlp_tc.cu)
+fr_status frtc_prepare(fr_engine* e);                // builds tensor maps for weights; idempotent
+void frtc_destroy(fr_engine* e);
+fr_status frtc_layer(fr_engine* e, fr_stream_s* s, int k, const float* in, int B, float* d_scores);

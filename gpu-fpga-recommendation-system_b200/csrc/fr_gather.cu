@@ -1,0 +1,282 @@
+// fr_gather.cu -- multi-table embedding lookup + concat (rows L1-L4 of SURVEY.md 8a).
+//
+// Replaces, on one B200, what the FPGA does with 30 HBM/DDR AXI masters and 17-44
+// on-chip tables: load_single_embedding_N_tables (embedding_47_krnl.cpp:916-935,
+// embedding_98_krnl.cpp:1016-1041, embedding_377_krnl.cpp:1180-1291) followed by the
+// group_* / gather_*_embedding_streams re-packers (47: 964-1217).  The concat order
+// is data (FrChunk list built from fr_segment_desc), not code.
+//
+// Mapping: one thread owns one 16-byte piece (float4 = one reference `axi_t`) of the
+// concat vector and walks ITEMS items with it, so the piece descriptor lives in
+// registers, the ITEMS index loads are issued back to back, then the ITEMS row
+// loads (128-bit, read-only path, no L1 allocation), then the ITEMS stores.
+// Consecutive threads own consecutive pieces: stores are fully coalesced and
+// lanes that share a table read one contiguous row.  HBM-bound integer/byte work:
+// no tensor cores, no shared memory (nothing is reused).
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "fr_common.h"
+
+namespace {
+
+constexpr int kItems = 4;  // items per thread (independent loads in flight)
+
+__device__ __forceinline__ float4 ld_row16(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// PUSH = false: out4 is the local [B][C] buffer.
+// PUSH = true : peer_out[r] is rank r's exchange buffer; item b lands on rank
+//               b / items_per_rank at local row b % items_per_rank (NVLink peer stores).
+template <bool ROUND, bool PUSH>
+__global__ void __launch_bounds__(256) gather_concat_kernel(const FrChunk* __restrict__ chunks,
+                                                            const int* __restrict__ chunk_ids, int n_chunks,
+                                                            const int32_t* __restrict__ idx, int T, int b_begin,
+                                                            int b_end, float4* __restrict__ out4,
+                                                            float4* const* __restrict__ peer_out, int C,
+                                                            int items_per_rank) {
+  const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ci >= n_chunks) return;
+  const int c = chunk_ids ? chunk_ids[ci] : ci;
+  const FrChunk ch = chunks[c];
+  const int b0 = b_begin + (blockIdx.y * blockDim.y + threadIdx.y) * kItems;
+
+  int64_t row[kItems];
+#pragma unroll
+  for (int i = 0; i < kItems; i++) {
+    const int b = b0 + i;
+    row[i] = (b < b_end) ? (int64_t)__ldg(idx + (size_t)b * T + ch.table) : 0;
+  }
+  float4 v[kItems];
+#pragma unroll
+  for (int i = 0; i < kItems; i++)  // 64-bit addressing: 100 M rows x 128 B = 12.8 GB tables
+    v[i] = ld_row16(ch.base + row[i] * ch.stride4 + ch.col4);
+#pragma unroll
+  for (int i = 0; i < kItems; i++) {
+    const int b = b0 + i;
+    if (b >= b_end) break;
+    float4 o = v[i];
+    if (ROUND) {
+      o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+    }
+    if (PUSH) {
+      const int r = b / items_per_rank;
+      peer_out[r][(size_t)(b - r * items_per_rank) * C + c] = o;
+    } else {
+      out4[(size_t)b * C + c] = o;
+    }
+  }
+}
+
+__global__ void fill_reference_kernel(float4* __restrict__ t, int64_t n4, int dim4, int64_t filled_rows) {
+  const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / dim4;
+    t[i] = (r < filled_rows && (r & 1) == 0) ? one : zero;
+  }
+}
+
+__device__ __forceinline__ uint32_t hash_bits(uint32_t seed, uint32_t table, uint64_t row, uint32_t col) {
+  uint64_t z = row * 0x9E3779B97F4A7C15ull + ((uint64_t)table << 40) + ((uint64_t)col << 28) + seed;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  const uint32_t h = (uint32_t)(z >> 16);
+  const uint32_t expo = 118u + ((h >> 23) & 0xFFu) % 9u;
+  return (h & 0x80000000u) | (expo << 23) | (h & 0x007FFFFFu);
+}
+
+__global__ void fill_hash_kernel(uint32_t* __restrict__ t, int64_t n, int dim, uint32_t seed, uint32_t table) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    t[i] = hash_bits(seed, table, (uint64_t)(i / dim), (uint32_t)(i % dim));
+}
+
+__global__ void merge_kernel(const float4* __restrict__ A, int dimA4, const float4* __restrict__ B, int64_t rowsB,
+                             int dimB4, float4* __restrict__ M, int64_t n4) {
+  const int dm4 = dimA4 + dimB4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / dm4;
+    const int c = (int)(i - r * dm4);
+    const int64_t ia = r / rowsB, ib = r - ia * rowsB;
+    M[i] = (c < dimA4) ? A[ia * dimA4 + c] : B[ib * dimB4 + (c - dimA4)];
+  }
+}
+
+// Wt[o][i] = rna_tf32(W[i][o]); 32x32 smem tile transpose.
+__global__ void transpose_round_kernel(const float* __restrict__ W, int in, int out, float* __restrict__ Wt) {
+  __shared__ float tile[32][33];
+  const int i0 = blockIdx.y * 32, o0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = i0 + r, o = o0 + threadIdx.x;
+    tile[r][threadIdx.x] = (i < in && o < out) ? W[(size_t)i * out + o] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int o = o0 + r, i = i0 + threadIdx.x;
+    if (o < out && i < in) Wt[(size_t)o * in + i] = round_tf32(tile[threadIdx.x][r]);
+  }
+}
+
+int grid_for(int64_t n, int block, int sm_count) {
+  int64_t g = (n + block - 1) / block;
+  const int64_t cap = (int64_t)sm_count * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+template <bool ROUND, bool PUSH>
+void launch_gather(const fr_engine* e, const int* d_ids, int n_chunks, const int32_t* d_idx, int b_begin, int b_end,
+                   float4* out4, float4* const* peers, int items_per_rank, cudaStream_t st) {
+  const int C = e->D / 4;
+  int bx = (n_chunks + 31) / 32 * 32;
+  if (bx > 128) bx = 128;
+  const int by = 256 / bx;
+  const int n_items = b_end - b_begin;
+  dim3 block(bx, by);
+  dim3 grid((n_chunks + bx - 1) / bx, (n_items + by * kItems - 1) / (by * kItems));
+  gather_concat_kernel<ROUND, PUSH><<<grid, block, 0, st>>>(e->d_chunks, d_ids, n_chunks, d_idx, (int)e->tables.size(),
+                                                            b_begin, b_end, out4, peers, C, items_per_rank);
+}
+
+}  // namespace
+
+fr_status frk_upload_chunks(fr_engine* e) {
+  const int C = e->D / 4;
+  std::vector<FrChunk> h(C);
+  std::vector<char> covered(C, 0);
+  for (const fr_segment_desc& s : e->segs) {
+    const FrTable& t = e->tables[s.table];
+    for (int k = 0; k < s.len / 4; k++) {
+      FrChunk& c = h[s.dst / 4 + k];
+      c.base = reinterpret_cast<const float4*>(t.d);
+      c.table = s.table;
+      c.stride4 = t.dim / 4;
+      c.col4 = s.col / 4 + k;
+      c.pad_ = 0;
+      covered[s.dst / 4 + k] = 1;
+    }
+  }
+  for (int i = 0; i < C; i++)
+    if (!covered[i]) return fr_fail(e, FR_ERR_INVALID, "concat float %d is not covered by any segment", i * 4);
+  if (!e->d_chunks) FR_CUDA(e, cudaMalloc(&e->d_chunks, sizeof(FrChunk) * C));
+  FR_CUDA(e, cudaMemcpy(e->d_chunks, h.data(), sizeof(FrChunk) * C, cudaMemcpyHostToDevice));
+  e->chunks_dirty = false;
+  return FR_OK;
+}
+
+fr_status frk_gather(fr_engine* e, const int32_t* d_idx, int B, float* d_out, bool round_tf32, cudaStream_t st) {
+  if (B == 0) return FR_OK;
+  if (round_tf32)
+    launch_gather<true, false>(e, nullptr, e->D / 4, d_idx, 0, B, reinterpret_cast<float4*>(d_out), nullptr, 1, st);
+  else
+    launch_gather<false, false>(e, nullptr, e->D / 4, d_idx, 0, B, reinterpret_cast<float4*>(d_out), nullptr, 1, st);
+  e->launches++;
+  FR_CUDA(e, cudaGetLastError());
+  return FR_OK;
+}
+
+fr_status frk_fill_reference(fr_engine* e, float* d, int64_t rows, int dim, int64_t debug_rows, cudaStream_t st) {
+  // host.cpp:66-88: pairs (2i, 2i+1) for i < rows/2 (or < debug_rows/2 with DEBUG)
+  int64_t pairs = rows / 2;
+  if (debug_rows > 0 && debug_rows / 2 < pairs) pairs = debug_rows / 2;
+  const int64_t n4 = rows * dim / 4;
+  fill_reference_kernel<<<grid_for(n4, 256, e->sm_count), 256, 0, st>>>(reinterpret_cast<float4*>(d), n4, dim / 4,
+                                                                        pairs * 2);
+  e->launches++;
+  FR_CUDA(e, cudaGetLastError());
+  return FR_OK;
+}
+
+fr_status frk_fill_hash(fr_engine* e, float* d, uint32_t seed, int table, int64_t rows, int dim, cudaStream_t st) {
+  const int64_t n = rows * dim;
+  fill_hash_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(reinterpret_cast<uint32_t*>(d), n, dim, seed,
+                                                                  (uint32_t)table);
+  e->launches++;
+  FR_CUDA(e, cudaGetLastError());
+  return FR_OK;
+}
+
+fr_status frk_merge(fr_engine* e, const float* A, int64_t rowsA, int dimA, const float* B, int64_t rowsB, int dimB,
+                    float* M, cudaStream_t st) {
+  const int64_t n4 = rowsA * rowsB * (dimA + dimB) / 4;
+  merge_kernel<<<grid_for(n4, 256, e->sm_count), 256, 0, st>>>(reinterpret_cast<const float4*>(A), dimA / 4,
+                                                               reinterpret_cast<const float4*>(B), rowsB, dimB / 4,
+                                                               reinterpret_cast<float4*>(M), n4);
+  e->launches++;
+  FR_CUDA(e, cudaGetLastError());
+  return FR_OK;
+}
+
+fr_status frk_transpose_round_tf32(fr_engine* e, const float* W, int in, int out, float* Wt, cudaStream_t st) {
+  dim3 grid((out + 31) / 32, (in + 31) / 32), block(32, 8);
+  transpose_round_kernel<<<grid, block, 0, st>>>(W, in, out, Wt);
+  e->launches++;
+  FR_CUDA(e, cudaGetLastError());
+  return FR_OK;
+}
+
+// Sharded step, phase 1: owned tables for the GLOBAL batch are pushed
+// to the rank that owns each item with NVLink peer stores; replicated (on-chip
+// class) tables are gathered locally for this rank's items only.
+static fr_status build_shard_lists(fr_engine* e) {
+  std::vector<int> owned, repl;
+  const int C = e->D / 4;
+  std::vector<int> table_of(C, -1);
+  for (const fr_segment_desc& s : e->segs)
+    for (int k = 0; k < s.len / 4; k++) table_of[s.dst / 4 + k] = s.table;
+  for (int c = 0; c < C; c++) {
+    const int o = e->owner.empty() ? e->rank : e->owner[table_of[c]];
+    if (o < 0) repl.push_back(c);
+    else if (o == e->rank) owned.push_back(c);
+  }
+  e->n_owned = (int)owned.size();
+  e->n_repl = (int)repl.size();
+  if (e->n_owned) {
+    FR_CUDA(e, cudaMalloc(&e->d_owned_ids, sizeof(int) * owned.size()));
+    FR_CUDA(e, cudaMemcpy(e->d_owned_ids, owned.data(), sizeof(int) * owned.size(), cudaMemcpyHostToDevice));
+  }
+  if (e->n_repl) {
+    FR_CUDA(e, cudaMalloc(&e->d_repl_ids, sizeof(int) * repl.size()));
+    FR_CUDA(e, cudaMemcpy(e->d_repl_ids, repl.data(), sizeof(int) * repl.size(), cudaMemcpyHostToDevice));
+  }
+  e->shard_lists_built = true;
+  return FR_OK;
+}
+
+fr_status frk_gather_push(fr_engine* e, const int32_t* d_idx, int B_global, cudaStream_t st) {
+  if (!e->shard_lists_built) {
+    std::lock_guard<std::mutex> g(e->mu);
+    if (!e->shard_lists_built) {
+      fr_status s = build_shard_lists(e);
+      if (s != FR_OK) return s;
+    }
+  }
+  const int per = B_global / e->world;
+  const bool round = (e->precision == FR_PREC_TF32);
+  float4* const* peers = reinterpret_cast<float4* const*>(e->d_peer_ptrs);
+  if (e->n_owned) {
+    if (round) launch_gather<true, true>(e, e->d_owned_ids, e->n_owned, d_idx, 0, B_global, nullptr, peers, per, st);
+    else launch_gather<false, true>(e, e->d_owned_ids, e->n_owned, d_idx, 0, B_global, nullptr, peers, per, st);
+    e->launches++;
+  }
+  if (e->n_repl) {
+    // local items only, written into this rank's own exchange buffer (row b - rank*per)
+    float4* own = reinterpret_cast<float4*>(e->d_xchg) - (size_t)e->rank * per * (e->D / 4);
+    const int b0 = e->rank * per, b1 = (e->rank + 1) * per;
+    if (round) launch_gather<true, false>(e, e->d_repl_ids, e->n_repl, d_idx, b0, b1, own, nullptr, 1, st);
+    else launch_gather<false, false>(e, e->d_repl_ids, e->n_repl, d_idx, b0, b1, own, nullptr, 1, st);
+    e->launches++;
+  }
+  FR_CUDA(e, cudaGetLastError());
+  return FR_OK;
+}

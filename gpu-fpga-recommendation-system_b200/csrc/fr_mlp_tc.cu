@@ -1,0 +1,442 @@
+// fr_mlp_tc.cu -- the MLP as tcgen05 / TMEM GEMMs (FR_PREC_TF32), sm_100a only.
+//
+// Replaces the four cublasLtMatmul calls of cuda_server.c:468-491 (FP32 SGEMM chain
+//   R1 = W1.X, R2 = W2.R1, R3 = W3.R2, out = W4.R3, alpha=1 beta=0)
+// with three hand-written kernels launches per batch:
+//   layer 1, 2 : Y[B][N] = rna_tf32(act(A[B][K] . Wt[N][K]^T + bias))     (EPI_STORE)
+//   layer 3+4  : score[b] = sig(b4 + sum_n w4[n] * act(A[b] . Wt3[n] + b3[n]))  (EPI_DOT)
+// i.e. bias + ReLU live in the TMEM epilogue and the 256->1 output layer plus the
+// sigmoid are folded into layer 3's epilogue, so R3 never exists in memory.
+//
+// One CTA computes one 128 x BLOCK_N output tile:
+//   warp 0      TMA producer  : cp.async.bulk.tensor 2D loads of the A (128 x 32 fp32)
+//                               and B (BLOCK_N x 32 fp32) K-slices into a STAGES-deep
+//                               128B-swizzled smem ring, completion on mbarriers
+//   warp 1      MMA issuer    : allocates TMEM, one elected lane issues
+//                               tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BLOCK_N, K=8)
+//                               x4 per K-slice, tcgen05.commit frees the smem slot
+//   warps 2..5  epilogue      : tcgen05.ld 32x32b (one TMEM lane = one output row per
+//                               thread), bias/ReLU/(dot), stores
+// Operands are K-major in smem for both A and B: activations are row-major [B][K]
+// as the reference has them (cuda_server.c:216), weights are transposed once at
+// load time ([in][out] -> [out][in], rounded to TF32).  FP32 accumulate in TMEM.
+// K tails (880 = 27.5 slices) and M tails rely on TMA zero fill of out-of-bounds
+// box elements; stores are masked by the row count.
+#include <cuda.h>
+
+#include "fr_common.h"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;            // fp32 elements = 128 bytes = one swizzle atom
+constexpr int UMMA_K = 8;              // tf32: 32 bytes of K per instruction
+constexpr int kThreads = 192;
+constexpr int kEpiWarp0 = 2;
+
+enum { EPI_STORE = 0, EPI_DOT = 1 };
+
+// ---- PTX wrappers -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* smem, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] . B[smem]^T, tf32 inputs, fp32 accumulate; issued by ONE thread.
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on an mbarrier once every previously issued tcgen05.mma has completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// 32 consecutive fp32 columns of this thread's TMEM lane.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// K-major, 128B-swizzled operand tile: rows are 128 bytes, 8-row groups are 1024 bytes
+// apart (SBO), LBO unused for swizzled K-major; descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                              // leading byte offset (ignored), bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                              // version, bits [46,48)
+  d |= (uint64_t)2 << 61;                              // layout type SWIZZLE_128B, bits [61,64)
+  return d;
+}
+
+// kind::tf32 instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=n.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+template <int BLOCK_N, int STAGES>
+struct SmemLayout {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 4;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 4;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kAuxOff = STAGES * kStageBytes;            // bias[BLOCK_N], w4[BLOCK_N]
+  static constexpr int kBarOff = kAuxOff + 2 * BLOCK_N * 4;
+  static constexpr int kTotal = kBarOff + (2 * STAGES + 1) * 8 + 16;
+  static constexpr int kDyn = kTotal + 1024;                      // slack for manual 1024-B alignment
+};
+
+struct TcParams {
+  const float* bias;   // [N] or null
+  float* out;          // EPI_STORE: Y [M][N]; EPI_DOT: scores [M]
+  const float* w4;     // EPI_DOT: output-layer weights [N]
+  const float* b4;     // EPI_DOT: output-layer bias [1] or null
+  int M, N, K;
+  int relu, sigmoid;
+};
+
+template <int BLOCK_N, int STAGES, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const TcParams p) {
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* s_bias = reinterpret_cast<float*>(smem + L::kAuxOff);
+  float* s_w4 = s_bias + BLOCK_N;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int m0 = blockIdx.y * BLOCK_M, n0 = blockIdx.x * BLOCK_N;
+  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  } else if (warp == 1) {
+    tmem_alloc(tmem_ptr, BLOCK_N);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; kb++) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* a_dst = smem + s * L::kStageBytes;
+        uint8_t* b_dst = a_dst + L::kABytes;
+        mbar_expect_tx(&full_bar[s], L::kStageBytes);
+        tma_load_2d(&tmap_a, &full_bar[s], a_dst, kb * BLOCK_K, m0);
+        tma_load_2d(&tmap_b, &full_bar[s], b_dst, kb * BLOCK_K, n0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc_tf32(BLOCK_N);
+    for (int kb = 0; kb < num_kb; kb++) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+        const uint64_t a_desc = make_smem_desc(a_addr);
+        const uint64_t b_desc = make_smem_desc(a_addr + L::kABytes);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+          // advance 32 bytes of K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+          umma_tf32(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[s]);                       // smem slot reusable once these MMAs retire
+        if (kb == num_kb - 1) umma_commit(tmem_full_bar);  // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
+    const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..127
+    for (int i = et; i < BLOCK_N; i += 128) {
+      s_bias[i] = p.bias ? p.bias[n0 + i] : 0.f;
+      if (EPI == EPI_DOT) s_w4[i] = p.w4[n0 + i];
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue-only named barrier
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp % 4;
+    const int row = m0 + q * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float dot = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c, r);
+      if (EPI == EPI_STORE) {
+        if (row < p.M) {
+          float4* dst = reinterpret_cast<float4*>(p.out + (size_t)row * p.N + n0 + c);
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            float4 o;
+            o.x = __uint_as_float(r[4 * j + 0]) + s_bias[c + 4 * j + 0];
+            o.y = __uint_as_float(r[4 * j + 1]) + s_bias[c + 4 * j + 1];
+            o.z = __uint_as_float(r[4 * j + 2]) + s_bias[c + 4 * j + 2];
+            o.w = __uint_as_float(r[4 * j + 3]) + s_bias[c + 4 * j + 3];
+            if (p.relu) {
+              o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+            }
+            o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+            dst[j] = o;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          float v = __uint_as_float(r[j]) + s_bias[c + j];
+          if (p.relu) v = fmaxf(v, 0.f);
+          dot = fmaf(v, s_w4[c + j], dot);
+        }
+      }
+    }
+    if (EPI == EPI_DOT && row < p.M) {
+      if (p.b4) dot += p.b4[0];
+      p.out[row] = p.sigmoid ? 1.f / (1.f + __expf(-dot)) : dot;
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BLOCK_N);
+  }
+}
+
+// ---- host side ----------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TcLayerCfg {
+  int block_n, stages, epi;
+};
+
+struct TcState {
+  PFN_encodeTiled encode = nullptr;
+  CUtensorMap w_map[3];
+  TcLayerCfg cfg[3];
+  bool ready = false;
+  // cached A-operand maps keyed by (pointer, K)
+  struct AMap {
+    const void* ptr;
+    int K, rows;
+    CUtensorMap map;
+  };
+  std::vector<AMap> a_maps;
+  std::mutex mu;
+};
+
+fr_status encode_2d(fr_engine* e, TcState* st, CUtensorMap* map, const void* base, int rows, int K, int box_rows) {
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = st->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fr_fail(e, FR_ERR_CUDA, "cuTensorMapEncodeTiled(rows=%d K=%d box=%d) failed: CUresult %d", rows, K, box_rows,
+                   (int)r);
+  return FR_OK;
+}
+
+template <int BLOCK_N, int STAGES, int EPI>
+fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, cudaStream_t st) {
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  static std::atomic<uint64_t> attr_done{0};  // bit d: opt-in smem size set on device d for this instantiation
+  const uint64_t bit = 1ull << (e->device & 63);
+  if (!(attr_done.load() & bit)) {
+    FR_CUDA(e, cudaFuncSetAttribute(tc_linear_kernel<BLOCK_N, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    L::kDyn));
+    attr_done.fetch_or(bit);
+  }
+  dim3 grid(p.N / BLOCK_N, (p.M + BLOCK_M - 1) / BLOCK_M);
+  tc_linear_kernel<BLOCK_N, STAGES, EPI><<<grid, kThreads, L::kDyn, st>>>(a, b, p);
+  e->launches++;
+  FR_CUDA(e, cudaGetLastError());
+  return FR_OK;
+}
+
+fr_status get_a_map(fr_engine* e, TcState* st, const void* ptr, int K, int rows, CUtensorMap* out) {
+  std::lock_guard<std::mutex> g(st->mu);
+  for (const TcState::AMap& m : st->a_maps)
+    if (m.ptr == ptr && m.K == K && m.rows == rows) {
+      *out = m.map;
+      return FR_OK;
+    }
+  TcState::AMap m;
+  m.ptr = ptr;
+  m.K = K;
+  m.rows = rows;
+  fr_status s = encode_2d(e, st, &m.map, ptr, rows, K, BLOCK_M);
+  if (s != FR_OK) return s;
+  if (st->a_maps.size() < 256) st->a_maps.push_back(m);
+  *out = m.map;
+  return FR_OK;
+}
+
+}  // namespace
+
+fr_status frtc_prepare(fr_engine* e) {
+  TcState* st = static_cast<TcState*>(e->tc_state);
+  if (st && st->ready) return FR_OK;
+  std::lock_guard<std::mutex> g(e->mu);
+  st = static_cast<TcState*>(e->tc_state);
+  if (!st) {
+    st = new TcState();
+    e->tc_state = st;
+  }
+  if (st->ready) return FR_OK;
+  if (!st->encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    FR_CUDA(e, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess)
+      return fr_fail(e, FR_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    st->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  }
+  if (e->dims[3] != 256)
+    return fr_fail(e, FR_ERR_UNSUPPORTED, "TF32 path folds the output layer into layer 3 and needs hidden[2] == 256 "
+                   "(got %d)", e->dims[3]);
+  // layer 1: N = 1024/2048, 128-wide tiles; layer 2: N = 512, 64-wide tiles (more CTAs); layer 3: whole 256 row.
+  st->cfg[0] = {128, 6, EPI_STORE};
+  st->cfg[1] = {64, 8, EPI_STORE};
+  st->cfg[2] = {256, 4, EPI_DOT};
+  for (int k = 0; k < 3; k++) {
+    if (e->dims[k + 1] % st->cfg[k].block_n)
+      return fr_fail(e, FR_ERR_UNSUPPORTED, "hidden[%d]=%d not a multiple of tile N %d", k, e->dims[k + 1],
+                     st->cfg[k].block_n);
+    fr_status s = encode_2d(e, st, &st->w_map[k], e->d_Wt[k], e->dims[k + 1], e->dims[k], st->cfg[k].block_n);
+    if (s != FR_OK) return s;
+  }
+  st->ready = true;
+  return FR_OK;
+}
+
+void frtc_destroy(fr_engine* e) {
+  delete static_cast<TcState*>(e->tc_state);
+  e->tc_state = nullptr;
+}
+
+// One launch: layer k (0,1: store tf32-rounded activations into s->d_h[k]; 2: layer 3 with the
+// output layer + sigmoid folded in, writes d_scores).
+fr_status frtc_layer(fr_engine* e, fr_stream_s* s, int k, const float* in, int B, float* d_scores) {
+  TcState* st = static_cast<TcState*>(e->tc_state);
+  const bool act = (e->mlp_mode == FR_MLP_BIAS_RELU_SIGMOID);
+  CUtensorMap a;
+  // rows = B: TMA zero-fills the M tail, so no stale rows are ever multiplied
+  fr_status r = get_a_map(e, st, in, e->dims[k], B, &a);
+  if (r != FR_OK) return r;
+  TcParams p;
+  p.bias = act ? e->d_bias[k] : nullptr;
+  p.M = B;
+  p.N = e->dims[k + 1];
+  p.K = e->dims[k];
+  p.relu = act ? 1 : 0;
+  p.sigmoid = act ? 1 : 0;
+  p.w4 = e->d_W[3];
+  p.b4 = act ? e->d_bias[3] : nullptr;
+  if (k == 0) {
+    p.out = s->d_h[0];
+    return launch<128, 6, EPI_STORE>(e, a, st->w_map[0], p, s->stream);
+  }
+  if (k == 1) {
+    p.out = s->d_h[1];
+    return launch<64, 8, EPI_STORE>(e, a, st->w_map[1], p, s->stream);
+  }
+  p.out = d_scores;
+  return launch<256, 4, EPI_DOT>(e, a, st->w_map[2], p, s->stream);
+}

@@ -1,0 +1,9 @@
+"""fleetrec -- Python host side of the B200-native FleetRec inference hot path.
+
+The product is ../libfleetrec.so (hand-written sm_100a kernels behind the C ABI
+in /include/fleetrec.h); this package only binds it (ctypes) and carries the
+model catalogues.  Nothing here computes on the CPU.
+"""
+from . import catalogue  # noqa: F401
+from ._capi import (FR_MLP_BIAS_RELU_SIGMOID, FR_MLP_LINEAR, FR_PREC_FP32, FR_PREC_TF32)  # noqa: F401
+from .engine import Engine, FleetRecError, Worker, merge_index  # noqa: F401

@@ -138,6 +138,11 @@ fr_status fr_infer(fr_engine* e, const int32_t* idx, int B, float* scores, fr_st
 fr_status fr_gather_only(fr_engine* e, const int32_t* idx, int B, float* concat, fr_stream s);
 /* B3 alone: x is what cuda_server.c:425-461 receives, [B][concat_floats] fp32. */
 fr_status fr_mlp_only(fr_engine* e, const float* x, int B, float* scores, fr_stream s);
+/* One launch of the MLP chain in isolation (unit-test hook): step k of the current
+ * precision's chain on x [B][in_k].  TF32: k = 0,1 -> y [B][out_k] (tf32-rounded
+ * activations), k = 2 -> y [B] scores (layer 3 with the output layer folded in).
+ * FP32: k = 0..2 -> y [B][out_k], k = 3 -> y [B] scores. */
+fr_status fr_layer_only(fr_engine* e, int k, const float* x, int B, float* y, fr_stream s);
 fr_status fr_sync(fr_engine* e, fr_stream s);
 
 /* ---- introspection ------------------------------------------------------ */
@@ -150,6 +155,12 @@ int64_t fr_table_bytes(const fr_engine* e);
  * kernels are launched on. */
 fr_status fr_mark(fr_engine* e, fr_stream s, int which);
 fr_status fr_elapsed_ms(fr_engine* e, fr_stream s, float* ms);
+/* Per-kernel device time for one batch: every kernel of the step is launched
+ * `reps` times back to back, alone, between two CUDA events on the worker's own
+ * stream (after one untimed pass).  ms5 = average ms per launch of {gather,
+ * layer 1, layer 2, layer 3 (+output layer when fused), output layer (FP32 path
+ * only, else 0)}.  Measurement hook for the roofline report (bench.py). */
+fr_status fr_time_kernels(fr_engine* e, const int32_t* idx, int B, int reps, fr_stream s, float* ms5);
 
 /* ---- table sharding across processes (one engine per GPU) ---------------- */
 /* owner[t] in [0, world) = rank holding table t, or -1 = replicated on every

@@ -87,30 +87,47 @@ void fro_gather(const float* const* tables, const int* dims, const fro_segment* 
  * cuda_server.c:215-217,468-473.  k ascends, fp32 (or double) accumulate. */
 static void layer_f32(const float* X, int B, int in, int out, const float* W, const float* bias, int relu,
                       float* Y, int threads) {
-  enum { RB = 4 };
+  /* register tile: RB rows x CB columns of Y stay in vector registers over the whole k loop
+   * (k ascending per output, exactly as a scalar loop would); W is first re-packed into
+   * contiguous [in][CB] column panels so the k loop streams memory linearly. */
+  enum { RB = 6, CB = 16 };
+  const int np = (out + CB - 1) / CB;
+  float* Wp = (float*)aligned_alloc(64, (size_t)np * in * CB * sizeof(float));
+#pragma omp parallel for schedule(static) num_threads(threads)
+  for (int p = 0; p < np; p++)
+    for (int k = 0; k < in; k++)
+      for (int j = 0; j < CB; j++)
+        Wp[((size_t)p * in + k) * CB + j] = (p * CB + j < out) ? W[(size_t)k * out + p * CB + j] : 0.0f;
 #pragma omp parallel for schedule(static) num_threads(threads)
   for (int b0 = 0; b0 < B; b0 += RB) {
-    int nb = B - b0 < RB ? B - b0 : RB;
-    float* acc = Y + (size_t)b0 * out;
-    for (int r = 0; r < nb; r++)
-      for (int j = 0; j < out; j++) acc[(size_t)r * out + j] = 0.0f;
-    for (int k = 0; k < in; k++) {
-      const float* w = W + (size_t)k * out;
-      for (int r = 0; r < nb; r++) {
-        const float a = X[(size_t)(b0 + r) * in + k];
-        float* y = acc + (size_t)r * out;
-        for (int j = 0; j < out; j++) y[j] += a * w[j];
+    const int nb = B - b0 < RB ? B - b0 : RB;
+    const float* xr[RB];
+    for (int r = 0; r < RB; r++) xr[r] = X + (size_t)(b0 + (r < nb ? r : 0)) * in;
+    for (int p = 0; p < np; p++) {
+      const int j0 = p * CB;
+      const int nc = out - j0 < CB ? out - j0 : CB;
+      const float* wp = Wp + (size_t)p * in * CB;
+      float acc[RB][CB];
+      for (int r = 0; r < RB; r++)
+        for (int j = 0; j < CB; j++) acc[r][j] = 0.0f;
+      for (int k = 0; k < in; k++) {
+        const float* w = wp + (size_t)k * CB;
+        for (int r = 0; r < RB; r++) {
+          const float a = xr[r][k];
+#pragma omp simd
+          for (int j = 0; j < CB; j++) acc[r][j] += a * w[j];
+        }
       }
-    }
-    if (bias || relu)
       for (int r = 0; r < nb; r++) {
-        float* y = acc + (size_t)r * out;
-        for (int j = 0; j < out; j++) {
-          float v = y[j] + (bias ? bias[j] : 0.0f);
+        float* y = Y + (size_t)(b0 + r) * out + j0;
+        for (int j = 0; j < nc; j++) {
+          float v = acc[r][j] + (bias ? bias[j0 + j] : 0.0f);
           y[j] = (relu && v < 0.0f) ? 0.0f : v;
         }
       }
+    }
   }
+  free(Wp);
 }
 
 static void layer_f64(const float* X, int B, int in, int out, const float* W, const float* bias, int relu,

@@ -176,3 +176,33 @@ def uniform_indices(model, B, seed=4321):
     for t in model.tables:
         idx[:, t.id] = rng.integers(0, t.rows, B, dtype=np.int64).astype(np.int32)
     return idx
+
+
+def hash_rows(seed, table_id, rows, dim):
+    """Vectorised fro_hash_bits: the [len(rows)][dim] fp32 values a hash-filled table
+    holds at the given row indices, computed without materialising the table
+    (full-size parity checks: 12.8 GB tables never exist on the host)."""
+    rows = np.asarray(rows, np.uint64).reshape(-1, 1)
+    cols = np.arange(dim, dtype=np.uint64).reshape(1, -1)
+    with np.errstate(over="ignore"):
+        z = rows * np.uint64(0x9E3779B97F4A7C15) + (np.uint64(table_id) << np.uint64(40)) \
+            + (cols << np.uint64(28)) + np.uint64(seed)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    h = (z >> np.uint64(16)).astype(np.uint32)
+    expo = np.uint32(118) + ((h >> np.uint32(23)) & np.uint32(0xFF)) % np.uint32(9)
+    bits = (h & np.uint32(0x80000000)) | (expo << np.uint32(23)) | (h & np.uint32(0x007FFFFF))
+    return bits.view(np.float32)
+
+
+def gather_hashed(model, seed, idx):
+    """oracle.gather() for hash-filled tables of any size (no table memory)."""
+    idx = np.asarray(idx)
+    out = np.empty((idx.shape[0], model.concat_floats), np.float32)
+    cache = {}
+    for s in model.segments:
+        if s.table not in cache:
+            cache[s.table] = hash_rows(seed, s.table, idx[:, s.table], model.tables[s.table].dim)
+        out[:, s.dst:s.dst + s.len] = cache[s.table][:, s.col:s.col + s.len]
+    return out

@@ -1,0 +1,259 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle -- needs a B200.
+
+Bit-exact for the lookup/concat (memcmp), tolerance for the MLP:
+  max_i |s_i - s^_i| / max(|s^_i|, 1e-6) <= 1e-3   (BASELINE.json north_star)
+against the oracle's fp32 MLP, in both arithmetic modes.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import fleetrec
+from fleetrec import catalogue
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+MODELS3 = ("small", "medium", "large_half")
+TOL = 1e-3
+
+
+def rel_err(got, exp):
+    return float(np.max(np.abs(got - exp) / np.maximum(np.abs(exp), 1e-6)))
+
+
+def assert_bits_equal(a, b):
+    assert a.shape == b.shape
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+# ---------------------------------------------------------------- lookup + concat
+@pytest.mark.parametrize("model", MODELS3)
+def test_gather_matches_reference_golden(model):
+    """CUDA gather vs the wire bytes the reference's own kernel emitted (tests/golden)."""
+    g = np.load(os.path.join(GOLD, f"ref_{model}.npz"))
+    cat = catalogue.load(model).with_row_cap(int(g["row_cap"]))
+    eng = fleetrec.Engine(cat, max_batch=128)
+    for t in cat.tables:
+        tab = oracle.fill_reference(t.rows, t.dim) if t.tier == "PLRAM" else \
+            oracle.fill_hash(int(g["seed"]), t.id, t.rows, t.dim)
+        eng.load_table(t.id, tab)
+    out = eng.gather_only(oracle.idx_reference(96, cat.n_tables))
+    assert_bits_equal(out[:32], g["wire_first32"])
+    assert hashlib.sha256(out.tobytes()).hexdigest() == str(g["wire96_sha256"])
+    eng.close()
+
+
+@pytest.mark.parametrize("model", ("small", "medium", "large_half", "large"))
+@pytest.mark.parametrize("B", (1, 37, 1000))
+def test_gather_bit_exact_vs_oracle(model, B):
+    cat = catalogue.load(model).with_row_cap(3000)
+    eng = fleetrec.Engine(cat, max_batch=1024)
+    tables = oracle.make_tables(cat, "hash", seed=11)
+    eng.load_tables(tables)
+    idx = oracle.uniform_indices(cat, B, seed=B)
+    assert_bits_equal(eng.gather_only(idx), oracle.gather(cat, tables, idx))
+    eng.close()
+
+
+def test_gather_edge_cases_and_device_fills():
+    cat = catalogue.load("small").with_row_cap(257)          # odd row count
+    eng = fleetrec.Engine(cat, max_batch=64)
+    eng.fill_hash(seed=5)
+    for t in (0, 29, 46):
+        assert_bits_equal(eng.read_table(t, 0, cat.tables[t].rows),
+                          oracle.fill_hash(5, t, cat.tables[t].rows, cat.tables[t].dim))
+    assert eng.gather_only(np.zeros((0, 47), np.int32)).shape == (0, 352)          # empty batch
+    idx = np.stack([np.array([t.rows - 1 for t in cat.tables], np.int32), np.zeros(47, np.int32)])
+    assert_bits_equal(eng.gather_only(idx), oracle.gather_hashed(cat, 5, idx))       # first / last rows
+    eng.close()
+    # reference fill + reference index list: the lookup KAT (all-ones / all-zeros items)
+    for model in MODELS3:
+        cat = catalogue.load(model).with_row_cap(201)
+        eng = fleetrec.Engine(cat, max_batch=64)
+        eng.fill_reference()
+        out = eng.gather_only(oracle.idx_reference(32, cat.n_tables))
+        for j, r in enumerate(catalogue.IDX_RANDOM):
+            assert np.all(out[j] == (1.0 if r % 2 == 0 else 0.0)), (model, j)
+        assert_bits_equal(eng.read_table(1, 0, 201), oracle.fill_reference(201, cat.tables[1].dim))
+        eng.close()
+    cat = catalogue.load("small").with_row_cap(1000)
+    eng = fleetrec.Engine(cat, max_batch=64)
+    eng.fill_reference(debug_rows=200)                        # host.cpp:75 `#define DEBUG`
+    assert_bits_equal(eng.read_table(0, 0, 1000), oracle.fill_reference(1000, cat.tables[0].dim, 200))
+    eng.close()
+
+
+def test_gather_full_size_small_model():
+    """BASELINE configs[1] tables at their real sizes (1.4 GB, 10 M-row DDR1): the
+    expected bytes come from the position-encoding hash, no host tables needed."""
+    cat = catalogue.load("small")
+    eng = fleetrec.Engine(cat, max_batch=4096)
+    eng.fill_hash(seed=0x5EED)
+    assert eng.table_bytes() == cat.table_bytes()
+    for idx in (oracle.zipf_indices(cat, 2048), oracle.uniform_indices(cat, 4096),
+                np.array([[t.rows - 1 for t in cat.tables]], np.int32)):
+        assert_bits_equal(eng.gather_only(idx), oracle.gather_hashed(cat, 0x5EED, idx))
+    eng.close()
+
+
+def test_errors_are_reported_not_fatal():
+    cat = catalogue.load("small").with_row_cap(100)
+    eng = fleetrec.Engine(cat, max_batch=32)
+    with pytest.raises(fleetrec.FleetRecError) as ei:
+        eng.gather_only(np.zeros((4, 47), np.int32))          # tables not loaded
+    assert ei.value.code == 4 and "not loaded" in str(ei.value)
+    eng.fill_hash()
+    with pytest.raises(fleetrec.FleetRecError):
+        eng.gather_only(np.zeros((33, 47), np.int32))         # B > max_batch
+    with pytest.raises(fleetrec.FleetRecError) as ei:
+        eng.infer(np.zeros((4, 47), np.int32))                # MLP not loaded
+    assert "layer" in str(ei.value)
+    with pytest.raises(fleetrec.FleetRecError):
+        eng.load_table(0, np.zeros((100, 12), np.float32))    # wrong dim
+    eng.close()
+
+
+# ---------------------------------------------------------------- MLP
+KAT = {"small": 47244640256.0, "medium": 118111600640.0, "large": 1065151889408.0}
+
+
+@pytest.mark.parametrize("prec", (fleetrec.FR_PREC_FP32, fleetrec.FR_PREC_TF32))
+@pytest.mark.parametrize("model", ("small", "medium", "large"))
+def test_mlp_all_ones_known_answer(model, prec):
+    """README.md:7-11: all-ones input and weights -> IN*H1*H2*H3, exact in fp32 and tf32."""
+    cat = catalogue.load(model).with_row_cap(64)
+    dims = cat.layer_dims
+    eng = fleetrec.Engine(cat, mlp_mode=fleetrec.FR_MLP_LINEAR, precision=prec, max_batch=256)
+    eng.load_mlp([np.ones((dims[k], dims[k + 1]), np.float32) for k in range(4)])
+    out = eng.mlp_only(np.ones((130, dims[0]), np.float32))
+    assert np.all(out == np.float32(KAT[model])), out[:4]
+    eng.close()
+
+
+@pytest.mark.parametrize("prec,tol", ((fleetrec.FR_PREC_FP32, 2e-5), (fleetrec.FR_PREC_TF32, TOL)))
+@pytest.mark.parametrize("model", ("small", "medium", "large"))
+@pytest.mark.parametrize("B", (1, 100, 2048, 4099))
+def test_mlp_bias_relu_sigmoid_vs_oracle(model, prec, tol, B):
+    cat = catalogue.load(model).with_row_cap(64)
+    dims = cat.layer_dims
+    W, b = oracle.make_weights(dims, seed=42)
+    x = np.random.default_rng(B).uniform(-1, 1, (B, dims[0])).astype(np.float32)
+    eng = fleetrec.Engine(cat, precision=prec, max_batch=4224)
+    eng.load_mlp(W, b)
+    got = eng.mlp_only(x)
+    exp = oracle.mlp(x, dims, W, b, mode=1)
+    assert rel_err(got, exp) <= tol, rel_err(got, exp)
+    eng.close()
+
+
+@pytest.mark.parametrize("prec,tol", ((fleetrec.FR_PREC_FP32, 2e-5), (fleetrec.FR_PREC_TF32, TOL)))
+def test_mlp_linear_mode_vs_oracle(prec, tol):
+    """Reference-exact mode (no bias / activation).  Positive weights and inputs keep
+    every output far from zero, so the element-wise relative error is well defined;
+    random-sign weights are checked against the output scale instead."""
+    cat = catalogue.load("small").with_row_cap(64)
+    dims = cat.layer_dims
+    rng = np.random.default_rng(3)
+    eng = fleetrec.Engine(cat, mlp_mode=fleetrec.FR_MLP_LINEAR, precision=prec, max_batch=1024)
+    Wp = [(rng.uniform(0, 2, (dims[k], dims[k + 1])) / dims[k]).astype(np.float32) for k in range(4)]
+    x = rng.uniform(0, 1, (777, dims[0])).astype(np.float32)
+    eng.load_mlp(Wp)
+    exp = oracle.mlp(x, dims, Wp, None, mode=0)
+    assert rel_err(eng.mlp_only(x), exp) <= tol
+    W, _ = oracle.make_weights(dims, seed=9)
+    x = rng.uniform(-1, 1, (777, dims[0])).astype(np.float32)
+    eng.load_mlp(W)
+    exp = oracle.mlp(x, dims, W, None, mode=0, acc64=True)
+    assert np.max(np.abs(eng.mlp_only(x) - exp)) / np.std(exp) <= 5 * tol
+    eng.close()
+
+
+# ---------------------------------------------------------------- end to end
+@pytest.mark.parametrize("prec,tol", ((fleetrec.FR_PREC_FP32, 2e-5), (fleetrec.FR_PREC_TF32, TOL)))
+@pytest.mark.parametrize("model", ("small", "medium"))
+def test_infer_end_to_end(model, prec, tol):
+    cat = catalogue.load(model).with_row_cap(20000)
+    dims = cat.layer_dims
+    tables = oracle.make_tables(cat, "hash", seed=77)
+    W, b = oracle.make_weights(dims, seed=42)
+    eng = fleetrec.Engine(cat, precision=prec, max_batch=2048)
+    eng.load_tables(tables)
+    eng.load_mlp(W, b)
+    workers = [fleetrec.Worker(eng) for _ in range(2)]
+    for B, w in ((2048, None), (256, workers[0]), (333, workers[1])):
+        idx = oracle.zipf_indices(cat, B, seed=B)
+        exp = oracle.mlp(oracle.gather(cat, tables, idx), dims, W, b, mode=1)
+        got = eng.infer(idx, worker=w)
+        assert rel_err(got, exp) <= tol, (B, rel_err(got, exp))
+    assert eng.launch_count() > 0
+    for w in workers:
+        w.close()
+    eng.close()
+
+
+def test_reference_chain_kat_through_infer():
+    """reference fill + index list + all-ones LINEAR MLP -> KAT value or 0."""
+    cat = catalogue.load("small").with_row_cap(200)
+    dims = cat.layer_dims
+    eng = fleetrec.Engine(cat, mlp_mode=fleetrec.FR_MLP_LINEAR, max_batch=64)
+    eng.fill_reference()
+    eng.load_mlp([np.ones((dims[k], dims[k + 1]), np.float32) for k in range(4)])
+    out = eng.infer(oracle.idx_reference(32, 47))
+    for j, r in enumerate(catalogue.IDX_RANDOM):
+        assert out[j] == (np.float32(KAT["small"]) if r % 2 == 0 else 0.0)
+    eng.close()
+
+
+def test_cartesian_merge_on_device():
+    """gather(M, remap(iA,iB)) == gather(A,iA) || gather(B,iB)  (SURVEY 8c-b)."""
+    T = catalogue.Table
+    tabs = [T(0, "HBM", 0, 0, 0, 37, 4, 1, 0), T(1, "HBM", 1, 1, 0, 11, 8, 2, 0), T(2, "HBM", 2, 2, 0, 37 * 11, 12, 3, 0),
+            T(3, "HBM", 3, 3, 0, 8, 8, 2, 0)]
+    S = catalogue.Segment
+    cat = catalogue.Model("merge", tabs, [S(0, 0, 0, 4), S(4, 1, 0, 8), S(12, 2, 0, 12), S(24, 3, 0, 8)], 32, 32,
+                          [128, 128, 256, 1])
+    eng = fleetrec.Engine(cat, max_batch=512)
+    for t in (0, 1, 3):
+        eng._chk(eng._L.fr_fill_table_hash(eng._h, t, 9))
+    eng.merge_tables(0, 1, 2)
+    assert_bits_equal(eng.read_table(2, 0, 37 * 11),
+                      oracle.merge_tables(oracle.fill_hash(9, 0, 37, 4), oracle.fill_hash(9, 1, 11, 8)))
+    ia, ib = np.meshgrid(np.arange(37), np.arange(11), indexing="ij")
+    idx = np.zeros((37 * 11, 4), np.int32)
+    idx[:, 0], idx[:, 1] = ia.ravel(), ib.ravel()
+    idx[:, 2] = [fleetrec.merge_index(a, b, 11) for a, b in zip(ia.ravel(), ib.ravel())]
+    out = eng.gather_only(idx)
+    assert_bits_equal(out[:, 0:12], out[:, 12:24])
+    eng.close()
+
+
+def tf32_rna(x):
+    b = x.view(np.uint32).astype(np.uint64)
+    return ((b + 0x1000) & 0xFFFFE000).astype(np.uint32).view(np.float32)
+
+
+@pytest.mark.parametrize("k", (0, 1, 2))
+@pytest.mark.parametrize("B", (128, 300))
+def test_tf32_single_layer_vs_numpy(k, B):
+    """Each tcgen05 GEMM configuration alone (128x128, 128x64, 128x256+dot tiles):
+    inputs pre-rounded to TF32, so the only difference to float64 is summation order."""
+    cat = catalogue.load("medium").with_row_cap(64)            # K = 880: exercises the K tail (27.5 slices)
+    dims = cat.layer_dims
+    W, b = oracle.make_weights(dims, seed=5)
+    eng = fleetrec.Engine(cat, max_batch=512)
+    eng.load_mlp(W, b)
+    x = tf32_rna(np.random.default_rng(k).uniform(-1, 1, (B, dims[k])).astype(np.float32))
+    h = np.maximum(x.astype(np.float64) @ tf32_rna(W[k]).astype(np.float64) + b[k], 0)
+    if k < 2:
+        got = eng.layer_only(k, x, dims[k + 1])
+        assert got.shape == h.shape
+        assert np.max(np.abs(got - h)) <= 2e-3 * max(1.0, np.abs(h).max())
+        assert np.array_equal(got.view(np.uint32) & 0x1FFF, np.zeros_like(got, np.uint32))   # stored tf32-rounded
+    else:
+        s = 1 / (1 + np.exp(-(h @ W[3].astype(np.float64)[:, 0] + b[3][0])))
+        got = eng.layer_only(k, x, 1)
+        assert rel_err(got, s.astype(np.float32)) <= 2e-4
+    eng.close()
