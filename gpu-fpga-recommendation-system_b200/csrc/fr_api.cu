@@ -225,7 +225,7 @@ extern "C" fr_status fr_load_table(fr_engine* e, int table_id, const float* host
   if (rows <= 0) return fr_fail(e, FR_ERR_INVALID, "rows must be > 0");
   tb.rows = rows;
   if ((st = ensure_table_mem(e, table_id)) != FR_OK) return st;
-  FR_CUDA(e, cudaMemcpy(tb.d, host_rows, (size_t)rows * dim * sizeof(float), cudaMemcpyHostToDevice));
+  FR_CUDA(e, fr_h2d(e, tb.d, host_rows, (size_t)rows * dim * sizeof(float)));
   tb.loaded = true;
   return FR_OK;
 }
@@ -275,9 +275,9 @@ extern "C" fr_status fr_load_mlp(fr_engine* e, int layer, const float* W, const 
   if (!e->d_W[layer]) FR_CUDA(e, cudaMalloc(&e->d_W[layer], nw * sizeof(float)));
   if (!e->d_Wt[layer]) FR_CUDA(e, cudaMalloc(&e->d_Wt[layer], nw * sizeof(float)));
   if (!e->d_bias[layer]) FR_CUDA(e, cudaMalloc(&e->d_bias[layer], (size_t)out * sizeof(float)));
-  FR_CUDA(e, cudaMemcpy(e->d_W[layer], W, nw * sizeof(float), cudaMemcpyHostToDevice));
-  if (bias) FR_CUDA(e, cudaMemcpy(e->d_bias[layer], bias, (size_t)out * sizeof(float), cudaMemcpyHostToDevice));
-  else FR_CUDA(e, cudaMemset(e->d_bias[layer], 0, (size_t)out * sizeof(float)));
+  FR_CUDA(e, fr_h2d(e, e->d_W[layer], W, nw * sizeof(float)));
+  if (bias) FR_CUDA(e, fr_h2d(e, e->d_bias[layer], bias, (size_t)out * sizeof(float)));
+  else FR_CUDA(e, cudaMemsetAsync(e->d_bias[layer], 0, (size_t)out * sizeof(float), e->default_stream->stream));
   fr_status st = frk_transpose_round_tf32(e, e->d_W[layer], in, out, e->d_Wt[layer], e->default_stream->stream);
   if (st != FR_OK) return st;
   FR_CUDA(e, cudaStreamSynchronize(e->default_stream->stream));
@@ -567,7 +567,7 @@ static fr_status upload_peers(fr_engine* e) {
     p[r] = e->peers[r].concat;
   }
   if (!e->d_peer_ptrs) FR_CUDA(e, cudaMalloc(&e->d_peer_ptrs, sizeof(float*) * e->world));
-  FR_CUDA(e, cudaMemcpy(e->d_peer_ptrs, p.data(), sizeof(float*) * e->world, cudaMemcpyHostToDevice));
+  FR_CUDA(e, fr_h2d(e, e->d_peer_ptrs, p.data(), sizeof(float*) * e->world));
   return FR_OK;
 }
 

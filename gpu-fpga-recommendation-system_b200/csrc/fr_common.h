@@ -96,6 +96,16 @@ fr_status fr_fail(const fr_engine* e, fr_status code, const char* fmt, ...);
                      "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
   } while (0)
 
+// Host->device upload that is COMPLETE on return.  A plain cudaMemcpy from pageable memory may
+// return once the bytes sit in the driver's staging buffer (the DMA is then ordered on the legacy
+// stream only), and the worker streams are cudaStreamNonBlocking -- a kernel launched right after
+// could read the old contents.  So every upload is enqueued on the engine's own stream and waited for.
+inline cudaError_t fr_h2d(fr_engine* e, void* dst, const void* src, size_t bytes) {
+  cudaError_t err = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, e->default_stream->stream);
+  if (err != cudaSuccess) return err;
+  return cudaStreamSynchronize(e->default_stream->stream);
+}
+
 // ---- kernels (each returns after enqueueing; bumps e->launches) -----------
 fr_status frk_upload_chunks(fr_engine* e);
 fr_status frk_gather(fr_engine* e, const int32_t* d_idx, int B, float* d_out, bool round_tf32, cudaStream_t st);

@@ -169,7 +169,7 @@ fr_status frk_upload_chunks(fr_engine* e) {
   for (int i = 0; i < C; i++)
     if (!covered[i]) return fr_fail(e, FR_ERR_INVALID, "concat float %d is not covered by any segment", i * 4);
   if (!e->d_chunks) FR_CUDA(e, cudaMalloc(&e->d_chunks, sizeof(FrChunk) * C));
-  FR_CUDA(e, cudaMemcpy(e->d_chunks, h.data(), sizeof(FrChunk) * C, cudaMemcpyHostToDevice));
+  FR_CUDA(e, fr_h2d(e, e->d_chunks, h.data(), sizeof(FrChunk) * C));
   e->chunks_dirty = false;
   return FR_OK;
 }
@@ -243,11 +243,11 @@ static fr_status build_shard_lists(fr_engine* e) {
   e->n_repl = (int)repl.size();
   if (e->n_owned) {
     FR_CUDA(e, cudaMalloc(&e->d_owned_ids, sizeof(int) * owned.size()));
-    FR_CUDA(e, cudaMemcpy(e->d_owned_ids, owned.data(), sizeof(int) * owned.size(), cudaMemcpyHostToDevice));
+    FR_CUDA(e, fr_h2d(e, e->d_owned_ids, owned.data(), sizeof(int) * owned.size()));
   }
   if (e->n_repl) {
     FR_CUDA(e, cudaMalloc(&e->d_repl_ids, sizeof(int) * repl.size()));
-    FR_CUDA(e, cudaMemcpy(e->d_repl_ids, repl.data(), sizeof(int) * repl.size(), cudaMemcpyHostToDevice));
+    FR_CUDA(e, fr_h2d(e, e->d_repl_ids, repl.data(), sizeof(int) * repl.size()));
   }
   e->shard_lists_built = true;
   return FR_OK;

@@ -146,10 +146,69 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
-template <int BLOCK_N, int STAGES>
+// ---- cluster helpers (2-CTA pairs) --------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+// 2-CTA TMA load: data lands in THIS CTA's smem, completion bytes are posted on the mbarrier at
+// cluster address `bar_cluster` (the pair leader's), which cta_group::2 permits.
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_cluster, void* smem, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(smem)),
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D (256 x N, rows 0..127 in the leader's TMEM, 128..255 in the peer's) (+)= A . B^T with A and B
+// halves read from BOTH CTAs' smem at the same offsets; issued by one thread of the leader CTA.
+__device__ __forceinline__ void umma_tf32_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive (once all prior MMAs of the pair retired) on the barrier at this offset in BOTH CTAs.
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+// CTAS = 1: one CTA owns a 128 x BLOCK_N tile.  CTAS = 2: a CTA pair (cluster of 2 along M) owns a
+// 256 x BLOCK_N tile; each CTA stages its own 128 rows of A and its own BLOCK_N/2 rows of B, so per
+// SM the smem fill per MMA cycle halves for B -- the point of cta_group::2 for 4-byte operands.
+template <int BLOCK_N, int STAGES, int CTAS>
 struct SmemLayout {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 4;
-  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 4;
+  static constexpr int kBRows = BLOCK_N / CTAS;
+  static constexpr int kBBytes = kBRows * BLOCK_K * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kAuxOff = STAGES * kStageBytes;            // bias[BLOCK_N], w4[BLOCK_N]
   static constexpr int kBarOff = kAuxOff + 2 * BLOCK_N * 4;
@@ -166,12 +225,18 @@ struct TcParams {
   int relu, sigmoid;
 };
 
-template <int BLOCK_N, int STAGES, int EPI>
+// kind::tf32 instruction descriptor: D=f32, A=B=tf32, both K-major, M = 128*CTAS, N = n.
+__host__ __device__ constexpr uint32_t make_idesc_tf32_m(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int BLOCK_N, int STAGES, int EPI, int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const TcParams p) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+  using L = SmemLayout<BLOCK_N, STAGES, CTAS>;
   extern __shared__ uint8_t smem_raw[];
+  // the dynamic-smem base offset is identical in both CTAs of a pair, so is the aligned layout
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* s_bias = reinterpret_cast<float*>(smem + L::kAuxOff);
   float* s_w4 = s_bias + BLOCK_N;
@@ -181,28 +246,34 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int m0 = blockIdx.y * BLOCK_M, n0 = blockIdx.x * BLOCK_N;
+  const uint32_t rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+  const bool leader = (rank == 0);
+  const int m0 = blockIdx.x * BLOCK_M;                       // this CTA's 128 rows (pair = 2 consecutive x)
+  const int n0 = blockIdx.y * BLOCK_N;                       // the (pair) tile's columns
+  const int nb0 = n0 + (int)rank * L::kBRows;                // rows of Wt this CTA stages
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
     for (int s = 0; s < STAGES; s++) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&full_bar[s], 1);   // the leader's producer arrives once; bytes of both CTAs are expected
+      mbar_init(&empty_bar[s], 1);  // one (multicast) tcgen05.commit per use
     }
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   } else if (warp == 1) {
-    tmem_alloc(tmem_ptr, BLOCK_N);
+    if (CTAS == 2) tmem_alloc_pair(tmem_ptr, BLOCK_N);
+    else tmem_alloc(tmem_ptr, BLOCK_N);
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();   // peer barriers must exist before any remote complete_tx / commit
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer (both CTAs of a pair) =====
     if (lane == 0) {
       for (int kb = 0; kb < num_kb; kb++) {
         const int s = kb % STAGES;
@@ -210,33 +281,48 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* a_dst = smem + s * L::kStageBytes;
         uint8_t* b_dst = a_dst + L::kABytes;
-        mbar_expect_tx(&full_bar[s], L::kStageBytes);
-        tma_load_2d(&tmap_a, &full_bar[s], a_dst, kb * BLOCK_K, m0);
-        tma_load_2d(&tmap_b, &full_bar[s], b_dst, kb * BLOCK_K, n0);
+        if (CTAS == 2) {
+          const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);   // leader's barrier
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * L::kStageBytes);
+          tma_load_2d_pair(&tmap_a, bar, a_dst, kb * BLOCK_K, m0);
+          tma_load_2d_pair(&tmap_b, bar, b_dst, kb * BLOCK_K, nb0);
+        } else {
+          mbar_expect_tx(&full_bar[s], L::kStageBytes);
+          tma_load_2d(&tmap_a, &full_bar[s], a_dst, kb * BLOCK_K, m0);
+          tma_load_2d(&tmap_b, &full_bar[s], b_dst, kb * BLOCK_K, nb0);
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    constexpr uint32_t idesc = make_idesc_tf32(BLOCK_N);
-    for (int kb = 0; kb < num_kb; kb++) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
-      mbar_wait(&full_bar[s], ph);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-        const uint64_t a_desc = make_smem_desc(a_addr);
-        const uint64_t b_desc = make_smem_desc(a_addr + L::kABytes);
+    // ===== MMA issuer (leader CTA only for a pair) =====
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_tf32_m(BLOCK_M * CTAS, BLOCK_N);
+      for (int kb = 0; kb < num_kb; kb++) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+          const uint64_t a_desc = make_smem_desc(a_addr);
+          const uint64_t b_desc = make_smem_desc(a_addr + L::kABytes);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
-          // advance 32 bytes of K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-          umma_tf32(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+            // advance 32 bytes of K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+            if (CTAS == 2) umma_tf32_pair(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            else umma_tf32(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
+          if (CTAS == 2) {
+            umma_commit_pair(&empty_bar[s]);                       // frees the slot in both CTAs
+            if (kb == num_kb - 1) umma_commit_pair(tmem_full_bar);  // accumulators complete in both CTAs
+          } else {
+            umma_commit(&empty_bar[s]);
+            if (kb == num_kb - 1) umma_commit(tmem_full_bar);
+          }
         }
-        umma_commit(&empty_bar[s]);                       // smem slot reusable once these MMAs retire
-        if (kb == num_kb - 1) umma_commit(tmem_full_bar);  // accumulator complete
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
@@ -288,10 +374,12 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     tc_fence_before();
   }
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();   // the peer's smem / TMEM must stay alive until the pair is done
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BLOCK_N);
+    if (CTAS == 2) tmem_dealloc_pair(tmem_base, BLOCK_N);
+    else tmem_dealloc(tmem_base, BLOCK_N);
   }
 }
 
@@ -301,7 +389,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct TcLayerCfg {
-  int block_n, stages, epi;
+  int block_n, ctas;   // (pair) tile width and CTAs per tile
 };
 
 struct TcState {
@@ -309,7 +397,7 @@ struct TcState {
   CUtensorMap w_map[3];
   TcLayerCfg cfg[3];
   bool ready = false;
-  // cached A-operand maps keyed by (pointer, K)
+  // cached A-operand maps keyed by (pointer, K, rows)
   struct AMap {
     const void* ptr;
     int K, rows;
@@ -333,20 +421,32 @@ fr_status encode_2d(fr_engine* e, TcState* st, CUtensorMap* map, const void* bas
   return FR_OK;
 }
 
-template <int BLOCK_N, int STAGES, int EPI>
+template <int BLOCK_N, int STAGES, int EPI, int CTAS>
 fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, cudaStream_t st) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+  using L = SmemLayout<BLOCK_N, STAGES, CTAS>;
+  static_assert(L::kDyn <= 227 * 1024, "tile configuration exceeds the 227 KB shared memory of an SM");
+  auto kern = tc_linear_kernel<BLOCK_N, STAGES, EPI, CTAS>;
   static std::atomic<uint64_t> attr_done{0};  // bit d: opt-in smem size set on device d for this instantiation
   const uint64_t bit = 1ull << (e->device & 63);
   if (!(attr_done.load() & bit)) {
-    FR_CUDA(e, cudaFuncSetAttribute(tc_linear_kernel<BLOCK_N, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    L::kDyn));
+    FR_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDyn));
     attr_done.fetch_or(bit);
   }
-  dim3 grid(p.N / BLOCK_N, (p.M + BLOCK_M - 1) / BLOCK_M);
-  tc_linear_kernel<BLOCK_N, STAGES, EPI><<<grid, kThreads, L::kDyn, st>>>(a, b, p);
+  const int m_tiles = (p.M + BLOCK_M * CTAS - 1) / (BLOCK_M * CTAS) * CTAS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(m_tiles, p.N / BLOCK_N, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = L::kDyn;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FR_CUDA(e, cudaLaunchKernelEx(&cfg, kern, a, b, p));
   e->launches++;
-  FR_CUDA(e, cudaGetLastError());
   return FR_OK;
 }
 
@@ -366,6 +466,14 @@ fr_status get_a_map(fr_engine* e, TcState* st, const void* ptr, int K, int rows,
   if (st->a_maps.size() < 256) st->a_maps.push_back(m);
   *out = m.map;
   return FR_OK;
+}
+
+// tile shapes: "N1,N2,N3[,ctas]" e.g. FR_TC_TILES=256,256,256,2 ; layer 3 must be 256 (whole row)
+void parse_tiles(TcLayerCfg cfg[3]) {
+  int n[3] = {256, 256, 256}, ctas = 2;
+  if (const char* env = getenv("FR_TC_TILES")) sscanf(env, "%d,%d,%d,%d", &n[0], &n[1], &n[2], &ctas);
+  for (int k = 0; k < 3; k++) cfg[k] = {n[k], ctas};
+  cfg[2].block_n = 256;
 }
 
 }  // namespace
@@ -391,15 +499,14 @@ fr_status frtc_prepare(fr_engine* e) {
   if (e->dims[3] != 256)
     return fr_fail(e, FR_ERR_UNSUPPORTED, "TF32 path folds the output layer into layer 3 and needs hidden[2] == 256 "
                    "(got %d)", e->dims[3]);
-  // layer 1: N = 1024/2048, 128-wide tiles; layer 2: N = 512, 64-wide tiles (more CTAs); layer 3: whole 256 row.
-  st->cfg[0] = {128, 6, EPI_STORE};
-  st->cfg[1] = {64, 8, EPI_STORE};
-  st->cfg[2] = {256, 4, EPI_DOT};
+  parse_tiles(st->cfg);
   for (int k = 0; k < 3; k++) {
-    if (e->dims[k + 1] % st->cfg[k].block_n)
-      return fr_fail(e, FR_ERR_UNSUPPORTED, "hidden[%d]=%d not a multiple of tile N %d", k, e->dims[k + 1],
-                     st->cfg[k].block_n);
-    fr_status s = encode_2d(e, st, &st->w_map[k], e->d_Wt[k], e->dims[k + 1], e->dims[k], st->cfg[k].block_n);
+    const TcLayerCfg c = st->cfg[k];
+    if ((c.block_n != 128 && c.block_n != 256) || (c.ctas != 1 && c.ctas != 2))
+      return fr_fail(e, FR_ERR_UNSUPPORTED, "tile N %d / ctas %d not built (N in {128,256}, ctas in {1,2})", c.block_n, c.ctas);
+    if (e->dims[k + 1] % c.block_n)
+      return fr_fail(e, FR_ERR_UNSUPPORTED, "hidden[%d]=%d not a multiple of tile N %d", k, e->dims[k + 1], c.block_n);
+    fr_status s = encode_2d(e, st, &st->w_map[k], e->d_Wt[k], e->dims[k + 1], e->dims[k], c.block_n / c.ctas);
     if (s != FR_OK) return s;
   }
   st->ready = true;
@@ -429,14 +536,14 @@ fr_status frtc_layer(fr_engine* e, fr_stream_s* s, int k, const float* in, int B
   p.sigmoid = act ? 1 : 0;
   p.w4 = e->d_W[3];
   p.b4 = act ? e->d_bias[3] : nullptr;
-  if (k == 0) {
-    p.out = s->d_h[0];
-    return launch<128, 6, EPI_STORE>(e, a, st->w_map[0], p, s->stream);
-  }
-  if (k == 1) {
-    p.out = s->d_h[1];
-    return launch<64, 8, EPI_STORE>(e, a, st->w_map[1], p, s->stream);
+  const TcLayerCfg c = st->cfg[k];
+  const CUtensorMap& w = st->w_map[k];
+  cudaStream_t cs = s->stream;
+  if (k < 2) {
+    p.out = s->d_h[k];
+    if (c.ctas == 2) return c.block_n == 256 ? launch<256, 6, EPI_STORE, 2>(e, a, w, p, cs) : launch<128, 8, EPI_STORE, 2>(e, a, w, p, cs);
+    return c.block_n == 256 ? launch<256, 4, EPI_STORE, 1>(e, a, w, p, cs) : launch<128, 6, EPI_STORE, 1>(e, a, w, p, cs);
   }
   p.out = d_scores;
-  return launch<256, 4, EPI_DOT>(e, a, st->w_map[2], p, s->stream);
+  return c.ctas == 2 ? launch<256, 6, EPI_DOT, 2>(e, a, w, p, cs) : launch<256, 4, EPI_DOT, 1>(e, a, w, p, cs);
 }

@@ -18,6 +18,8 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 MODELS3 = ("small", "medium", "large_half")
 TOL = 1e-3
+# FR_TC_TILES: tcgen05 tile width of layers 1..3 and CTAs per tile (1 = cta_group::1, 2 = CTA pair)
+TILES = ("128,128,256,1", "256,256,256,1", "128,128,256,2", "256,256,256,2")
 
 
 def rel_err(got, exp):
@@ -120,10 +122,13 @@ def test_errors_are_reported_not_fatal():
 KAT = {"small": 47244640256.0, "medium": 118111600640.0, "large": 1065151889408.0}
 
 
-@pytest.mark.parametrize("prec", (fleetrec.FR_PREC_FP32, fleetrec.FR_PREC_TF32))
+@pytest.mark.parametrize("prec,tiles", ((fleetrec.FR_PREC_FP32, ""), (fleetrec.FR_PREC_TF32, TILES[0]),
+                                        (fleetrec.FR_PREC_TF32, TILES[1]), (fleetrec.FR_PREC_TF32, TILES[2]),
+                                        (fleetrec.FR_PREC_TF32, TILES[3])))
 @pytest.mark.parametrize("model", ("small", "medium", "large"))
-def test_mlp_all_ones_known_answer(model, prec):
+def test_mlp_all_ones_known_answer(model, prec, tiles, monkeypatch):
     """README.md:7-11: all-ones input and weights -> IN*H1*H2*H3, exact in fp32 and tf32."""
+    monkeypatch.setenv("FR_TC_TILES", tiles or TILES[3])
     cat = catalogue.load(model).with_row_cap(64)
     dims = cat.layer_dims
     eng = fleetrec.Engine(cat, mlp_mode=fleetrec.FR_MLP_LINEAR, precision=prec, max_batch=256)
@@ -235,11 +240,13 @@ def tf32_rna(x):
     return ((b + 0x1000) & 0xFFFFE000).astype(np.uint32).view(np.float32)
 
 
+@pytest.mark.parametrize("tiles", TILES)
 @pytest.mark.parametrize("k", (0, 1, 2))
 @pytest.mark.parametrize("B", (128, 300))
-def test_tf32_single_layer_vs_numpy(k, B):
+def test_tf32_single_layer_vs_numpy(k, B, tiles, monkeypatch):
     """Each tcgen05 GEMM configuration alone (128x128, 128x64, 128x256+dot tiles):
     inputs pre-rounded to TF32, so the only difference to float64 is summation order."""
+    monkeypatch.setenv("FR_TC_TILES", tiles)                   # tile width per layer, CTAs per tile
     cat = catalogue.load("medium").with_row_cap(64)            # K = 880: exercises the K tail (27.5 slices)
     dims = cat.layer_dims
     W, b = oracle.make_weights(dims, seed=5)
