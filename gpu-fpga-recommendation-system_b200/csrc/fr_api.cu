@@ -5,8 +5,10 @@
 //   FPGA/host/embedding_47_krnl/host.cpp:324-761  (allocate + init tables, migrate, launch)
 //   GPU/final_network_cublasLt_1_node_no_FIFO_scatter/cuda_server.c:101-183,346-354,406-495
 //                                                  (per-worker buffers + stream, weights H2D, batch loop)
+#include <limits.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "fr_common.h"
@@ -104,6 +106,8 @@ static fr_status alloc_stream(fr_engine* e, fr_stream_s** out) {
 static void free_stream(fr_stream_s* s) {
   if (!s) return;
   if (s->stream) cudaStreamSynchronize(s->stream);
+  for (fr_stream_s::Graph& g : s->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   cudaFree(s->d_idx);
   cudaFree(s->d_x);
   for (int k = 0; k < 3; k++) cudaFree(s->d_h[k]);
@@ -150,6 +154,7 @@ extern "C" fr_status fr_create(const fr_model_desc* desc, int n_gpus, const int*
   e->mlp_mode = desc->mlp_mode;
   e->precision = desc->precision;
   e->max_batch = desc->max_batch;
+  if (const char* env = getenv("FR_GRAPHS")) e->use_graphs = atoi(env) != 0;
   e->tables.resize(desc->n_tables);
   for (int t = 0; t < desc->n_tables; t++) {
     e->tables[t].rows = desc->tables[t].rows;
@@ -186,6 +191,8 @@ extern "C" void fr_destroy(fr_engine* e) {
     if (e->peers[r].ipc && e->peers[r].concat) cudaIpcCloseMemHandle(e->peers[r].concat);
   cudaFree(e->d_peer_ptrs);
   cudaFree(e->d_xchg);
+  cudaFree(e->d_epoch);
+  if (e->h_shard_err) cudaFreeHost(e->h_shard_err);
   delete e;
 }
 
@@ -412,22 +419,93 @@ static fr_status emit_scores(fr_engine* e, fr_stream_s* s, float* scores, int B,
   return FR_OK;
 }
 
-extern "C" fr_status fr_infer(fr_engine* e, const int32_t* idx, int B, float* scores, fr_stream s) {
-  fr_status st = prep(e, &s, B, true, true);
-  if (st != FR_OK) return st;
-  if (B > 0 && !scores) return fr_fail(e, FR_ERR_INVALID, "null scores");
+// Enqueue one batch on the worker's stream: [H2D idx] -> gather -> MLP launches -> [D2H scores].
+static fr_status infer_enqueue(fr_engine* e, fr_stream_s* s, const int32_t* idx, int B, float* scores) {
   const int32_t* d_idx = nullptr;
-  if ((st = stage_idx(e, s, idx, B, &d_idx)) != FR_OK) return st;
+  fr_status st = stage_idx(e, s, idx, B, &d_idx);
+  if (st != FR_OK) return st;
   if ((st = frk_gather(e, d_idx, B, s->d_x, e->precision == FR_PREC_TF32, s->stream)) != FR_OK) return st;
   float* d_scores = (B > 0 && is_device_ptr(scores)) ? scores : s->d_scores;
   if ((st = run_mlp(e, s, s->d_x, B, d_scores)) != FR_OK) return st;
   return emit_scores(e, s, scores, B, d_scores);
 }
 
+// device memory or page-locked host memory: the only buffers a captured memcpy node may reference
+static bool is_capturable_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged || a.type == cudaMemoryTypeHost;
+}
+
+extern "C" fr_status fr_infer(fr_engine* e, const int32_t* idx, int B, float* scores, fr_stream s) {
+  fr_status st = prep(e, &s, B, true, true);
+  if (st != FR_OK) return st;
+  if (B == 0) return FR_OK;
+  if (!idx || !scores) return fr_fail(e, FR_ERR_INVALID, "null idx/scores");
+  if (e->world > 1) return fr_fail(e, FR_ERR_STATE, "engine is table-sharded over %d ranks: use fr_shard_infer", e->world);
+  if (!e->use_graphs) return infer_enqueue(e, s, idx, B, scores);
+
+  // The batch is 4-5 tiny launches; issued one by one the host (~5 us per launch) is the bottleneck,
+  // so a buffer combination seen before is replayed as one CUDA graph.
+  fr_stream_s::Graph* g = nullptr;
+  for (fr_stream_s::Graph& c : s->graphs)
+    if (c.idx == idx && c.scores == scores && c.B == B && c.mode == e->mlp_mode && c.prec == e->precision) g = &c;
+  if (g && g->exec) {
+    FR_CUDA(e, cudaGraphLaunch(g->exec, s->stream));
+    e->launches += g->launches;
+    return FR_OK;
+  }
+  if (!g) {
+    if (s->graphs.size() >= 512 || !is_capturable_ptr(idx) || !is_capturable_ptr(scores))
+      return infer_enqueue(e, s, idx, B, scores);
+    s->graphs.push_back({idx, scores, B, e->mlp_mode, e->precision, 0, 0, nullptr});
+    g = &s->graphs.back();
+  }
+  if (g->seen < 1) {  // first sighting: plain launches (also warms attribute / tensor-map caches)
+    g->seen++;
+    return infer_enqueue(e, s, idx, B, scores);
+  }
+  if (g->seen == INT_MAX) return infer_enqueue(e, s, idx, B, scores);  // capture failed before
+  const int64_t l0 = e->launches.load();
+  cudaError_t ce = cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal);
+  if (ce != cudaSuccess) {
+    cudaGetLastError();
+    g->seen = INT_MAX;
+    return infer_enqueue(e, s, idx, B, scores);
+  }
+  st = infer_enqueue(e, s, idx, B, scores);
+  cudaGraph_t graph = nullptr;
+  ce = cudaStreamEndCapture(s->stream, &graph);
+  const int captured = (int)(e->launches.load() - l0);
+  e->launches -= captured;  // nothing ran yet
+  if (st != FR_OK || ce != cudaSuccess || !graph) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    g->seen = INT_MAX;
+    return infer_enqueue(e, s, idx, B, scores);
+  }
+  ce = cudaGraphInstantiate(&g->exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) {
+    cudaGetLastError();
+    g->exec = nullptr;
+    g->seen = INT_MAX;
+    return infer_enqueue(e, s, idx, B, scores);
+  }
+  g->launches = captured;
+  FR_CUDA(e, cudaGraphLaunch(g->exec, s->stream));
+  e->launches += g->launches;
+  return FR_OK;
+}
+
 extern "C" fr_status fr_gather_only(fr_engine* e, const int32_t* idx, int B, float* concat, fr_stream s) {
   fr_status st = prep(e, &s, B, true, false);
   if (st != FR_OK) return st;
   if (B > 0 && !concat) return fr_fail(e, FR_ERR_INVALID, "null concat");
+  if (e->world > 1) return fr_fail(e, FR_ERR_STATE, "engine is table-sharded over %d ranks: use fr_shard_gather_push", e->world);
   const int32_t* d_idx = nullptr;
   if ((st = stage_idx(e, s, idx, B, &d_idx)) != FR_OK) return st;
   if (B == 0) return FR_OK;
@@ -515,13 +593,17 @@ extern "C" fr_status fr_time_kernels(fr_engine* e, const int32_t* idx, int B, in
   const bool round = e->precision == FR_PREC_TF32;
   // every kernel is timed alone, back to back `reps` times, events on its own stream
   for (int pass = 0; pass < 2; pass++) {  // pass 0 = warm-up
-    FR_CUDA(e, cudaEventRecord(e0, s->stream));
-    for (int r = 0; r < reps; r++)
-      if ((st = frk_gather(e, d_idx, B, s->d_x, round, s->stream)) != FR_OK) return st;
-    FR_CUDA(e, cudaEventRecord(e1, s->stream));
-    FR_CUDA(e, cudaEventSynchronize(e1));
-    FR_CUDA(e, cudaEventElapsedTime(&ms5[0], e0, e1));
     const float* in = s->d_x;
+    if (e->world == 1) {
+      FR_CUDA(e, cudaEventRecord(e0, s->stream));
+      for (int r = 0; r < reps; r++)
+        if ((st = frk_gather(e, d_idx, B, s->d_x, round, s->stream)) != FR_OK) return st;
+      FR_CUDA(e, cudaEventRecord(e1, s->stream));
+      FR_CUDA(e, cudaEventSynchronize(e1));
+      FR_CUDA(e, cudaEventElapsedTime(&ms5[0], e0, e1));
+    } else {
+      in = e->d_xchg;  // sharded: the lookup needs every rank; time the MLP on the last exchanged batch
+    }
     for (int k = 0; k < mlp_steps(e); k++) {
       const float* out = nullptr;
       FR_CUDA(e, cudaEventRecord(e0, s->stream));
@@ -539,12 +621,20 @@ extern "C" fr_status fr_time_kernels(fr_engine* e, const int32_t* idx, int B, in
 
 // ---------------------------------------------------------------------------
 // Sharding: table-wise model parallel, push all-to-all over NVLink.
+//
+// Exchange region of one rank (ONE cudaMalloc, exported through CUDA IPC):
+//   [ concat buffer 0 | concat buffer 1 | flags: int32[world] ]
+// concat buffer p holds this rank's B_global/world items of the step with parity p; flags[r] is
+// the last step rank r has finished pushing for (written by rank r over NVLink).
+static size_t xchg_buf_floats(const fr_engine* e) { return (size_t)(e->max_batch / e->world) * e->D; }
+
 extern "C" fr_status fr_shard_init(fr_engine* e, int rank, int world, const int* owner) {
   if (!e) return fr_fail(nullptr, FR_ERR_INVALID, "null engine");
   if (world < 1 || rank < 0 || rank >= world || !owner) return fr_fail(e, FR_ERR_INVALID, "fr_shard_init: rank/world/owner");
   for (const FrTable& t : e->tables)
     if (t.d) return fr_fail(e, FR_ERR_STATE, "fr_shard_init must precede table loading");
   if (e->max_batch % world) return fr_fail(e, FR_ERR_INVALID, "max_batch %d not divisible by world %d", e->max_batch, world);
+  if (e->d_xchg) return fr_fail(e, FR_ERR_STATE, "fr_shard_init called twice");
   e->rank = rank;
   e->world = world;
   e->owner.assign(owner, owner + e->tables.size());
@@ -553,10 +643,18 @@ extern "C" fr_status fr_shard_init(fr_engine* e, int rank, int world, const int*
     e->tables[t].resident = (owner[t] == -1 || owner[t] == rank);
   }
   FR_CUDA(e, cudaSetDevice(e->device));
-  if (!e->d_xchg) FR_CUDA(e, cudaMalloc(&e->d_xchg, (size_t)(e->max_batch / world) * e->D * sizeof(float)));
+  const size_t bytes = 2 * xchg_buf_floats(e) * sizeof(float) + (size_t)world * sizeof(int);
+  FR_CUDA(e, cudaMalloc(&e->d_xchg, bytes));
+  FR_CUDA(e, cudaMemsetAsync(e->d_xchg, 0, bytes, e->default_stream->stream));
+  FR_CUDA(e, cudaMalloc(&e->d_epoch, sizeof(int)));
+  FR_CUDA(e, cudaMemsetAsync(e->d_epoch, 0, sizeof(int), e->default_stream->stream));
+  FR_CUDA(e, cudaHostAlloc(&e->h_shard_err, sizeof(int), cudaHostAllocMapped));
+  *e->h_shard_err = 0;
+  FR_CUDA(e, cudaStreamSynchronize(e->default_stream->stream));
   e->peers.assign(world, FrPeer());
   e->peers[rank].concat = e->d_xchg;
   e->chunks_dirty = true;
+  e->shard_step = 0;
   return FR_OK;
 }
 
@@ -619,15 +717,22 @@ extern "C" fr_status fr_shard_attach_local(fr_engine* e, fr_engine* const* peers
   return upload_peers(e);
 }
 
+static fr_status shard_check(fr_engine* e, int B_global) {
+  if (!e->d_xchg) return fr_fail(e, FR_ERR_STATE, "fr_shard_init first");
+  if (!e->d_peer_ptrs) return fr_fail(e, FR_ERR_STATE, "exchange buffers not attached (fr_shard_import)");
+  if (B_global % e->world) return fr_fail(e, FR_ERR_INVALID, "B_global %d not divisible by world %d", B_global, e->world);
+  return FR_OK;
+}
+
+// Two-phase form (the host barriers all ranks between the calls); parity 0 buffer only.
 extern "C" fr_status fr_shard_gather_push(fr_engine* e, const int32_t* idx, int B_global, fr_stream s) {
   fr_status st = prep(e, &s, B_global, true, false);
   if (st != FR_OK) return st;
-  if (!e->d_peer_ptrs) return fr_fail(e, FR_ERR_STATE, "exchange buffers not attached (fr_shard_import)");
-  if (B_global % e->world) return fr_fail(e, FR_ERR_INVALID, "B_global %d not divisible by world %d", B_global, e->world);
+  if ((st = shard_check(e, B_global)) != FR_OK) return st;
   const int32_t* d_idx = nullptr;
   if ((st = stage_idx(e, s, idx, B_global, &d_idx)) != FR_OK) return st;
   if (B_global == 0) return FR_OK;
-  return frk_gather_push(e, d_idx, B_global, s->stream);
+  return frk_gather_push(e, d_idx, B_global, 0, s->stream);
 }
 
 extern "C" fr_status fr_shard_mlp(fr_engine* e, int B_global, float* scores_local, fr_stream s) {
@@ -648,9 +753,45 @@ extern "C" fr_status fr_shard_read_concat(fr_engine* e, int B_global, float* con
   if (!s) s = e->default_stream;
   FR_CUDA(e, cudaSetDevice(e->device));
   const int Bl = B_global / e->world;
-  FR_CUDA(e, cudaMemcpyAsync(concat_local, e->d_xchg, (size_t)Bl * e->D * sizeof(float), cudaMemcpyDefault, s->stream));
+  const float* src = e->d_xchg + (size_t)(e->shard_step & 1) * xchg_buf_floats(e);  // last step's parity
+  FR_CUDA(e, cudaMemcpyAsync(concat_local, src, (size_t)Bl * e->D * sizeof(float), cudaMemcpyDefault, s->stream));
   return FR_OK;
 }
+
+// One-call sharded step with device-side synchronisation (no host barrier, no NCCL on the data
+// path): push my tables' pieces for the global batch into the owners' buffers of this step's
+// parity -> publish "rank r finished step n" into every peer's flag array -> wait until all
+// ranks have published step n -> MLP over my B_global/world items.  Every rank must call it
+// the same number of times with the same global batch.  Not captured into a graph: the step
+// number is a launch argument.
+static fr_status shard_infer_enqueue(fr_engine* e, fr_stream_s* s, const int32_t* idx, int B_global, float* scores,
+                                     int step) {
+  const int32_t* d_idx = nullptr;
+  fr_status st = stage_idx(e, s, idx, B_global, &d_idx);
+  if (st != FR_OK) return st;
+  const int parity = step & 1;
+  if ((st = frk_gather_push(e, d_idx, B_global, parity, s->stream)) != FR_OK) return st;
+  if ((st = frk_shard_signal_wait(e, step, s->stream)) != FR_OK) return st;
+  const int Bl = B_global / e->world;
+  float* d_scores = is_device_ptr(scores) ? scores : s->d_scores;
+  const float* x = e->d_xchg + (size_t)parity * xchg_buf_floats(e);
+  if ((st = run_mlp(e, s, x, Bl, d_scores)) != FR_OK) return st;
+  return emit_scores(e, s, scores, Bl, d_scores);
+}
+
+extern "C" fr_status fr_shard_infer(fr_engine* e, const int32_t* idx, int B_global, float* scores_local, fr_stream s) {
+  fr_status st = prep(e, &s, B_global, true, true);
+  if (st != FR_OK) return st;
+  if ((st = shard_check(e, B_global)) != FR_OK) return st;
+  if (B_global == 0) return FR_OK;
+  if (!idx || !scores_local) return fr_fail(e, FR_ERR_INVALID, "null idx/scores");
+  if (s != e->default_stream && !e->streams.empty() && s != e->streams[0])
+    return fr_fail(e, FR_ERR_UNSUPPORTED, "sharded steps are ordered: use one worker stream for fr_shard_infer");
+  if (*e->h_shard_err) return fr_fail(e, FR_ERR_STATE, "a previous sharded step timed out waiting for a peer rank");
+  const int step = ++e->shard_step;
+  return shard_infer_enqueue(e, s, idx, B_global, scores_local, step);
+}
+
 
 // ---------------------------------------------------------------------------
 extern "C" int64_t fr_merge_index(int64_t iA, int64_t iB, int64_t rowsB) { return iA * rowsB + iB; }

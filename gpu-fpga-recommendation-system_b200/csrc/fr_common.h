@@ -38,6 +38,17 @@ struct fr_stream_s {
   float* d_h[3] = {nullptr, nullptr, nullptr};  // [max_batch][hidden k]
   float* d_scores = nullptr;  // [max_batch]
   cudaEvent_t ev[2] = {nullptr, nullptr};
+  // One batch = H2D? + gather + 3..4 GEMM launches + D2H?: replayed as ONE cudaGraphLaunch once a
+  // (idx, scores, B, mode) combination has been seen twice on this worker (launch-bound otherwise).
+  struct Graph {
+    const void* idx;
+    const void* scores;
+    int B, mode, prec;
+    int seen;               // direct (un-captured) runs so far
+    int launches;           // kernels inside the graph
+    cudaGraphExec_t exec;   // null until captured
+  };
+  std::vector<Graph> graphs;
 };
 
 struct FrPeer {
@@ -56,6 +67,7 @@ struct fr_engine {
   int mlp_mode = FR_MLP_BIAS_RELU_SIGMOID;
   int precision = FR_PREC_TF32;
   int max_batch = 0;
+  bool use_graphs = true;  // FR_GRAPHS=0 disables CUDA-graph replay of fr_infer
 
   std::vector<FrTable> tables;
   FrChunk* d_chunks = nullptr;  // [D/4]
@@ -82,6 +94,9 @@ struct fr_engine {
   int* d_repl_ids = nullptr;     // pieces of replicated tables (local items only)
   int n_repl = 0;
   bool shard_lists_built = false;
+  int* d_epoch = nullptr;        // device copy of the last published step (debug / introspection)
+  int* h_shard_err = nullptr;    // pinned+mapped: set to 1 by the wait kernel on time-out
+  int shard_step = 0;            // host-side step counter of fr_shard_infer
 
   std::atomic<int64_t> launches{0};
   mutable std::string err;
@@ -109,7 +124,9 @@ inline cudaError_t fr_h2d(fr_engine* e, void* dst, const void* src, size_t bytes
 // ---- kernels (each returns after enqueueing; bumps e->launches) -----------
 fr_status frk_upload_chunks(fr_engine* e);
 fr_status frk_gather(fr_engine* e, const int32_t* d_idx, int B, float* d_out, bool round_tf32, cudaStream_t st);
-fr_status frk_gather_push(fr_engine* e, const int32_t* d_idx, int B_global, cudaStream_t st);
+fr_status frk_gather_push(fr_engine* e, const int32_t* d_idx, int B_global, int parity, cudaStream_t st);
+// publish "this rank finished pushing step `step`" to every peer, then wait for all peers' flags
+fr_status frk_shard_signal_wait(fr_engine* e, int step, cudaStream_t st);
 fr_status frk_fill_reference(fr_engine* e, float* d, int64_t rows, int dim, int64_t debug_rows, cudaStream_t st);
 fr_status frk_fill_hash(fr_engine* e, float* d, uint32_t seed, int table, int64_t rows, int dim, cudaStream_t st);
 fr_status frk_merge(fr_engine* e, const float* A, int64_t rowsA, int dimA, const float* B, int64_t rowsB, int dimB,

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) gather_concat_kernel(const FrChunk* __res
                                                             const int32_t* __restrict__ idx, int T, int b_begin,
                                                             int b_end, float4* __restrict__ out4,
                                                             float4* const* __restrict__ peer_out, int C,
-                                                            int items_per_rank) {
+                                                            int items_per_rank, long long peer_off4) {
   const int ci = blockIdx.x * blockDim.x + threadIdx.x;
   if (ci >= n_chunks) return;
   const int c = chunk_ids ? chunk_ids[ci] : ci;
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) gather_concat_kernel(const FrChunk* __res
     }
     if (PUSH) {
       const int r = b / items_per_rank;
-      peer_out[r][(size_t)(b - r * items_per_rank) * C + c] = o;
+      peer_out[r][peer_off4 + (size_t)(b - r * items_per_rank) * C + c] = o;
     } else {
       out4[(size_t)b * C + c] = o;
     }
@@ -136,7 +136,7 @@ int grid_for(int64_t n, int block, int sm_count) {
 
 template <bool ROUND, bool PUSH>
 void launch_gather(const fr_engine* e, const int* d_ids, int n_chunks, const int32_t* d_idx, int b_begin, int b_end,
-                   float4* out4, float4* const* peers, int items_per_rank, cudaStream_t st) {
+                   float4* out4, float4* const* peers, int items_per_rank, cudaStream_t st, long long peer_off4 = 0) {
   const int C = e->D / 4;
   int bx = (n_chunks + 31) / 32 * 32;
   if (bx > 128) bx = 128;
@@ -145,7 +145,7 @@ void launch_gather(const fr_engine* e, const int* d_ids, int n_chunks, const int
   dim3 block(bx, by);
   dim3 grid((n_chunks + bx - 1) / bx, (n_items + by * kItems - 1) / (by * kItems));
   gather_concat_kernel<ROUND, PUSH><<<grid, block, 0, st>>>(e->d_chunks, d_ids, n_chunks, d_idx, (int)e->tables.size(),
-                                                            b_begin, b_end, out4, peers, C, items_per_rank);
+                                                            b_begin, b_end, out4, peers, C, items_per_rank, peer_off4);
 }
 
 }  // namespace
@@ -253,7 +253,7 @@ static fr_status build_shard_lists(fr_engine* e) {
   return FR_OK;
 }
 
-fr_status frk_gather_push(fr_engine* e, const int32_t* d_idx, int B_global, cudaStream_t st) {
+fr_status frk_gather_push(fr_engine* e, const int32_t* d_idx, int B_global, int parity, cudaStream_t st) {
   if (!e->shard_lists_built) {
     std::lock_guard<std::mutex> g(e->mu);
     if (!e->shard_lists_built) {
@@ -263,20 +263,62 @@ fr_status frk_gather_push(fr_engine* e, const int32_t* d_idx, int B_global, cuda
   }
   const int per = B_global / e->world;
   const bool round = (e->precision == FR_PREC_TF32);
+  // concat buffer `parity` of every rank's exchange region (same layout on all ranks)
+  const long long off4 = (long long)parity * (e->max_batch / e->world) * (e->D / 4);
   float4* const* peers = reinterpret_cast<float4* const*>(e->d_peer_ptrs);
   if (e->n_owned) {
-    if (round) launch_gather<true, true>(e, e->d_owned_ids, e->n_owned, d_idx, 0, B_global, nullptr, peers, per, st);
-    else launch_gather<false, true>(e, e->d_owned_ids, e->n_owned, d_idx, 0, B_global, nullptr, peers, per, st);
+    if (round) launch_gather<true, true>(e, e->d_owned_ids, e->n_owned, d_idx, 0, B_global, nullptr, peers, per, st, off4);
+    else launch_gather<false, true>(e, e->d_owned_ids, e->n_owned, d_idx, 0, B_global, nullptr, peers, per, st, off4);
     e->launches++;
   }
   if (e->n_repl) {
-    // local items only, written into this rank's own exchange buffer (row b - rank*per)
-    float4* own = reinterpret_cast<float4*>(e->d_xchg) - (size_t)e->rank * per * (e->D / 4);
+    // local items only, written into this rank's own buffer (row b - rank*per)
+    float4* own = reinterpret_cast<float4*>(e->d_xchg) + off4 - (size_t)e->rank * per * (e->D / 4);
     const int b0 = e->rank * per, b1 = (e->rank + 1) * per;
     if (round) launch_gather<true, false>(e, e->d_repl_ids, e->n_repl, d_idx, b0, b1, own, nullptr, 1, st);
     else launch_gather<false, false>(e, e->d_repl_ids, e->n_repl, d_idx, b0, b1, own, nullptr, 1, st);
     e->launches++;
   }
+  FR_CUDA(e, cudaGetLastError());
+  return FR_OK;
+}
+
+// Device-side step barrier of the sharded path.  Flags live behind the two concat buffers of
+// every rank's exchange region: flags[r] = last step rank r finished pushing.
+namespace {
+__global__ void shard_signal_wait_kernel(float* const* __restrict__ peer_base, long long flags_off_floats, int rank,
+                                         int world, int step, int* epoch, int* err, long long timeout_cycles) {
+  const int t = threadIdx.x;
+  // all stores of the preceding push kernel(s) are complete (stream order); make them visible
+  // system-wide before the flag that announces them
+  __threadfence_system();
+  if (t < world) {
+    int* f = reinterpret_cast<int*>(peer_base[t] + flags_off_floats) + rank;
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f), "r"(step) : "memory");
+  }
+  if (t == 0) *epoch = step;
+  if (t < world) {
+    const int* mine = reinterpret_cast<const int*>(peer_base[rank] + flags_off_floats) + t;
+    const long long t0 = clock64();
+    int v;
+    do {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if (v < step && clock64() - t0 > timeout_cycles) {
+        *reinterpret_cast<volatile int*>(err) = 1;   // surfaced by the next fr_shard_infer / fr_sync
+        break;
+      }
+    } while (v < step);
+  }
+}
+}  // namespace
+
+fr_status frk_shard_signal_wait(fr_engine* e, int step, cudaStream_t st) {
+  const long long flags_off = 2ll * (e->max_batch / e->world) * e->D;
+  int* d_err = nullptr;
+  FR_CUDA(e, cudaHostGetDevicePointer(&d_err, e->h_shard_err, 0));
+  shard_signal_wait_kernel<<<1, 32, 0, st>>>(e->d_peer_ptrs, flags_off, e->rank, e->world, step, e->d_epoch, d_err,
+                                             4000000000ll /* ~2 s at 1.9 GHz */);
+  e->launches++;
   FR_CUDA(e, cudaGetLastError());
   return FR_OK;
 }

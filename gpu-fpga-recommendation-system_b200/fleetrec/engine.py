@@ -235,6 +235,10 @@ class Engine:
     def shard_mlp(self, B_global, scores, worker=None):
         self._chk(self._L.fr_shard_mlp(self._h, B_global, _ptr(scores), worker._h if worker else None))
 
+    def shard_infer(self, idx, B_global, scores, worker=None):
+        """One-call sharded step (device-side sync); scores: [B_global/world]."""
+        self._chk(self._L.fr_shard_infer(self._h, _ptr(idx), B_global, _ptr(scores), worker._h if worker else None))
+
     def shard_read_concat(self, B_global, worker=None):
         out = np.empty((B_global // self.world, self.model.concat_floats), np.float32)
         self._chk(self._L.fr_shard_read_concat(self._h, B_global, out.ctypes.data, worker._h if worker else None))

@@ -181,6 +181,13 @@ fr_status fr_shard_attach_local(fr_engine* e, fr_engine* const* peers);
  * has barriered all ranks): MLP over the local items, scores [B_global/world]. */
 fr_status fr_shard_gather_push(fr_engine* e, const int32_t* idx, int B_global, fr_stream s);
 fr_status fr_shard_mlp(fr_engine* e, int B_global, float* scores_local, fr_stream s);
+/* The same step as ONE asynchronous call with device-side synchronisation: push ->
+ * publish a per-rank step flag into every peer's exchange region -> spin until all
+ * ranks have published this step -> MLP.  No host barrier, no NCCL on the data path.
+ * Every rank must issue the same sequence of calls with the same global batch.
+ * world <= 32.  A peer that never arrives makes the wait give up after ~2 s and the
+ * next call return FR_ERR_STATE. */
+fr_status fr_shard_infer(fr_engine* e, const int32_t* idx, int B_global, float* scores_local, fr_stream s);
 /* Local concat buffer after the exchange (parity hook), [B_global/world][concat_floats]. */
 fr_status fr_shard_read_concat(fr_engine* e, int B_global, float* concat_local, fr_stream s);
 

@@ -264,3 +264,37 @@ def test_tf32_single_layer_vs_numpy(k, B, tiles, monkeypatch):
         got = eng.layer_only(k, x, 1)
         assert rel_err(got, s.astype(np.float32)) <= 2e-4
     eng.close()
+
+
+def test_infer_graph_replay_matches_direct():
+    """fr_infer replays a CUDA graph from the 2nd call on for the same (idx, scores) buffers:
+    new index CONTENTS in the same device / pinned buffers must give new, correct scores."""
+    import torch
+    cat = catalogue.load("small").with_row_cap(20000)
+    dims = cat.layer_dims
+    tables = oracle.make_tables(cat, "hash", seed=3)
+    W, b = oracle.make_weights(dims, seed=42)
+    eng = fleetrec.Engine(cat, max_batch=512)
+    eng.load_tables(tables)
+    eng.load_mlp(W, b)
+    w = fleetrec.Worker(eng)
+    B = 512
+    for kind in ("device", "pinned"):
+        idx_buf = torch.empty((B, 47), dtype=torch.int32, device="cuda") if kind == "device" else \
+            torch.empty((B, 47), dtype=torch.int32).pin_memory()
+        sc_buf = torch.empty(B, dtype=torch.float32, device="cuda") if kind == "device" else \
+            torch.empty(B, dtype=torch.float32).pin_memory()
+        l0 = eng.launch_count()
+        for it in range(4):
+            idx = oracle.zipf_indices(cat, B, seed=100 + it)
+            idx_buf.copy_(torch.from_numpy(idx))
+            torch.cuda.synchronize()
+            eng.infer_async(idx_buf if kind == "device" else idx_buf.numpy(),
+                            sc_buf if kind == "device" else sc_buf.numpy(), B, w)
+            eng.sync(w)
+            got = sc_buf.cpu().numpy() if kind == "device" else sc_buf.numpy().copy()
+            exp = oracle.mlp(oracle.gather(cat, tables, idx), dims, W, b, mode=1)
+            assert rel_err(got, exp) <= TOL, (kind, it)
+        assert eng.launch_count() - l0 == 4 * 4          # gather + 3 GEMM launches per batch, replayed or not
+    w.close()
+    eng.close()
