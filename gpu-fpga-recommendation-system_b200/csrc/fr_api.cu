@@ -155,6 +155,7 @@ extern "C" fr_status fr_create(const fr_model_desc* desc, int n_gpus, const int*
   e->precision = desc->precision;
   e->max_batch = desc->max_batch;
   if (const char* env = getenv("FR_GRAPHS")) e->use_graphs = atoi(env) != 0;
+  if (const char* env = getenv("FR_PDL")) e->use_pdl = atoi(env) != 0;
   e->tables.resize(desc->n_tables);
   for (int t = 0; t < desc->n_tables; t++) {
     e->tables[t].rows = desc->tables[t].rows;

@@ -68,6 +68,7 @@ struct fr_engine {
   int precision = FR_PREC_TF32;
   int max_batch = 0;
   bool use_graphs = true;  // FR_GRAPHS=0 disables CUDA-graph replay of fr_infer
+  bool use_pdl = true;     // FR_PDL=0: no programmatic dependent launch between the kernels of a batch
 
   std::vector<FrTable> tables;
   FrChunk* d_chunks = nullptr;  // [D/4]

@@ -62,6 +62,12 @@ __global__ void __launch_bounds__(256) gather_concat_kernel(const FrChunk* __res
 #pragma unroll
   for (int i = 0; i < kItems; i++)  // 64-bit addressing: 100 M rows x 128 B = 12.8 GB tables
     v[i] = ld_row16(ch.base + row[i] * ch.stride4 + ch.col4);
+  // Programmatic dependent launch: indices and tables are not written by the kernels of the
+  // preceding batch, so everything above overlaps its tail; the concat buffer is (the first MLP
+  // layer of the previous batch read it), so the stores wait for the grid dependency.  Both
+  // instructions are no-ops when the launch carries no programmatic attribute.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < kItems; i++) {
     const int b = b0 + i;
@@ -144,8 +150,17 @@ void launch_gather(const fr_engine* e, const int* d_ids, int n_chunks, const int
   const int n_items = b_end - b_begin;
   dim3 block(bx, by);
   dim3 grid((n_chunks + bx - 1) / bx, (n_items + by * kItems - 1) / (by * kItems));
-  gather_concat_kernel<ROUND, PUSH><<<grid, block, 0, st>>>(e->d_chunks, d_ids, n_chunks, d_idx, (int)e->tables.size(),
-                                                            b_begin, b_end, out4, peers, C, items_per_rank, peer_off4);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (e->use_pdl && !PUSH) ? 1 : 0;   // the sharded push is ordered by its own flag kernel
+  cudaLaunchKernelEx(&cfg, gather_concat_kernel<ROUND, PUSH>, (const FrChunk*)e->d_chunks, d_ids, n_chunks, d_idx,
+                     (int)e->tables.size(), b_begin, b_end, out4, peers, C, items_per_rank, peer_off4);
 }
 
 }  // namespace

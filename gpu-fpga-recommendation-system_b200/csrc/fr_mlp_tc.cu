@@ -141,11 +141,6 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 
-// kind::tf32 instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=n.
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-}
-
 // ---- cluster helpers (2-CTA pairs) --------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -201,8 +196,37 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
       : "memory");
 }
 
-// CTAS = 1: one CTA owns a 128 x BLOCK_N tile.  CTAS = 2: a CTA pair (cluster of 2 along M) owns a
-// 256 x BLOCK_N tile; each CTA stages its own 128 rows of A and its own BLOCK_N/2 rows of B, so per
+// ---- TMA store / programmatic dependent launch ----------------------------------
+// smem (128B-swizzled box) -> global; completion tracked by this thread's bulk async-groups.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most N of this thread's store groups may still be READING their smem source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// PDL: block until the preceding kernel of the stream has completed and its writes are visible
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// PDL: the next kernel of the stream may start its prologue now
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+
+constexpr int kMaxN = 2048;          // widest layer whose bias vector is staged in smem (large model H1)
+constexpr int kStoreBoxRows = 32;    // TMA store box: one epilogue warp's 32 rows x 32 fp32 columns
+constexpr int kStoreBufBytes = kStoreBoxRows * BLOCK_K * 4;   // 4 KB, 128B-swizzled
+
+// CTAS = 1: one CTA owns 128 x BLOCK_N tiles.  CTAS = 2: a CTA pair (cluster of 2 along M) owns
+// 256 x BLOCK_N tiles; each CTA stages its own 128 rows of A and its own BLOCK_N/2 rows of B, so per
 // SM the smem fill per MMA cycle halves for B -- the point of cta_group::2 for 4-byte operands.
 template <int BLOCK_N, int STAGES, int CTAS>
 struct SmemLayout {
@@ -210,19 +234,23 @@ struct SmemLayout {
   static constexpr int kBRows = BLOCK_N / CTAS;
   static constexpr int kBBytes = kBRows * BLOCK_K * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kAuxOff = STAGES * kStageBytes;            // bias[BLOCK_N], w4[BLOCK_N]
-  static constexpr int kBarOff = kAuxOff + 2 * BLOCK_N * 4;
-  static constexpr int kTotal = kBarOff + (2 * STAGES + 1) * 8 + 16;
+  static constexpr int kStoreOff = STAGES * kStageBytes;          // 4 epilogue warps x 2 store buffers
+  static constexpr int kAuxOff = kStoreOff + 4 * 2 * kStoreBufBytes;   // bias[kMaxN], w4[256]
+  static constexpr int kBarOff = kAuxOff + (kMaxN + 256) * 4;
+  static constexpr int kNumBars = 2 * STAGES + 4;                 // full, empty, tmem_full[2], tmem_empty[2]
+  static constexpr int kTotal = kBarOff + kNumBars * 8 + 16;
   static constexpr int kDyn = kTotal + 1024;                      // slack for manual 1024-B alignment
+  static constexpr int kTmemCols = 2 * BLOCK_N;                   // two accumulator stages
 };
 
 struct TcParams {
   const float* bias;   // [N] or null
-  float* out;          // EPI_STORE: Y [M][N]; EPI_DOT: scores [M]
+  float* out;          // EPI_DOT: scores [M]  (EPI_STORE writes through tmap_out)
   const float* w4;     // EPI_DOT: output-layer weights [N]
   const float* b4;     // EPI_DOT: output-layer bias [1] or null
   int M, N, K;
   int relu, sigmoid;
+  int pdl;             // launched with programmatic stream serialization
 };
 
 // kind::tf32 instruction descriptor: D=f32, A=B=tf32, both K-major, M = 128*CTAS, N = n.
@@ -230,156 +258,202 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32_m(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// Persistent: cluster c (one CTA or a CTA pair) walks tiles c, c + n_clusters, ... of the
+// (M / (128*CTAS)) x (N / BLOCK_N) tile grid, n fastest.  Three pipelines run concurrently:
+//   smem ring   full/empty        TMA producer  <-> MMA issuer
+//   TMEM        tmem_full/empty   MMA issuer    <-> epilogue   (two accumulator stages, so the
+//                                 epilogue of tile i overlaps the MMAs of tile i+1)
+//   store bufs  bulk async-groups epilogue warp <-> TMA store  (two 4 KB buffers per warp)
 template <int BLOCK_N, int STAGES, int EPI, int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const TcParams p) {
+                 const __grid_constant__ CUtensorMap tmap_out, const TcParams p) {
   using L = SmemLayout<BLOCK_N, STAGES, CTAS>;
   extern __shared__ uint8_t smem_raw[];
   // the dynamic-smem base offset is identical in both CTAs of a pair, so is the aligned layout
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* s_bias = reinterpret_cast<float*>(smem + L::kAuxOff);
-  float* s_w4 = s_bias + BLOCK_N;
+  float* s_w4 = s_bias + kMaxN;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2], the leader's are the ones used
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const uint32_t rank = (CTAS == 2) ? cluster_ctarank() : 0u;
   const bool leader = (rank == 0);
-  const int m0 = blockIdx.x * BLOCK_M;                       // this CTA's 128 rows (pair = 2 consecutive x)
-  const int n0 = blockIdx.y * BLOCK_N;                       // the (pair) tile's columns
-  const int nb0 = n0 + (int)rank * L::kBRows;                // rows of Wt this CTA stages
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int n_tiles_n = p.N / BLOCK_N;
+  const int n_tiles = ((p.M + BLOCK_M * CTAS - 1) / (BLOCK_M * CTAS)) * n_tiles_n;
+  const int cluster_id = blockIdx.x / CTAS, n_clusters = gridDim.x / CTAS;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    if (EPI == EPI_STORE) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_out) : "memory");
     for (int s = 0; s < STAGES; s++) {
       mbar_init(&full_bar[s], 1);   // the leader's producer arrives once; bytes of both CTAs are expected
       mbar_init(&empty_bar[s], 1);  // one (multicast) tcgen05.commit per use
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; a++) {
+      mbar_init(&tmem_full_bar[a], 1);          // one (multicast) tcgen05.commit per tile
+      mbar_init(&tmem_empty_bar[a], 4 * CTAS);  // every epilogue warp of every CTA of the pair
+    }
     fence_barrier_init();
   } else if (warp == 1) {
-    if (CTAS == 2) tmem_alloc_pair(tmem_ptr, BLOCK_N);
-    else tmem_alloc(tmem_ptr, BLOCK_N);
+    if (CTAS == 2) tmem_alloc_pair(tmem_ptr, L::kTmemCols);
+    else tmem_alloc(tmem_ptr, L::kTmemCols);
+  } else if (warp >= kEpiWarp0) {
+    // weights, not produced by the preceding kernel: staged before the grid dependency resolves
+    const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..127
+    for (int i = et; i < p.N; i += 128) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    if (EPI == EPI_DOT)
+      for (int i = et; i < BLOCK_N; i += 128) s_w4[i] = p.w4[i];
   }
   tc_fence_before();
   if (CTAS == 2) cluster_sync_all();   // peer barriers must exist before any remote complete_tx / commit
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (p.pdl) griddep_wait();           // activations of the previous kernel are complete and visible from here
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs of a pair) =====
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; kb++) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* a_dst = smem + s * L::kStageBytes;
-        uint8_t* b_dst = a_dst + L::kABytes;
-        if (CTAS == 2) {
-          const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);   // leader's barrier
-          if (leader) mbar_expect_tx(&full_bar[s], 2 * L::kStageBytes);
-          tma_load_2d_pair(&tmap_a, bar, a_dst, kb * BLOCK_K, m0);
-          tma_load_2d_pair(&tmap_b, bar, b_dst, kb * BLOCK_K, nb0);
-        } else {
-          mbar_expect_tx(&full_bar[s], L::kStageBytes);
-          tma_load_2d(&tmap_a, &full_bar[s], a_dst, kb * BLOCK_K, m0);
-          tma_load_2d(&tmap_b, &full_bar[s], b_dst, kb * BLOCK_K, nb0);
+      uint32_t kc = 0;   // k-slices issued so far (ring position runs on across tiles)
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+        const int m0 = ((tile / n_tiles_n) * CTAS + (int)rank) * BLOCK_M;
+        const int nb0 = (tile % n_tiles_n) * BLOCK_N + (int)rank * L::kBRows;
+        for (int kb = 0; kb < num_kb; kb++, kc++) {
+          const int s = kc % STAGES;
+          const uint32_t ph = (kc / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* a_dst = smem + s * L::kStageBytes;
+          uint8_t* b_dst = a_dst + L::kABytes;
+          if (CTAS == 2) {
+            const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);   // leader's barrier
+            if (leader) mbar_expect_tx(&full_bar[s], 2 * L::kStageBytes);
+            tma_load_2d_pair(&tmap_a, bar, a_dst, kb * BLOCK_K, m0);
+            tma_load_2d_pair(&tmap_b, bar, b_dst, kb * BLOCK_K, nb0);
+          } else {
+            mbar_expect_tx(&full_bar[s], L::kStageBytes);
+            tma_load_2d(&tmap_a, &full_bar[s], a_dst, kb * BLOCK_K, m0);
+            tma_load_2d(&tmap_b, &full_bar[s], b_dst, kb * BLOCK_K, nb0);
+          }
         }
       }
+      if (p.pdl) griddep_launch();
     }
     __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only for a pair) =====
     if (leader) {
       constexpr uint32_t idesc = make_idesc_tf32_m(BLOCK_M * CTAS, BLOCK_N);
-      for (int kb = 0; kb < num_kb; kb++) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t kc = 0, it = 0;
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
+        const uint32_t as = it & 1;
+        mbar_wait(&tmem_empty_bar[as], ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator stage
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-          const uint64_t a_desc = make_smem_desc(a_addr);
-          const uint64_t b_desc = make_smem_desc(a_addr + L::kABytes);
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; kb++, kc++) {
+          const int s = kc % STAGES;
+          const uint32_t ph = (kc / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+            const uint64_t a_desc = make_smem_desc(a_addr);
+            const uint64_t b_desc = make_smem_desc(a_addr + L::kABytes);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
-            // advance 32 bytes of K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-            if (CTAS == 2) umma_tf32_pair(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-            else umma_tf32(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+              // advance 32 bytes of K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+              if (CTAS == 2) umma_tf32_pair(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+              else umma_tf32(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            }
+            if (CTAS == 2) {
+              umma_commit_pair(&empty_bar[s]);                            // frees the slot in both CTAs
+              if (kb == num_kb - 1) umma_commit_pair(&tmem_full_bar[as]);  // accumulators complete in both CTAs
+            } else {
+              umma_commit(&empty_bar[s]);
+              if (kb == num_kb - 1) umma_commit(&tmem_full_bar[as]);
+            }
           }
-          if (CTAS == 2) {
-            umma_commit_pair(&empty_bar[s]);                       // frees the slot in both CTAs
-            if (kb == num_kb - 1) umma_commit_pair(tmem_full_bar);  // accumulators complete in both CTAs
-          } else {
-            umma_commit(&empty_bar[s]);
-            if (kb == num_kb - 1) umma_commit(tmem_full_bar);
-          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else {
     // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
-    const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..127
-    for (int i = et; i < BLOCK_N; i += 128) {
-      s_bias[i] = p.bias ? p.bias[n0 + i] : 0.f;
-      if (EPI == EPI_DOT) s_w4[i] = p.w4[n0 + i];
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue-only named barrier
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
     const int q = warp % 4;
-    const int row = m0 + q * 32 + lane;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    float dot = 0.f;
+    uint8_t* store_buf = smem + L::kStoreOff + (warp - kEpiWarp0) * 2 * kStoreBufBytes;
+    const uint32_t empty_remote = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);   // leader's tmem_empty_bar[0]
+    uint32_t it = 0, sc = 0;   // tiles done, store chunks issued
+    for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
+      const uint32_t as = it & 1;
+      const int row0 = ((tile / n_tiles_n) * CTAS + (int)rank) * BLOCK_M + q * 32;
+      const int n0 = (tile % n_tiles_n) * BLOCK_N;
+      mbar_wait(&tmem_full_bar[as], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
+      float dot = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += 32) {
-      uint32_t r[32];
-      tmem_ld32(taddr + c, r);
-      if (EPI == EPI_STORE) {
-        if (row < p.M) {
-          float4* dst = reinterpret_cast<float4*>(p.out + (size_t)row * p.N + n0 + c);
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c, r);
+        if (EPI == EPI_STORE) {
+          uint8_t* buf = store_buf + (sc & 1) * kStoreBufBytes;
+          if (lane == 0) bulk_wait_read<1>();   // the store issued two chunks ago no longer reads `buf`
+          __syncwarp();
+          const float* bs = s_bias + n0 + c;
 #pragma unroll
           for (int j = 0; j < 8; j++) {
             float4 o;
-            o.x = __uint_as_float(r[4 * j + 0]) + s_bias[c + 4 * j + 0];
-            o.y = __uint_as_float(r[4 * j + 1]) + s_bias[c + 4 * j + 1];
-            o.z = __uint_as_float(r[4 * j + 2]) + s_bias[c + 4 * j + 2];
-            o.w = __uint_as_float(r[4 * j + 3]) + s_bias[c + 4 * j + 3];
+            o.x = __uint_as_float(r[4 * j + 0]) + bs[4 * j + 0];
+            o.y = __uint_as_float(r[4 * j + 1]) + bs[4 * j + 1];
+            o.z = __uint_as_float(r[4 * j + 2]) + bs[4 * j + 2];
+            o.w = __uint_as_float(r[4 * j + 3]) + bs[4 * j + 3];
             if (p.relu) {
               o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
             }
             o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
-            dst[j] = o;
+            // 128B swizzle: 16-byte chunk j of row `lane` lives at chunk j ^ (lane & 7)
+            *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M) {   // rows past M inside the box are clipped by the TMA unit
+            tma_store_2d(&tmap_out, buf, n0 + c, row0);
+            bulk_commit();
+          }
+          sc++;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            float v = __uint_as_float(r[j]) + s_bias[c + j];
+            if (p.relu) v = fmaxf(v, 0.f);
+            dot = fmaf(v, s_w4[c + j], dot);
           }
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-          float v = __uint_as_float(r[j]) + s_bias[c + j];
-          if (p.relu) v = fmaxf(v, 0.f);
-          dot = fmaf(v, s_w4[c + j], dot);
-        }
+      }
+      // this warp's quarter of the accumulator stage has been read: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(empty_remote + as * 8);
+      if (EPI == EPI_DOT && row0 + lane < p.M) {
+        if (p.b4) dot += p.b4[0];
+        p.out[row0 + lane] = p.sigmoid ? 1.f / (1.f + __expf(-dot)) : dot;
       }
     }
-    if (EPI == EPI_DOT && row < p.M) {
-      if (p.b4) dot += p.b4[0];
-      p.out[row] = p.sigmoid ? 1.f / (1.f + __expf(-dot)) : dot;
-    }
+    if (EPI == EPI_STORE && lane == 0) bulk_wait_all<0>();   // stores complete before the CTA retires
     tc_fence_before();
   }
   if (CTAS == 2) cluster_sync_all();   // the peer's smem / TMEM must stay alive until the pair is done
   else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    if (CTAS == 2) tmem_dealloc_pair(tmem_base, BLOCK_N);
-    else tmem_dealloc(tmem_base, BLOCK_N);
+    if (CTAS == 2) tmem_dealloc_pair(tmem_base, L::kTmemCols);
+    else tmem_dealloc(tmem_base, L::kTmemCols);
   }
 }
 
@@ -397,10 +471,11 @@ struct TcState {
   CUtensorMap w_map[3];
   TcLayerCfg cfg[3];
   bool ready = false;
-  // cached A-operand maps keyed by (pointer, K, rows)
+  // cached activation maps keyed by (pointer, K, rows, box rows): 128-row boxes feed the A operand,
+  // 32-row boxes are the epilogue's store boxes
   struct AMap {
     const void* ptr;
-    int K, rows;
+    int K, rows, box_rows;
     CUtensorMap map;
   };
   std::vector<AMap> a_maps;
@@ -421,10 +496,14 @@ fr_status encode_2d(fr_engine* e, TcState* st, CUtensorMap* map, const void* bas
   return FR_OK;
 }
 
+int g_max_clusters = 0;   // FR_TC_MAX_CLUSTERS: cap the persistent grid (tests force several tiles per cluster)
+
 template <int BLOCK_N, int STAGES, int EPI, int CTAS>
-fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, cudaStream_t st) {
+fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const TcParams& p,
+                 cudaStream_t st) {
   using L = SmemLayout<BLOCK_N, STAGES, CTAS>;
   static_assert(L::kDyn <= 227 * 1024, "tile configuration exceeds the 227 KB shared memory of an SM");
+  static_assert(L::kTmemCols == 256 || L::kTmemCols == 512, "TMEM allocation must be a power of two");
   auto kern = tc_linear_kernel<BLOCK_N, STAGES, EPI, CTAS>;
   static std::atomic<uint64_t> attr_done{0};  // bit d: opt-in smem size set on device d for this instantiation
   const uint64_t bit = 1ull << (e->device & 63);
@@ -432,28 +511,34 @@ fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const
     FR_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDyn));
     attr_done.fetch_or(bit);
   }
-  const int m_tiles = (p.M + BLOCK_M * CTAS - 1) / (BLOCK_M * CTAS) * CTAS;
+  // persistent: one cluster per tile up to one CTA per SM
+  const int n_tiles = (p.M + BLOCK_M * CTAS - 1) / (BLOCK_M * CTAS) * (p.N / BLOCK_N);
+  int max_clusters = e->sm_count / CTAS;
+  if (g_max_clusters > 0 && g_max_clusters < max_clusters) max_clusters = g_max_clusters;   // test knob
+  const int n_clusters = n_tiles < max_clusters ? n_tiles : max_clusters;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(m_tiles, p.N / BLOCK_N, 1);
+  cfg.gridDim = dim3(n_clusters * CTAS, 1, 1);
   cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = L::kDyn;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTAS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  FR_CUDA(e, cudaLaunchKernelEx(&cfg, kern, a, b, p));
+  cfg.numAttrs = p.pdl ? 2 : 1;
+  FR_CUDA(e, cudaLaunchKernelEx(&cfg, kern, a, b, o, p));
   e->launches++;
   return FR_OK;
 }
 
-fr_status get_a_map(fr_engine* e, TcState* st, const void* ptr, int K, int rows, CUtensorMap* out) {
+fr_status get_a_map(fr_engine* e, TcState* st, const void* ptr, int K, int rows, int box_rows, CUtensorMap* out) {
   std::lock_guard<std::mutex> g(st->mu);
   for (const TcState::AMap& m : st->a_maps)
-    if (m.ptr == ptr && m.K == K && m.rows == rows) {
+    if (m.ptr == ptr && m.K == K && m.rows == rows && m.box_rows == box_rows) {
       *out = m.map;
       return FR_OK;
     }
@@ -461,9 +546,10 @@ fr_status get_a_map(fr_engine* e, TcState* st, const void* ptr, int K, int rows,
   m.ptr = ptr;
   m.K = K;
   m.rows = rows;
-  fr_status s = encode_2d(e, st, &m.map, ptr, rows, K, BLOCK_M);
+  m.box_rows = box_rows;
+  fr_status s = encode_2d(e, st, &m.map, ptr, rows, K, box_rows);
   if (s != FR_OK) return s;
-  if (st->a_maps.size() < 256) st->a_maps.push_back(m);
+  if (st->a_maps.size() < 1024) st->a_maps.push_back(m);
   *out = m.map;
   return FR_OK;
 }
@@ -500,12 +586,16 @@ fr_status frtc_prepare(fr_engine* e) {
     return fr_fail(e, FR_ERR_UNSUPPORTED, "TF32 path folds the output layer into layer 3 and needs hidden[2] == 256 "
                    "(got %d)", e->dims[3]);
   parse_tiles(st->cfg);
+  const char* cap = getenv("FR_TC_MAX_CLUSTERS");
+  g_max_clusters = cap ? atoi(cap) : 0;
   for (int k = 0; k < 3; k++) {
     const TcLayerCfg c = st->cfg[k];
     if ((c.block_n != 128 && c.block_n != 256) || (c.ctas != 1 && c.ctas != 2))
       return fr_fail(e, FR_ERR_UNSUPPORTED, "tile N %d / ctas %d not built (N in {128,256}, ctas in {1,2})", c.block_n, c.ctas);
     if (e->dims[k + 1] % c.block_n)
       return fr_fail(e, FR_ERR_UNSUPPORTED, "hidden[%d]=%d not a multiple of tile N %d", k, e->dims[k + 1], c.block_n);
+    if (e->dims[k + 1] > kMaxN)
+      return fr_fail(e, FR_ERR_UNSUPPORTED, "hidden[%d]=%d wider than the %d-float bias staging area", k, e->dims[k + 1], kMaxN);
     fr_status s = encode_2d(e, st, &st->w_map[k], e->d_Wt[k], e->dims[k + 1], e->dims[k], c.block_n / c.ctas);
     if (s != FR_OK) return s;
   }
@@ -523,10 +613,13 @@ void frtc_destroy(fr_engine* e) {
 fr_status frtc_layer(fr_engine* e, fr_stream_s* s, int k, const float* in, int B, float* d_scores) {
   TcState* st = static_cast<TcState*>(e->tc_state);
   const bool act = (e->mlp_mode == FR_MLP_BIAS_RELU_SIGMOID);
-  CUtensorMap a;
-  // rows = B: TMA zero-fills the M tail, so no stale rows are ever multiplied
-  fr_status r = get_a_map(e, st, in, e->dims[k], B, &a);
+  CUtensorMap a, o;
+  // rows = B: TMA zero-fills the M tail on load and clips it on store, so no stale rows are ever
+  // multiplied or written
+  fr_status r = get_a_map(e, st, in, e->dims[k], B, BLOCK_M, &a);
   if (r != FR_OK) return r;
+  o = a;
+  if (k < 2 && (r = get_a_map(e, st, s->d_h[k], e->dims[k + 1], B, kStoreBoxRows, &o)) != FR_OK) return r;
   TcParams p;
   p.bias = act ? e->d_bias[k] : nullptr;
   p.M = B;
@@ -536,14 +629,14 @@ fr_status frtc_layer(fr_engine* e, fr_stream_s* s, int k, const float* in, int B
   p.sigmoid = act ? 1 : 0;
   p.w4 = e->d_W[3];
   p.b4 = act ? e->d_bias[3] : nullptr;
+  p.pdl = e->use_pdl ? 1 : 0;
+  p.out = d_scores;
   const TcLayerCfg c = st->cfg[k];
   const CUtensorMap& w = st->w_map[k];
   cudaStream_t cs = s->stream;
   if (k < 2) {
-    p.out = s->d_h[k];
-    if (c.ctas == 2) return c.block_n == 256 ? launch<256, 6, EPI_STORE, 2>(e, a, w, p, cs) : launch<128, 8, EPI_STORE, 2>(e, a, w, p, cs);
-    return c.block_n == 256 ? launch<256, 4, EPI_STORE, 1>(e, a, w, p, cs) : launch<128, 6, EPI_STORE, 1>(e, a, w, p, cs);
+    if (c.ctas == 2) return c.block_n == 256 ? launch<256, 5, EPI_STORE, 2>(e, a, w, o, p, cs) : launch<128, 7, EPI_STORE, 2>(e, a, w, o, p, cs);
+    return c.block_n == 256 ? launch<256, 3, EPI_STORE, 1>(e, a, w, o, p, cs) : launch<128, 5, EPI_STORE, 1>(e, a, w, o, p, cs);
   }
-  p.out = d_scores;
-  return c.ctas == 2 ? launch<256, 6, EPI_DOT, 2>(e, a, w, p, cs) : launch<256, 4, EPI_DOT, 1>(e, a, w, p, cs);
+  return c.ctas == 2 ? launch<256, 5, EPI_DOT, 2>(e, a, w, o, p, cs) : launch<256, 3, EPI_DOT, 1>(e, a, w, o, p, cs);
 }

@@ -298,3 +298,38 @@ def test_infer_graph_replay_matches_direct():
         assert eng.launch_count() - l0 == 4 * 4          # gather + 3 GEMM launches per batch, replayed or not
     w.close()
     eng.close()
+
+
+@pytest.mark.parametrize("tiles", TILES)
+@pytest.mark.parametrize("clusters,pdl", ((1, "1"), (3, "0"), (0, "1")))
+def test_tf32_persistent_tile_loop(tiles, clusters, pdl, monkeypatch):
+    """The tcgen05 kernels are persistent: a cluster walks tiles c, c+G, ...  with two TMEM
+    accumulator stages and two TMA-store buffers per epilogue warp.  Capping the grid
+    (FR_TC_MAX_CLUSTERS) makes every cluster run many tiles, so ring positions, accumulator
+    stage parities and store-buffer reuse all wrap several times; clusters=0 is the production
+    grid at a batch with > 148 tiles.  Checked per layer against float64 on TF32-rounded
+    inputs and through the whole chain against the oracle, with and without PDL."""
+    monkeypatch.setenv("FR_TC_TILES", tiles)
+    monkeypatch.setenv("FR_PDL", pdl)
+    if clusters:
+        monkeypatch.setenv("FR_TC_MAX_CLUSTERS", str(clusters))
+    else:
+        monkeypatch.delenv("FR_TC_MAX_CLUSTERS", raising=False)
+    B = 1300 if clusters else 20000
+    cat = catalogue.load("small").with_row_cap(64)
+    dims = cat.layer_dims
+    W, b = oracle.make_weights(dims, seed=11)
+    eng = fleetrec.Engine(cat, max_batch=B)
+    eng.load_mlp(W, b)
+    rng = np.random.default_rng(clusters)
+    for k in (0, 1):
+        x = tf32_rna(rng.uniform(-1, 1, (B, dims[k])).astype(np.float32))
+        h = np.maximum(x.astype(np.float64) @ tf32_rna(W[k]).astype(np.float64) + b[k], 0)
+        got = eng.layer_only(k, x, dims[k + 1])
+        assert np.max(np.abs(got - h)) <= 2e-3 * max(1.0, np.abs(h).max()), k
+    x = rng.uniform(-1, 1, (B, dims[0])).astype(np.float32)
+    for _ in range(2):   # twice: the second chain runs back to back with the first on the same stream
+        got = eng.mlp_only(x)
+    assert rel_err(got, oracle.mlp(x, dims, W, b, mode=1)) <= TOL
+    eng.close()
+    monkeypatch.delenv("FR_TC_MAX_CLUSTERS", raising=False)
