@@ -32,6 +32,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "gpu-fpga-recommendation-system_b200"))
 
+def trace(msg):
+    """Progress marks on stderr (BENCH_TRACE=1): tells which phase a hung run was in."""
+    if os.environ.get("BENCH_TRACE"):
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 METRIC = "inferences/sec (gather+MLP)"
 UNIT = "inferences/s"
 
@@ -190,8 +196,7 @@ def run_ours(args):
     if sharded:
         from fleetrec import shard
         owner = shard.plan_owners(cat, world)
-        eng.shard_init(rank, world, owner)
-        args.streams = 1                      # sharded steps are ordered on one worker stream
+        eng.shard_init(rank, world, owner)   # every worker stream gets its own exchange slot
     eng.fill_hash(seed=0x5EED)
     W, b = oracle.make_weights(dims, seed=42)
     eng.load_mlp(W, b)
@@ -211,6 +216,7 @@ def run_ours(args):
     sc_host = [torch.empty(B, dtype=torch.float32).pin_memory() for _ in range(args.streams)]
     torch.cuda.synchronize()
 
+    trace("setup done, parity gate")
     # correctness gate before timing anything: one batch against the oracle (hash-filled tables)
     i0 = idx_host[0].numpy()
     lo, hi = (rank * B, (rank + 1) * B) if sharded else (0, B)
@@ -229,14 +235,17 @@ def run_ours(args):
     assert gate_err <= (1e-3 if args.precision == "tf32" else 2e-5), f"score parity gate failed: {gate_err}"
 
     def timed(step_fn, steps, warmup):
+        trace(f"timed({step_fn.__name__}, {steps}, {warmup}) graphs")
         # one-time setup, like loading weights: every (index buffer, score buffer) pair is shown to
         # the engine twice so its CUDA graphs are instantiated before the W warm-up steps begin
         for i in range(2 * pool * args.streams // np.gcd(pool, args.streams)):
             step_fn(i)
         barrier()
+        trace("warmup")
         for i in range(warmup):
             step_fn(i)
         barrier()
+        trace("timed region")
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = eng.launch_count()
         e0.record(main)
@@ -249,7 +258,9 @@ def run_ours(args):
             ev.record(s)
             main.wait_event(ev)
         e1.record(main)
+        trace("enqueued, waiting")
         barrier()
+        trace("done")
         ms = e0.elapsed_time(e1)
         if dist is not None:
             t = torch.tensor([ms], device="cuda")
@@ -289,6 +300,7 @@ def run_ours(args):
     e2e = world * args.steps * B / (ms_e2e * 1e-3)
 
     # ---- per-kernel times (each kernel alone, CUDA events on its own stream) and rooflines
+    trace("per-kernel times")
     pk = peaks()
     kms = eng.time_kernels(idx_dev[1], B, reps=args.kernel_reps, worker=workers[0])
     names = ["gather_concat", "mlp_layer1", "mlp_layer2", "mlp_layer3+out", "mlp_out"]
@@ -313,6 +325,19 @@ def run_ours(args):
                     peak_source=pk["src"] + ("; tf32 tensor peak taken as half the measured dense bf16 rate"
                                              if dom["bound"] == "tensor" and args.precision == "tf32" else ""),
                     share_of_step=dom["ms"] / sum(k["ms"] for k in kernels))
+
+    # ---- the same kernels at a large batch (north star: tensor-pipe utilisation at batch >= 4096)
+    large = None
+    if not sharded and args.gather_batch >= 4096:
+        LB = args.gather_batch
+        lidx = torch.from_numpy(oracle.zipf_indices(cat, LB, seed=99)).cuda()
+        lms = eng.time_kernels(lidx, LB, reps=max(args.kernel_reps // 2, 2), worker=workers[0])
+        lfl = [f * LB / B for f in flops]
+        large = dict(batch=LB, kernels=[dict(name=n, ms=ms, achieved=fl / (ms * 1e-3) / 1e12, unit="TFLOP/s",
+                                             frac=fl / (ms * 1e-3) / 1e12 / tensor_peak)
+                                        for n, ms, fl in zip(names, lms, lfl) if ms > 0 and fl > 0],
+                     mlp_ms=sum(lms[1:]), mlp_tflops=sum(lfl) / (sum(lms[1:]) * 1e-3) / 1e12,
+                     mlp_frac=sum(lfl) / (sum(lms[1:]) * 1e-3) / 1e12 / tensor_peak, peak=tensor_peak)
 
     # ---- stand-alone gather at a large batch, uniform indices (the HBM-roofline test of the lookup)
     gather = None
@@ -343,11 +368,164 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": Bg * T * 4, "d2h_bytes_per_step": B * 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
-            "gather_standalone": gather, "cpu_baseline": cpu}
+            "gather_standalone": gather, "mlp_large_batch": large, "cpu_baseline": cpu}
     print(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------- config 5: gather HBM-roofline stress
+def run_stress(args):
+    """BASELINE.json configs[4], 1-GPU variant: T tables x R rows x dim 64 (256-byte rows),
+    lookup+concat only, uniform indices (tables >> L2: algorithmic bytes ~ DRAM bytes, the honest
+    HBM-roofline test) and Zipf(1.05) indices (hot heads become L2-resident).  With N ranks every rank
+    holds its own T x R tables (weak scaling, no exchange: the lookup of disjoint table sets is
+    embarrassingly parallel)."""
+    import torch
+
+    import fleetrec
+    from fleetrec import catalogue
+    from oracle import oracle
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    T, dim, B = args.stress_tables, 64, args.gather_batch
+    rows, eng = args.stress_rows, None
+    while eng is None:
+        cat = catalogue.synthetic(T, rows, dim)
+        eng = fleetrec.Engine(cat, device=local, max_batch=B)
+        try:
+            eng.fill_hash(seed=0x5EED)
+        except fleetrec.FleetRecError as ex:        # HBM too small for this many rows: halve and say so
+            if ex.code != fleetrec.FR_ERR_OOM or rows <= 65536:
+                raise
+            eng.close()
+            eng, rows = None, rows // 2
+    w = fleetrec.Worker(eng)
+    out = torch.empty(B, cat.concat_floats, dtype=torch.float32, device="cuda")
+    pk = peaks()
+    alg = B * cat.gather_bytes_per_item(materialised=True)
+    res = {}
+    for kind in ("uniform", "zipf"):
+        gen = oracle.uniform_indices if kind == "uniform" else oracle.zipf_indices
+        pool = [torch.from_numpy(gen(cat, B, seed=4321 + 17 * i + 1000 * rank)).cuda() for i in range(4)]
+        # parity gate on a sample: bit-exact against the oracle's hash fill
+        eng.gather_only_async(pool[0], out, B, w)
+        eng.sync(w)
+        exp = oracle.gather_hashed(cat, 0x5EED, pool[0][:128].cpu().numpy())
+        assert np.array_equal(out[:128].cpu().numpy().view(np.uint32), exp.view(np.uint32)), "concat not bit-exact"
+        for i in range(max(args.warmup, 3)):
+            eng.gather_only_async(pool[i % 4], out, B, w)
+        eng.sync(w)
+        if dist is not None:
+            dist.barrier()
+        eng.mark(0, w)
+        for i in range(args.steps):
+            eng.gather_only_async(pool[i % 4], out, B, w)
+        eng.mark(1, w)
+        ms = eng.elapsed_ms(w)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        per = ms / args.steps
+        res[kind] = dict(ms_per_launch=per, items_per_s=world * B / (per * 1e-3),
+                         achieved=alg / (per * 1e-3) / 1e9, frac=alg / (per * 1e-3) / 1e9 / pk["hbm"])
+    if rank == 0:
+        u = res["uniform"]
+        line = {"metric": "gather HBM GB/s (lookup+concat, stress tables)", "value": world * u["achieved"], "unit": "GB/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": u["ms_per_launch"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 rows (byte copy)",
+                "data": "synthetic",
+                "config": {"workload": f"BASELINE.json configs[4] per-GPU slice: {T} tables x {rows} rows x dim {dim} "
+                                       f"({cat.table_bytes() / 1e9:.1f} GB per GPU), lookup+concat only, batch {B}",
+                           "rows_requested": args.stress_rows, "rows_used": rows,
+                           "note": "the literal config (1000 x 10M x 64 fp32 = 2.56 TB) exceeds 8 x 180 GB; rows are "
+                                   "scaled so one GPU's slice fits HBM, tables stay >> L2 (126 MB)",
+                           "l2": "uniform indices over tables far larger than L2; a pool of 4 index batches rotates"},
+                "gpu_launches": int(2 * (args.steps + max(args.warmup, 3) + 1)),
+                "roofline": {"bound": "hbm", "achieved": u["achieved"], "peak": pk["hbm"], "unit": "GB/s", "frac": u["frac"],
+                             "traffic": None, "kernel": "gather_concat", "ms_per_launch": u["ms_per_launch"],
+                             "peak_source": pk["src"], "algorithmic_bytes_per_item": cat.gather_bytes_per_item(True)},
+                "uniform": res["uniform"], "zipf": res["zipf"]}
+        print(json.dumps(line))
+    w.close()
+    eng.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------- config 3: batch sweep, latency vs throughput
+def run_sweep(args):
+    """BASELINE.json configs[2]: medium model (98 tables, 15.1 GB), B in 1..16384.  Per B: device latency of
+    one fr_infer (CUDA events around each graph launch on the worker's stream, >= `--sweep-launches`
+    launches, p50 / p99), host wall time of fr_infer -> fr_sync on pinned buffers, throughput = B / p50."""
+    import torch
+
+    import fleetrec
+    from fleetrec import catalogue
+    from oracle import oracle
+
+    torch.cuda.set_device(0)
+    cat = catalogue.load(args.model)
+    dims = cat.layer_dims
+    prec = fleetrec.FR_PREC_TF32 if args.precision == "tf32" else fleetrec.FR_PREC_FP32
+    eng = fleetrec.Engine(cat, device=0, precision=prec, max_batch=16384)
+    eng.fill_hash(seed=0x5EED)
+    W, b = oracle.make_weights(dims, seed=42)
+    eng.load_mlp(W, b)
+    w = fleetrec.Worker(eng)
+    ws = torch.cuda.ExternalStream(w.cuda_stream)
+    rows = []
+    n = args.sweep_launches
+    for B in [1 << k for k in range(0, 15)]:
+        idx_d = [torch.from_numpy(oracle.zipf_indices(cat, B, seed=77 + i)).cuda() for i in range(4)]
+        idx_h = [t.cpu().pin_memory() for t in idx_d]
+        sc_d = torch.empty(B, dtype=torch.float32, device="cuda")
+        sc_h = torch.empty(B, dtype=torch.float32).pin_memory()
+        for i in range(12):                       # graphs instantiated, caches warm
+            eng.infer_async(idx_d[i % 4], sc_d, B, w)
+            eng.infer_async(idx_h[i % 4].numpy(), sc_h.numpy(), B, w)
+        eng.sync(w)
+        if B == 256:                              # parity gate inside the sweep
+            exp = oracle.mlp(oracle.gather_hashed(cat, 0x5EED, idx_h[3].numpy()), dims, W, b, mode=1)
+            err = float(np.max(np.abs(sc_h.numpy() - exp) / np.maximum(np.abs(exp), 1e-6)))
+            assert err <= 1e-3, err
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for i, (e0, e1) in enumerate(evs):
+            e0.record(ws)
+            eng.infer_async(idx_d[i % 4], sc_d, B, w)
+            e1.record(ws)
+            if i % 64 == 63:
+                eng.sync(w)                       # isolated launches: latency, not pipelined throughput
+        eng.sync(w)
+        dev = np.array([e0.elapsed_time(e1) for e0, e1 in evs]) * 1e3
+        wall = []
+        for i in range(min(n, 300)):
+            t0 = time.perf_counter()
+            eng.infer_async(idx_h[i % 4].numpy(), sc_h.numpy(), B, w)
+            eng.sync(w)
+            wall.append((time.perf_counter() - t0) * 1e6)
+        wall = np.array(wall)
+        rows.append(dict(batch=B, dev_p50_us=float(np.percentile(dev, 50)), dev_p99_us=float(np.percentile(dev, 99)),
+                         host_p50_us=float(np.percentile(wall, 50)), host_p99_us=float(np.percentile(wall, 99)),
+                         inferences_per_s=B / (float(np.percentile(dev, 50)) * 1e-6), launches=n))
+    w.close()
+    eng.close()
+    best = max(rows, key=lambda r: r["inferences_per_s"])
+    print(json.dumps({"metric": "p99 batch latency / throughput sweep", "unit": "us", "n_gpus": 1,
+                      "config": {"workload": f"BASELINE.json configs[2]: FleetRec {args.model} model, batch sweep 1-16384, "
+                                             "one batch in flight, Zipf(1.05) indices, device-resident indices for "
+                                             "dev_*; pinned host buffers + sync for host_*", "precision": args.precision},
+                      "value": best["dev_p99_us"], "best_batch": best["batch"], "data": "synthetic", "sweep": rows}))
 
 
 def main():
@@ -358,7 +536,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="small")
     ap.add_argument("--batch", type=int, default=2048)
-    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--streams", type=int, default=8)
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--tiles", default="", help="FR_TC_TILES override: N1,N2,N3,ctas")
     ap.add_argument("--shard", default="tables", choices=["replicated", "tables"],
@@ -366,11 +544,25 @@ def main():
     ap.add_argument("--gather-batch", type=int, default=16384)
     ap.add_argument("--kernel-reps", type=int, default=50)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--workload", default="model", choices=["model", "stress", "sweep"],
+                    help="model: gather+MLP of --model (the headline); stress: configs[4] gather HBM roofline; "
+                         "sweep: configs[2] latency/throughput batch sweep")
+    ap.add_argument("--stress-tables", type=int, default=125)
+    ap.add_argument("--stress-rows", type=int, default=4000000)
+    ap.add_argument("--sweep-launches", type=int, default=1000)
     args = ap.parse_args()
     if args.tiles:
         os.environ["FR_TC_TILES"] = args.tiles
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "stress":
+        if args.steps == 2000:
+            args.steps = 50
+        run_stress(args)
+    elif args.workload == "sweep":
+        if args.model == "small":
+            args.model = "medium"
+        run_sweep(args)
     else:
         args.warmup = max(args.warmup, 3)
         run_ours(args)

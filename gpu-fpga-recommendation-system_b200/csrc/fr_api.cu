@@ -99,6 +99,7 @@ static fr_status alloc_stream(fr_engine* e, fr_stream_s** out) {
   FR_CUDA(e, cudaMalloc(&s->d_scores, mb * sizeof(float)));
   FR_CUDA(e, cudaEventCreate(&s->ev[0]));
   FR_CUDA(e, cudaEventCreate(&s->ev[1]));
+  s->slot = e->next_slot++;   // creation order: identical on every rank of a sharded job
   *out = s;
   return FR_OK;
 }
@@ -155,7 +156,7 @@ extern "C" fr_status fr_create(const fr_model_desc* desc, int n_gpus, const int*
   e->precision = desc->precision;
   e->max_batch = desc->max_batch;
   if (const char* env = getenv("FR_GRAPHS")) e->use_graphs = atoi(env) != 0;
-  if (const char* env = getenv("FR_PDL")) e->use_pdl = atoi(env) != 0;
+  if (const char* env = getenv("FR_PDL")) e->pdl_mask = atoi(env) & 7;
   e->tables.resize(desc->n_tables);
   for (int t = 0; t < desc->n_tables; t++) {
     e->tables[t].rows = desc->tables[t].rows;
@@ -192,7 +193,7 @@ extern "C" void fr_destroy(fr_engine* e) {
     if (e->peers[r].ipc && e->peers[r].concat) cudaIpcCloseMemHandle(e->peers[r].concat);
   cudaFree(e->d_peer_ptrs);
   cudaFree(e->d_xchg);
-  cudaFree(e->d_epoch);
+  cudaFree(e->d_step);
   if (e->h_shard_err) cudaFreeHost(e->h_shard_err);
   delete e;
 }
@@ -441,43 +442,41 @@ static bool is_capturable_ptr(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged || a.type == cudaMemoryTypeHost;
 }
 
-extern "C" fr_status fr_infer(fr_engine* e, const int32_t* idx, int B, float* scores, fr_stream s) {
-  fr_status st = prep(e, &s, B, true, true);
-  if (st != FR_OK) return st;
-  if (B == 0) return FR_OK;
-  if (!idx || !scores) return fr_fail(e, FR_ERR_INVALID, "null idx/scores");
-  if (e->world > 1) return fr_fail(e, FR_ERR_STATE, "engine is table-sharded over %d ranks: use fr_shard_infer", e->world);
-  if (!e->use_graphs) return infer_enqueue(e, s, idx, B, scores);
-
-  // The batch is 4-5 tiny launches; issued one by one the host (~5 us per launch) is the bottleneck,
-  // so a buffer combination seen before is replayed as one CUDA graph.
+// The batch is 4-6 tiny launches; issued one by one the host (~5 us per launch) is the bottleneck,
+// so a (idx, scores, B, variant) combination seen before on this worker is replayed as ONE CUDA
+// graph.  `enqueue` issues the step's work on s->stream (it is called directly, or under capture).
+template <class F>
+static fr_status run_or_replay(fr_engine* e, fr_stream_s* s, const void* idx, const void* scores, int B, int variant,
+                               F&& enqueue) {
+  if (!e->use_graphs) return enqueue();
   fr_stream_s::Graph* g = nullptr;
   for (fr_stream_s::Graph& c : s->graphs)
-    if (c.idx == idx && c.scores == scores && c.B == B && c.mode == e->mlp_mode && c.prec == e->precision) g = &c;
+    if (c.idx == idx && c.scores == scores && c.B == B && c.mode == e->mlp_mode && c.prec == e->precision &&
+        c.variant == variant)
+      g = &c;
   if (g && g->exec) {
     FR_CUDA(e, cudaGraphLaunch(g->exec, s->stream));
     e->launches += g->launches;
     return FR_OK;
   }
   if (!g) {
-    if (s->graphs.size() >= 512 || !is_capturable_ptr(idx) || !is_capturable_ptr(scores))
-      return infer_enqueue(e, s, idx, B, scores);
-    s->graphs.push_back({idx, scores, B, e->mlp_mode, e->precision, 0, 0, nullptr});
+    if (s->graphs.size() >= 512 || !is_capturable_ptr(idx) || !is_capturable_ptr(scores)) return enqueue();
+    s->graphs.push_back({idx, scores, B, e->mlp_mode, e->precision, variant, 0, 0, nullptr});
     g = &s->graphs.back();
   }
   if (g->seen < 1) {  // first sighting: plain launches (also warms attribute / tensor-map caches)
     g->seen++;
-    return infer_enqueue(e, s, idx, B, scores);
+    return enqueue();
   }
-  if (g->seen == INT_MAX) return infer_enqueue(e, s, idx, B, scores);  // capture failed before
+  if (g->seen == INT_MAX) return enqueue();  // capture failed before
   const int64_t l0 = e->launches.load();
   cudaError_t ce = cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal);
   if (ce != cudaSuccess) {
     cudaGetLastError();
     g->seen = INT_MAX;
-    return infer_enqueue(e, s, idx, B, scores);
+    return enqueue();
   }
-  st = infer_enqueue(e, s, idx, B, scores);
+  fr_status st = enqueue();
   cudaGraph_t graph = nullptr;
   ce = cudaStreamEndCapture(s->stream, &graph);
   const int captured = (int)(e->launches.load() - l0);
@@ -486,7 +485,7 @@ extern "C" fr_status fr_infer(fr_engine* e, const int32_t* idx, int B, float* sc
     cudaGetLastError();
     if (graph) cudaGraphDestroy(graph);
     g->seen = INT_MAX;
-    return infer_enqueue(e, s, idx, B, scores);
+    return enqueue();
   }
   ce = cudaGraphInstantiate(&g->exec, graph, 0);
   cudaGraphDestroy(graph);
@@ -494,12 +493,21 @@ extern "C" fr_status fr_infer(fr_engine* e, const int32_t* idx, int B, float* sc
     cudaGetLastError();
     g->exec = nullptr;
     g->seen = INT_MAX;
-    return infer_enqueue(e, s, idx, B, scores);
+    return enqueue();
   }
   g->launches = captured;
   FR_CUDA(e, cudaGraphLaunch(g->exec, s->stream));
   e->launches += g->launches;
   return FR_OK;
+}
+
+extern "C" fr_status fr_infer(fr_engine* e, const int32_t* idx, int B, float* scores, fr_stream s) {
+  fr_status st = prep(e, &s, B, true, true);
+  if (st != FR_OK) return st;
+  if (B == 0) return FR_OK;
+  if (!idx || !scores) return fr_fail(e, FR_ERR_INVALID, "null idx/scores");
+  if (e->world > 1) return fr_fail(e, FR_ERR_STATE, "engine is table-sharded over %d ranks: use fr_shard_infer", e->world);
+  return run_or_replay(e, s, idx, scores, B, 0, [&] { return infer_enqueue(e, s, idx, B, scores); });
 }
 
 extern "C" fr_status fr_gather_only(fr_engine* e, const int32_t* idx, int B, float* concat, fr_stream s) {
@@ -603,7 +611,8 @@ extern "C" fr_status fr_time_kernels(fr_engine* e, const int32_t* idx, int B, in
       FR_CUDA(e, cudaEventSynchronize(e1));
       FR_CUDA(e, cudaEventElapsedTime(&ms5[0], e0, e1));
     } else {
-      in = e->d_xchg;  // sharded: the lookup needs every rank; time the MLP on the last exchanged batch
+      // sharded: the lookup needs every rank; time the MLP on this worker's last exchanged batch
+      in = e->d_xchg + fr_xchg_concat_off(e, s->slot < e->n_slots ? s->slot : 0, s->shard_step & 1);
     }
     for (int k = 0; k < mlp_steps(e); k++) {
       const float* out = nullptr;
@@ -623,12 +632,12 @@ extern "C" fr_status fr_time_kernels(fr_engine* e, const int32_t* idx, int B, in
 // ---------------------------------------------------------------------------
 // Sharding: table-wise model parallel, push all-to-all over NVLink.
 //
-// Exchange region of one rank (ONE cudaMalloc, exported through CUDA IPC):
-//   [ concat buffer 0 | concat buffer 1 | flags: int32[world] ]
-// concat buffer p holds this rank's B_global/world items of the step with parity p; flags[r] is
-// the last step rank r has finished pushing for (written by rank r over NVLink).
-static size_t xchg_buf_floats(const fr_engine* e) { return (size_t)(e->max_batch / e->world) * e->D; }
-
+// Exchange region of one rank (ONE cudaMalloc, exported through CUDA IPC), n_slots times:
+//   [ concat buffer 0 | concat buffer 1 | flags: int32[world] (padded to 256 B) ]
+// A slot belongs to one worker stream (same creation order on every rank), so several sharded
+// steps are in flight at once, one per worker.  Within a slot, concat buffer p holds this rank's
+// B_global/world items of the step with parity p; flags[r] is the last step of the slot rank r
+// has finished pushing for (written by rank r over NVLink).
 extern "C" fr_status fr_shard_init(fr_engine* e, int rank, int world, const int* owner) {
   if (!e) return fr_fail(nullptr, FR_ERR_INVALID, "null engine");
   if (world < 1 || rank < 0 || rank >= world || !owner) return fr_fail(e, FR_ERR_INVALID, "fr_shard_init: rank/world/owner");
@@ -643,19 +652,21 @@ extern "C" fr_status fr_shard_init(fr_engine* e, int rank, int world, const int*
     if (owner[t] < -1 || owner[t] >= world) return fr_fail(e, FR_ERR_INVALID, "owner[%d]=%d", (int)t, owner[t]);
     e->tables[t].resident = (owner[t] == -1 || owner[t] == rank);
   }
+  if (world > 32) return fr_fail(e, FR_ERR_UNSUPPORTED, "world %d > 32 (one warp publishes and polls the flags)", world);
   FR_CUDA(e, cudaSetDevice(e->device));
-  const size_t bytes = 2 * xchg_buf_floats(e) * sizeof(float) + (size_t)world * sizeof(int);
+  e->n_slots = 9;   // the default worker + 8 created workers
+  if (const char* env = getenv("FR_SHARD_SLOTS")) e->n_slots = atoi(env) > 0 ? atoi(env) : 1;
+  const size_t bytes = (size_t)e->n_slots * fr_xchg_slot_floats(e) * sizeof(float);
   FR_CUDA(e, cudaMalloc(&e->d_xchg, bytes));
   FR_CUDA(e, cudaMemsetAsync(e->d_xchg, 0, bytes, e->default_stream->stream));
-  FR_CUDA(e, cudaMalloc(&e->d_epoch, sizeof(int)));
-  FR_CUDA(e, cudaMemsetAsync(e->d_epoch, 0, sizeof(int), e->default_stream->stream));
+  FR_CUDA(e, cudaMalloc(&e->d_step, sizeof(int) * e->n_slots));
+  FR_CUDA(e, cudaMemsetAsync(e->d_step, 0, sizeof(int) * e->n_slots, e->default_stream->stream));
   FR_CUDA(e, cudaHostAlloc(&e->h_shard_err, sizeof(int), cudaHostAllocMapped));
   *e->h_shard_err = 0;
   FR_CUDA(e, cudaStreamSynchronize(e->default_stream->stream));
   e->peers.assign(world, FrPeer());
   e->peers[rank].concat = e->d_xchg;
   e->chunks_dirty = true;
-  e->shard_step = 0;
   return FR_OK;
 }
 
@@ -718,8 +729,10 @@ extern "C" fr_status fr_shard_attach_local(fr_engine* e, fr_engine* const* peers
   return upload_peers(e);
 }
 
-static fr_status shard_check(fr_engine* e, int B_global) {
+static fr_status shard_check(fr_engine* e, const fr_stream_s* s, int B_global) {
   if (!e->d_xchg) return fr_fail(e, FR_ERR_STATE, "fr_shard_init first");
+  if (s->slot >= e->n_slots)
+    return fr_fail(e, FR_ERR_UNSUPPORTED, "worker %d has no exchange slot (%d slots; FR_SHARD_SLOTS)", s->slot, e->n_slots);
   if (!e->d_peer_ptrs) return fr_fail(e, FR_ERR_STATE, "exchange buffers not attached (fr_shard_import)");
   if (B_global % e->world) return fr_fail(e, FR_ERR_INVALID, "B_global %d not divisible by world %d", B_global, e->world);
   return FR_OK;
@@ -729,22 +742,22 @@ static fr_status shard_check(fr_engine* e, int B_global) {
 extern "C" fr_status fr_shard_gather_push(fr_engine* e, const int32_t* idx, int B_global, fr_stream s) {
   fr_status st = prep(e, &s, B_global, true, false);
   if (st != FR_OK) return st;
-  if ((st = shard_check(e, B_global)) != FR_OK) return st;
+  if ((st = shard_check(e, s, B_global)) != FR_OK) return st;
   const int32_t* d_idx = nullptr;
   if ((st = stage_idx(e, s, idx, B_global, &d_idx)) != FR_OK) return st;
   if (B_global == 0) return FR_OK;
-  return frk_gather_push(e, d_idx, B_global, 0, s->stream);
+  return frk_gather_push(e, d_idx, B_global, s->slot, 0, s->stream);
 }
 
 extern "C" fr_status fr_shard_mlp(fr_engine* e, int B_global, float* scores_local, fr_stream s) {
   fr_status st = prep(e, &s, B_global, false, true);
   if (st != FR_OK) return st;
-  if (!e->d_xchg) return fr_fail(e, FR_ERR_STATE, "fr_shard_init first");
+  if ((st = shard_check(e, s, B_global)) != FR_OK) return st;
   const int Bl = B_global / e->world;
   if (Bl == 0) return FR_OK;
   if (!scores_local) return fr_fail(e, FR_ERR_INVALID, "null scores");
   float* d_scores = is_device_ptr(scores_local) ? scores_local : s->d_scores;
-  if ((st = run_mlp(e, s, e->d_xchg, Bl, d_scores)) != FR_OK) return st;
+  if ((st = run_mlp(e, s, e->d_xchg + fr_xchg_concat_off(e, s->slot, 0), Bl, d_scores)) != FR_OK) return st;
   return emit_scores(e, s, scores_local, Bl, d_scores);
 }
 
@@ -753,29 +766,29 @@ extern "C" fr_status fr_shard_read_concat(fr_engine* e, int B_global, float* con
   if (!e->d_xchg) return fr_fail(e, FR_ERR_STATE, "fr_shard_init first");
   if (!s) s = e->default_stream;
   FR_CUDA(e, cudaSetDevice(e->device));
+  if (s->slot >= e->n_slots) return fr_fail(e, FR_ERR_UNSUPPORTED, "worker has no exchange slot");
   const int Bl = B_global / e->world;
-  const float* src = e->d_xchg + (size_t)(e->shard_step & 1) * xchg_buf_floats(e);  // last step's parity
+  const float* src = e->d_xchg + fr_xchg_concat_off(e, s->slot, s->shard_step & 1);  // last step's parity
   FR_CUDA(e, cudaMemcpyAsync(concat_local, src, (size_t)Bl * e->D * sizeof(float), cudaMemcpyDefault, s->stream));
   return FR_OK;
 }
 
 // One-call sharded step with device-side synchronisation (no host barrier, no NCCL on the data
 // path): push my tables' pieces for the global batch into the owners' buffers of this step's
-// parity -> publish "rank r finished step n" into every peer's flag array -> wait until all
-// ranks have published step n -> MLP over my B_global/world items.  Every rank must call it
-// the same number of times with the same global batch.  Not captured into a graph: the step
-// number is a launch argument.
+// parity -> publish "rank r finished step n of this slot" into every peer's flag block -> wait
+// until all ranks have published step n -> MLP over my B_global/world items.  Every rank must issue
+// the same sequence of calls per worker with the same global batch.  The step number lives on the
+// device, so the step is replayed as a CUDA graph (one per buffer parity).
 static fr_status shard_infer_enqueue(fr_engine* e, fr_stream_s* s, const int32_t* idx, int B_global, float* scores,
-                                     int step) {
+                                     int parity) {
   const int32_t* d_idx = nullptr;
   fr_status st = stage_idx(e, s, idx, B_global, &d_idx);
   if (st != FR_OK) return st;
-  const int parity = step & 1;
-  if ((st = frk_gather_push(e, d_idx, B_global, parity, s->stream)) != FR_OK) return st;
-  if ((st = frk_shard_signal_wait(e, step, s->stream)) != FR_OK) return st;
+  if ((st = frk_gather_push(e, d_idx, B_global, s->slot, parity, s->stream)) != FR_OK) return st;
+  if ((st = frk_shard_signal_wait(e, s->slot, s->stream)) != FR_OK) return st;
   const int Bl = B_global / e->world;
   float* d_scores = is_device_ptr(scores) ? scores : s->d_scores;
-  const float* x = e->d_xchg + (size_t)parity * xchg_buf_floats(e);
+  const float* x = e->d_xchg + fr_xchg_concat_off(e, s->slot, parity);
   if ((st = run_mlp(e, s, x, Bl, d_scores)) != FR_OK) return st;
   return emit_scores(e, s, scores, Bl, d_scores);
 }
@@ -783,14 +796,13 @@ static fr_status shard_infer_enqueue(fr_engine* e, fr_stream_s* s, const int32_t
 extern "C" fr_status fr_shard_infer(fr_engine* e, const int32_t* idx, int B_global, float* scores_local, fr_stream s) {
   fr_status st = prep(e, &s, B_global, true, true);
   if (st != FR_OK) return st;
-  if ((st = shard_check(e, B_global)) != FR_OK) return st;
+  if ((st = shard_check(e, s, B_global)) != FR_OK) return st;
   if (B_global == 0) return FR_OK;
   if (!idx || !scores_local) return fr_fail(e, FR_ERR_INVALID, "null idx/scores");
-  if (s != e->default_stream && !e->streams.empty() && s != e->streams[0])
-    return fr_fail(e, FR_ERR_UNSUPPORTED, "sharded steps are ordered: use one worker stream for fr_shard_infer");
   if (*e->h_shard_err) return fr_fail(e, FR_ERR_STATE, "a previous sharded step timed out waiting for a peer rank");
-  const int step = ++e->shard_step;
-  return shard_infer_enqueue(e, s, idx, B_global, scores_local, step);
+  const int parity = (++s->shard_step) & 1;
+  return run_or_replay(e, s, idx, scores_local, B_global, 1 + parity,
+                       [&] { return shard_infer_enqueue(e, s, idx, B_global, scores_local, parity); });
 }
 
 

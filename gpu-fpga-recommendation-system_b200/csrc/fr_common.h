@@ -44,11 +44,16 @@ struct fr_stream_s {
     const void* idx;
     const void* scores;
     int B, mode, prec;
+    int variant;            // 0: fr_infer; 1 / 2: fr_shard_infer with exchange-buffer parity 0 / 1
     int seen;               // direct (un-captured) runs so far
     int launches;           // kernels inside the graph
     cudaGraphExec_t exec;   // null until captured
   };
   std::vector<Graph> graphs;
+  // table-sharded steps: which exchange slot this worker owns (creation order, identical on every
+  // rank) and how many sharded steps it has issued (parity of the concat buffer = step & 1)
+  int slot = 0;
+  int shard_step = 0;
 };
 
 struct FrPeer {
@@ -68,7 +73,12 @@ struct fr_engine {
   int precision = FR_PREC_TF32;
   int max_batch = 0;
   bool use_graphs = true;  // FR_GRAPHS=0 disables CUDA-graph replay of fr_infer
-  bool use_pdl = true;     // FR_PDL=0: no programmatic dependent launch between the kernels of a batch
+  // Programmatic dependent launch between the kernels of a batch, FR_PDL bit mask: 1 = MLP layers 2 and 3
+  // start under the tail of the layer before, 2 = layer 1 under the lookup, 4 = the lookup under the
+  // previous batch's last layer.  0 = every launch fully serialised.  Default 6: with bit 0 set (a
+  // cluster-launched persistent kernel as the programmatic dependent of another one) 8 deep-queued
+  // worker streams deadlocked on the device in 8 of 12 runs on B200 / driver 580; masks 0 and 6 never did.
+  int pdl_mask = 6;
 
   std::vector<FrTable> tables;
   FrChunk* d_chunks = nullptr;  // [D/4]
@@ -87,7 +97,10 @@ struct fr_engine {
   // sharding
   int rank = 0, world = 1;
   std::vector<int> owner;        // [T], -1 replicated
-  float* d_xchg = nullptr;       // [max_batch/world... sized max_batch][D] receive buffer
+  float* d_xchg = nullptr;       // exchange region: n_slots x { concat[2][max_batch/world][D], flags[world] }
+  int n_slots = 0;               // in-flight sharded steps (one per worker stream), FR_SHARD_SLOTS
+  int next_slot = 0;             // slot handed to the next stream created
+  int* d_step = nullptr;         // [n_slots] device-side step counters (the flag kernel increments its slot's)
   std::vector<FrPeer> peers;     // [world]
   float** d_peer_ptrs = nullptr; // device copy of peers[].concat
   int* d_owned_ids = nullptr;    // concat pieces this rank produces for every item
@@ -95,9 +108,7 @@ struct fr_engine {
   int* d_repl_ids = nullptr;     // pieces of replicated tables (local items only)
   int n_repl = 0;
   bool shard_lists_built = false;
-  int* d_epoch = nullptr;        // device copy of the last published step (debug / introspection)
   int* h_shard_err = nullptr;    // pinned+mapped: set to 1 by the wait kernel on time-out
-  int shard_step = 0;            // host-side step counter of fr_shard_infer
 
   std::atomic<int64_t> launches{0};
   mutable std::string err;
@@ -125,9 +136,19 @@ inline cudaError_t fr_h2d(fr_engine* e, void* dst, const void* src, size_t bytes
 // ---- kernels (each returns after enqueueing; bumps e->launches) -----------
 fr_status frk_upload_chunks(fr_engine* e);
 fr_status frk_gather(fr_engine* e, const int32_t* d_idx, int B, float* d_out, bool round_tf32, cudaStream_t st);
-fr_status frk_gather_push(fr_engine* e, const int32_t* d_idx, int B_global, int parity, cudaStream_t st);
-// publish "this rank finished pushing step `step`" to every peer, then wait for all peers' flags
-fr_status frk_shard_signal_wait(fr_engine* e, int step, cudaStream_t st);
+fr_status frk_gather_push(fr_engine* e, const int32_t* d_idx, int B_global, int slot, int parity, cudaStream_t st);
+// publish "this rank finished pushing the next step of `slot`" to every peer, then wait for all peers' flags
+fr_status frk_shard_signal_wait(fr_engine* e, int slot, cudaStream_t st);
+
+// exchange-region geometry (floats): one slot = two concat buffers + a flag block
+inline size_t fr_xchg_buf_floats(const fr_engine* e) { return (size_t)(e->max_batch / e->world) * e->D; }
+inline size_t fr_xchg_slot_floats(const fr_engine* e) { return 2 * fr_xchg_buf_floats(e) + 64; }
+inline size_t fr_xchg_concat_off(const fr_engine* e, int slot, int parity) {
+  return (size_t)slot * fr_xchg_slot_floats(e) + (size_t)parity * fr_xchg_buf_floats(e);
+}
+inline size_t fr_xchg_flags_off(const fr_engine* e, int slot) {
+  return (size_t)slot * fr_xchg_slot_floats(e) + 2 * fr_xchg_buf_floats(e);
+}
 fr_status frk_fill_reference(fr_engine* e, float* d, int64_t rows, int dim, int64_t debug_rows, cudaStream_t st);
 fr_status frk_fill_hash(fr_engine* e, float* d, uint32_t seed, int table, int64_t rows, int dim, cudaStream_t st);
 fr_status frk_merge(fr_engine* e, const float* A, int64_t rowsA, int dimA, const float* B, int64_t rowsB, int dimB,

@@ -158,7 +158,7 @@ void launch_gather(const fr_engine* e, const int* d_ids, int n_chunks, const int
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (e->use_pdl && !PUSH) ? 1 : 0;   // the sharded push is ordered by its own flag kernel
+  cfg.numAttrs = ((e->pdl_mask & 4) && !PUSH) ? 1 : 0;   // the sharded push is ordered by its own flag kernel
   cudaLaunchKernelEx(&cfg, gather_concat_kernel<ROUND, PUSH>, (const FrChunk*)e->d_chunks, d_ids, n_chunks, d_idx,
                      (int)e->tables.size(), b_begin, b_end, out4, peers, C, items_per_rank, peer_off4);
 }
@@ -268,7 +268,7 @@ static fr_status build_shard_lists(fr_engine* e) {
   return FR_OK;
 }
 
-fr_status frk_gather_push(fr_engine* e, const int32_t* d_idx, int B_global, int parity, cudaStream_t st) {
+fr_status frk_gather_push(fr_engine* e, const int32_t* d_idx, int B_global, int slot, int parity, cudaStream_t st) {
   if (!e->shard_lists_built) {
     std::lock_guard<std::mutex> g(e->mu);
     if (!e->shard_lists_built) {
@@ -278,8 +278,8 @@ fr_status frk_gather_push(fr_engine* e, const int32_t* d_idx, int B_global, int 
   }
   const int per = B_global / e->world;
   const bool round = (e->precision == FR_PREC_TF32);
-  // concat buffer `parity` of every rank's exchange region (same layout on all ranks)
-  const long long off4 = (long long)parity * (e->max_batch / e->world) * (e->D / 4);
+  // concat buffer `parity` of slot `slot` in every rank's exchange region (same layout on all ranks)
+  const long long off4 = (long long)(fr_xchg_concat_off(e, slot, parity) / 4);
   float4* const* peers = reinterpret_cast<float4* const*>(e->d_peer_ptrs);
   if (e->n_owned) {
     if (round) launch_gather<true, true>(e, e->d_owned_ids, e->n_owned, d_idx, 0, B_global, nullptr, peers, per, st, off4);
@@ -288,7 +288,7 @@ fr_status frk_gather_push(fr_engine* e, const int32_t* d_idx, int B_global, int 
   }
   if (e->n_repl) {
     // local items only, written into this rank's own buffer (row b - rank*per)
-    float4* own = reinterpret_cast<float4*>(e->d_xchg) + off4 - (size_t)e->rank * per * (e->D / 4);
+    float4* own = reinterpret_cast<float4*>(e->d_xchg) + off4 - (long long)e->rank * per * (e->D / 4);
     const int b0 = e->rank * per, b1 = (e->rank + 1) * per;
     if (round) launch_gather<true, false>(e, e->d_repl_ids, e->n_repl, d_idx, b0, b1, own, nullptr, 1, st);
     else launch_gather<false, false>(e, e->d_repl_ids, e->n_repl, d_idx, b0, b1, own, nullptr, 1, st);
@@ -298,12 +298,16 @@ fr_status frk_gather_push(fr_engine* e, const int32_t* d_idx, int B_global, int 
   return FR_OK;
 }
 
-// Device-side step barrier of the sharded path.  Flags live behind the two concat buffers of
-// every rank's exchange region: flags[r] = last step rank r finished pushing.
+// Device-side step barrier of the sharded path.  Every slot of a rank's exchange region ends in a
+// flag block: flags[r] = last step of this slot rank r finished pushing.  The step number lives in
+// device memory (one counter per slot, bumped here), so the launch has no per-step argument and the
+// whole sharded step can be replayed as a CUDA graph.
 namespace {
 __global__ void shard_signal_wait_kernel(float* const* __restrict__ peer_base, long long flags_off_floats, int rank,
-                                         int world, int step, int* epoch, int* err, long long timeout_cycles) {
+                                         int world, int* step_counter, int* err, long long timeout_cycles) {
   const int t = threadIdx.x;
+  const int step = *step_counter + 1;   // kernels of one slot are stream-ordered: no race on the counter
+  __syncwarp();
   // all stores of the preceding push kernel(s) are complete (stream order); make them visible
   // system-wide before the flag that announces them
   __threadfence_system();
@@ -311,7 +315,7 @@ __global__ void shard_signal_wait_kernel(float* const* __restrict__ peer_base, l
     int* f = reinterpret_cast<int*>(peer_base[t] + flags_off_floats) + rank;
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f), "r"(step) : "memory");
   }
-  if (t == 0) *epoch = step;
+  if (t == 0) *step_counter = step;
   if (t < world) {
     const int* mine = reinterpret_cast<const int*>(peer_base[rank] + flags_off_floats) + t;
     const long long t0 = clock64();
@@ -327,12 +331,11 @@ __global__ void shard_signal_wait_kernel(float* const* __restrict__ peer_base, l
 }
 }  // namespace
 
-fr_status frk_shard_signal_wait(fr_engine* e, int step, cudaStream_t st) {
-  const long long flags_off = 2ll * (e->max_batch / e->world) * e->D;
+fr_status frk_shard_signal_wait(fr_engine* e, int slot, cudaStream_t st) {
   int* d_err = nullptr;
   FR_CUDA(e, cudaHostGetDevicePointer(&d_err, e->h_shard_err, 0));
-  shard_signal_wait_kernel<<<1, 32, 0, st>>>(e->d_peer_ptrs, flags_off, e->rank, e->world, step, e->d_epoch, d_err,
-                                             4000000000ll /* ~2 s at 1.9 GHz */);
+  shard_signal_wait_kernel<<<1, 32, 0, st>>>(e->d_peer_ptrs, (long long)fr_xchg_flags_off(e, slot), e->rank, e->world,
+                                             e->d_step + slot, d_err, 20000000000ll /* ~10 s at 1.9 GHz */);
   e->launches++;
   FR_CUDA(e, cudaGetLastError());
   return FR_OK;

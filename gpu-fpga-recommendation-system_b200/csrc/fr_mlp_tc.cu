@@ -250,7 +250,8 @@ struct TcParams {
   const float* b4;     // EPI_DOT: output-layer bias [1] or null
   int M, N, K;
   int relu, sigmoid;
-  int pdl;             // launched with programmatic stream serialization
+  int pdl;             // issue griddepcontrol.wait / launch_dependents (no-ops unless a launch in the chain
+                       // carries the programmatic-serialization attribute)
 };
 
 // kind::tf32 instruction descriptor: D=f32, A=B=tf32, both K-major, M = 128*CTAS, N = n.
@@ -500,7 +501,7 @@ int g_max_clusters = 0;   // FR_TC_MAX_CLUSTERS: cap the persistent grid (tests 
 
 template <int BLOCK_N, int STAGES, int EPI, int CTAS>
 fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const TcParams& p,
-                 cudaStream_t st) {
+                 bool pdl_attr, cudaStream_t st) {
   using L = SmemLayout<BLOCK_N, STAGES, CTAS>;
   static_assert(L::kDyn <= 227 * 1024, "tile configuration exceeds the 227 KB shared memory of an SM");
   static_assert(L::kTmemCols == 256 || L::kTmemCols == 512, "TMEM allocation must be a power of two");
@@ -529,7 +530,7 @@ fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = p.pdl ? 2 : 1;
+  cfg.numAttrs = pdl_attr ? 2 : 1;
   FR_CUDA(e, cudaLaunchKernelEx(&cfg, kern, a, b, o, p));
   e->launches++;
   return FR_OK;
@@ -629,14 +630,15 @@ fr_status frtc_layer(fr_engine* e, fr_stream_s* s, int k, const float* in, int B
   p.sigmoid = act ? 1 : 0;
   p.w4 = e->d_W[3];
   p.b4 = act ? e->d_bias[3] : nullptr;
-  p.pdl = e->use_pdl ? 1 : 0;
+  p.pdl = e->pdl_mask ? 1 : 0;
+  const bool pa = (e->pdl_mask & (k == 0 ? 2 : 1)) != 0;   // may this layer start under the tail of its predecessor
   p.out = d_scores;
   const TcLayerCfg c = st->cfg[k];
   const CUtensorMap& w = st->w_map[k];
   cudaStream_t cs = s->stream;
   if (k < 2) {
-    if (c.ctas == 2) return c.block_n == 256 ? launch<256, 5, EPI_STORE, 2>(e, a, w, o, p, cs) : launch<128, 7, EPI_STORE, 2>(e, a, w, o, p, cs);
-    return c.block_n == 256 ? launch<256, 3, EPI_STORE, 1>(e, a, w, o, p, cs) : launch<128, 5, EPI_STORE, 1>(e, a, w, o, p, cs);
+    if (c.ctas == 2) return c.block_n == 256 ? launch<256, 5, EPI_STORE, 2>(e, a, w, o, p, pa, cs) : launch<128, 7, EPI_STORE, 2>(e, a, w, o, p, pa, cs);
+    return c.block_n == 256 ? launch<256, 3, EPI_STORE, 1>(e, a, w, o, p, pa, cs) : launch<128, 5, EPI_STORE, 1>(e, a, w, o, p, pa, cs);
   }
-  return c.ctas == 2 ? launch<256, 5, EPI_DOT, 2>(e, a, w, o, p, cs) : launch<256, 3, EPI_DOT, 1>(e, a, w, o, p, cs);
+  return c.ctas == 2 ? launch<256, 5, EPI_DOT, 2>(e, a, w, o, p, pa, cs) : launch<256, 3, EPI_DOT, 1>(e, a, w, o, p, pa, cs);
 }
