@@ -234,6 +234,8 @@ def run_ours(args):
     gate_err = float(np.max(np.abs(sc_host[0].numpy() - exp_s) / np.maximum(np.abs(exp_s), 1e-6)))
     assert gate_err <= (1e-3 if args.precision == "tf32" else 2e-5), f"score parity gate failed: {gate_err}"
 
+    host_us = {}   # host time to enqueue one step (if it approaches ms_per_step the host, not the GPU, is the limit)
+
     def timed(step_fn, steps, warmup):
         trace(f"timed({step_fn.__name__}, {steps}, {warmup}) graphs")
         # one-time setup, like loading weights: every (index buffer, score buffer) pair is shown to
@@ -251,8 +253,10 @@ def run_ours(args):
         e0.record(main)
         for s in wstreams:
             s.wait_event(e0)
+        t_host = time.perf_counter()
         for i in range(steps):
             step_fn(i)
+        host_us[step_fn.__name__] = (time.perf_counter() - t_host) / steps * 1e6
         for s in wstreams:
             ev = torch.cuda.Event()
             ev.record(s)
@@ -367,7 +371,7 @@ def run_ours(args):
             "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": Bg * T * 4, "d2h_bytes_per_step": B * 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
+            "gpu_launches": int(launches), "host_enqueue_us_per_step": host_us, "clocks": clocks, "roofline": roofline, "kernels": kernels,
             "gather_standalone": gather, "mlp_large_batch": large, "cpu_baseline": cpu}
     print(json.dumps(line))
     if dist is not None:
@@ -528,7 +532,21 @@ def run_sweep(args):
                       "value": best["dev_p99_us"], "best_batch": best["batch"], "data": "synthetic", "sweep": rows}))
 
 
+def arm_hard_limit():
+    """A run that has not finished after BENCH_HARD_LIMIT_S (default 900 s; the whole default run takes
+    under a minute) is hung: say so and leave, instead of holding the GPU until somebody else's limit."""
+    limit = float(os.environ.get("BENCH_HARD_LIMIT_S", "900"))
+
+    def fire():
+        print(f"bench.py: no result after {limit:.0f} s -- device or collective hung; aborting", file=sys.stderr, flush=True)
+        os._exit(3)
+    t = threading.Timer(limit, fire)
+    t.daemon = True
+    t.start()
+
+
 def main():
+    arm_hard_limit()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
@@ -536,7 +554,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="small")
     ap.add_argument("--batch", type=int, default=2048)
-    ap.add_argument("--streams", type=int, default=8)
+    ap.add_argument("--streams", type=int, default=12)
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--tiles", default="", help="FR_TC_TILES override: N1,N2,N3,ctas")
     ap.add_argument("--shard", default="tables", choices=["replicated", "tables"],

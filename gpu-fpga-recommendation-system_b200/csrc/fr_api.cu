@@ -195,6 +195,7 @@ extern "C" void fr_destroy(fr_engine* e) {
   cudaFree(e->d_xchg);
   cudaFree(e->d_step);
   if (e->h_shard_err) cudaFreeHost(e->h_shard_err);
+  if (e->h_watch) cudaFreeHost(e->h_watch);
   delete e;
 }
 
@@ -562,7 +563,15 @@ extern "C" fr_status fr_layer_only(fr_engine* e, int k, const float* x, int B, f
 extern "C" fr_status fr_sync(fr_engine* e, fr_stream s) {
   if (!e) return fr_fail(nullptr, FR_ERR_INVALID, "null engine");
   if (!s) s = e->default_stream;
-  FR_CUDA(e, cudaStreamSynchronize(s->stream));
+  cudaError_t ce = cudaStreamSynchronize(s->stream);
+  if (ce != cudaSuccess) {
+    const int* w = e->h_watch;
+    if (w && w[0])
+      return fr_fail(e, FR_ERR_CUDA, "cudaStreamSynchronize: %s; tcgen05 kernel watchdog: wait %d (1 smem slot free, 2 TMEM stage "
+                     "free, 3 smem slot full, 4 TMEM stage full) gave up in CTA %d of %d, warp %d, parity %d, counters %d/%d",
+                     cudaGetErrorString(ce), w[1], w[2], w[5], w[3], w[4], w[6], w[7]);
+    return fr_fail(e, FR_ERR_CUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(ce));
+  }
   return FR_OK;
 }
 
@@ -654,7 +663,7 @@ extern "C" fr_status fr_shard_init(fr_engine* e, int rank, int world, const int*
   }
   if (world > 32) return fr_fail(e, FR_ERR_UNSUPPORTED, "world %d > 32 (one warp publishes and polls the flags)", world);
   FR_CUDA(e, cudaSetDevice(e->device));
-  e->n_slots = 9;   // the default worker + 8 created workers
+  e->n_slots = 17;   // the default worker + 16 created workers
   if (const char* env = getenv("FR_SHARD_SLOTS")) e->n_slots = atoi(env) > 0 ? atoi(env) : 1;
   const size_t bytes = (size_t)e->n_slots * fr_xchg_slot_floats(e) * sizeof(float);
   FR_CUDA(e, cudaMalloc(&e->d_xchg, bytes));

@@ -76,9 +76,10 @@ struct fr_engine {
   // Programmatic dependent launch between the kernels of a batch, FR_PDL bit mask: 1 = MLP layers 2 and 3
   // start under the tail of the layer before, 2 = layer 1 under the lookup, 4 = the lookup under the
   // previous batch's last layer.  0 = every launch fully serialised.  Default 6: with bit 0 set (a
-  // cluster-launched persistent kernel as the programmatic dependent of another one) 8 deep-queued
-  // worker streams deadlocked on the device in 8 of 12 runs on B200 / driver 580; masks 0 and 6 never did.
-  int pdl_mask = 6;
+  // Default 0: with programmatic edges inside the replayed graphs, 8-12 deep-queued worker streams
+  // deadlocked on the device intermittently on B200 / driver 580 (bit 0: 8 of 12 runs; mask 6: 1 of ~12),
+  // never without them; with 8 workers in flight the edges buy <= 2% anyway (10% with 4 workers).
+  int pdl_mask = 0;
 
   std::vector<FrTable> tables;
   FrChunk* d_chunks = nullptr;  // [D/4]
@@ -109,6 +110,7 @@ struct fr_engine {
   int n_repl = 0;
   bool shard_lists_built = false;
   int* h_shard_err = nullptr;    // pinned+mapped: set to 1 by the wait kernel on time-out
+  int* h_watch = nullptr;        // pinned+mapped int[8]: which barrier wait a tcgen05 kernel gave up on before trapping
 
   std::atomic<int64_t> launches{0};
   mutable std::string err;

@@ -23,6 +23,7 @@
 // K tails (880 = 27.5 slices) and M tails rely on TMA zero fill of out-of-bounds
 // box elements; stores are masked by the row count.
 #include <cuda.h>
+#include <string.h>
 
 #include "fr_common.h"
 
@@ -45,17 +46,42 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
+// Where a kernel that gave up waiting says so: pinned + mapped host memory, written once, then trap.
+// {magic, code, blockIdx.x, warp, parity, gridDim.x, k-slices done, tile}
+__device__ int* g_watch = nullptr;
+constexpr long long kWatchCycles = 6000000000ll;   // ~3 s at 1.97 GHz: no legitimate wait comes close
+
+__device__ __noinline__ void watchdog_fire(int code, uint32_t parity, uint32_t a, uint32_t b) {
+  int* w = g_watch;
+  if (w && atomicCAS(w, 0, 0x57415443) == 0) {
+    w[1] = code; w[2] = blockIdx.x; w[3] = threadIdx.x / 32; w[4] = (int)parity; w[5] = gridDim.x; w[6] = (int)a; w[7] = (int)b;
+    __threadfence_system();
+  }
+  __trap();
+}
+
+// Bounded spin: a wait that outlives kWatchCycles is a protocol bug (or a peer CTA that died); the
+// kernel records which wait it was and traps, so the host sees an error instead of a hung stream.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int code = 0, uint32_t a = 0, uint32_t b = 0) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t spins = 0; !done; spins++) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && (spins & 1023) == 1023) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kWatchCycles) watchdog_fire(code, parity, a, b);
+    }
+  }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -329,7 +355,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int kb = 0; kb < num_kb; kb++, kc++) {
           const int s = kc % STAGES;
           const uint32_t ph = (kc / STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_wait(&empty_bar[s], ph ^ 1, 1, kc, tile);
           uint8_t* a_dst = smem + s * L::kStageBytes;
           uint8_t* b_dst = a_dst + L::kABytes;
           if (CTAS == 2) {
@@ -354,13 +380,13 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t kc = 0, it = 0;
       for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
         const uint32_t as = it & 1;
-        mbar_wait(&tmem_empty_bar[as], ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator stage
+        mbar_wait(&tmem_empty_bar[as], ((it >> 1) & 1) ^ 1, 2, kc, tile);   // the epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         for (int kb = 0; kb < num_kb; kb++, kc++) {
           const int s = kc % STAGES;
           const uint32_t ph = (kc / STAGES) & 1;
-          mbar_wait(&full_bar[s], ph);
+          mbar_wait(&full_bar[s], ph, 3, kc, tile);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
@@ -394,7 +420,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t as = it & 1;
       const int row0 = ((tile / n_tiles_n) * CTAS + (int)rank) * BLOCK_M + q * 32;
       const int n0 = (tile % n_tiles_n) * BLOCK_N;
-      mbar_wait(&tmem_full_bar[as], (it >> 1) & 1);
+      mbar_wait(&tmem_full_bar[as], (it >> 1) & 1, 4, it, tile);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
       float dot = 0.f;
@@ -498,6 +524,11 @@ fr_status encode_2d(fr_engine* e, TcState* st, CUtensorMap* map, const void* bas
 }
 
 int g_max_clusters = 0;   // FR_TC_MAX_CLUSTERS: cap the persistent grid (tests force several tiles per cluster)
+// A cluster's fixed cost (pipeline fill, last epilogue, teardown: ~4 us) is only hidden behind further
+// tiles, so short tiles are ganged: every cluster gets at least this many K-slices of main loop
+// (FR_TC_MIN_KB; small model layer 1 has 11 per tile -> two tiles per cluster, +10% batches/s with 8
+// workers in flight, at +5 us latency of that layer).
+int g_min_kb = 16;
 
 template <int BLOCK_N, int STAGES, int EPI, int CTAS>
 fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const TcParams& p,
@@ -516,7 +547,10 @@ fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const
   const int n_tiles = (p.M + BLOCK_M * CTAS - 1) / (BLOCK_M * CTAS) * (p.N / BLOCK_N);
   int max_clusters = e->sm_count / CTAS;
   if (g_max_clusters > 0 && g_max_clusters < max_clusters) max_clusters = g_max_clusters;   // test knob
-  const int n_clusters = n_tiles < max_clusters ? n_tiles : max_clusters;
+  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int gang = num_kb >= g_min_kb ? 1 : (g_min_kb + num_kb - 1) / num_kb;   // tiles per cluster wanted
+  int n_clusters = (n_tiles + gang - 1) / gang;
+  if (n_clusters > max_clusters) n_clusters = max_clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n_clusters * CTAS, 1, 1);
   cfg.blockDim = dim3(kThreads, 1, 1);
@@ -589,6 +623,14 @@ fr_status frtc_prepare(fr_engine* e) {
   parse_tiles(st->cfg);
   const char* cap = getenv("FR_TC_MAX_CLUSTERS");
   g_max_clusters = cap ? atoi(cap) : 0;
+  if (const char* env = getenv("FR_TC_MIN_KB")) g_min_kb = atoi(env) > 0 ? atoi(env) : 1;
+  if (!e->h_watch) {
+    FR_CUDA(e, cudaHostAlloc(&e->h_watch, 8 * sizeof(int), cudaHostAllocMapped));
+    memset(e->h_watch, 0, 8 * sizeof(int));
+  }
+  int* d_watch = nullptr;
+  FR_CUDA(e, cudaHostGetDevicePointer(&d_watch, e->h_watch, 0));
+  FR_CUDA(e, cudaMemcpyToSymbol(g_watch, &d_watch, sizeof(d_watch)));
   for (int k = 0; k < 3; k++) {
     const TcLayerCfg c = st->cfg[k];
     if ((c.block_n != 128 && c.block_n != 256) || (c.ctas != 1 && c.ctas != 2))

@@ -333,3 +333,27 @@ def test_tf32_persistent_tile_loop(tiles, clusters, pdl, monkeypatch):
     assert rel_err(got, oracle.mlp(x, dims, W, b, mode=1)) <= TOL
     eng.close()
     monkeypatch.delenv("FR_TC_MAX_CLUSTERS", raising=False)
+
+
+def test_merge_planner_engine_matches_unmerged_engine():
+    """plan merges under a byte budget, build the merged tables on the device
+    (fr_merge_tables), drive the merged engine with remapped indices: concat vectors bit-identical
+    to the un-merged engine's and to the oracle's, scores within tolerance, fewer index columns read."""
+    from fleetrec import merge
+    cat = catalogue.load("small").with_row_cap(2000)
+    dims = cat.layer_dims
+    tables = oracle.make_tables(cat, "hash", seed=31)
+    W, b = oracle.make_weights(dims, seed=42)
+    plan = merge.plan_merges(cat, 256 << 20)
+    assert plan.lookups_saved >= 4
+    mm = merge.apply_merges(cat, plan.pairs)
+    eng = merge.build(mm, tables, max_batch=512)
+    eng.load_mlp(W, b)
+    idx = oracle.zipf_indices(cat, 500, seed=3)
+    idx[0, :] = 0
+    idx[1, :] = [t.rows - 1 for t in cat.tables]
+    exp = oracle.gather(cat, tables, idx)
+    got = eng.gather_only(mm.remap(idx))
+    assert_bits_equal(got, exp)
+    assert rel_err(eng.infer(mm.remap(idx)), oracle.mlp(exp, dims, W, b, mode=1)) <= TOL
+    eng.close()

@@ -167,3 +167,63 @@ def test_catalogue_bytes_and_flops():
     assert [m[n].gather_bytes_per_item() for n in ("small", "medium", "large")] == [1596, 3896, 17380]
     assert [m[n].mlp_flops_per_item() for n in ("small", "medium", "large")] == [2032128, 3113472, 18612736]
     assert abs(m["small"].table_bytes() / 1e9 - 1.415) < 1e-3
+
+
+# ---------------------------------------------------------------- Cartesian-merge planner
+def test_merge_planner_preserves_the_concat_vector():
+    """plan -> merged catalogue -> remapped indices: gathering from the merged tables gives the
+    ORIGINAL concat vector bit for bit (incl. corner rows), with fewer lookups per item, inside the
+    byte budget and the int32 index range."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                    "gpu-fpga-recommendation-system_b200"))
+    from fleetrec import catalogue, merge
+    cat = catalogue.load("small").with_row_cap(300)
+    budget = 40 << 20
+    plan = merge.plan_merges(cat, budget)
+    assert plan.pairs and plan.extra_bytes <= budget
+    flat = [t for p in plan.pairs for t in p]
+    assert len(flat) == len(set(flat))                                   # every table merged at most once
+    mm = merge.apply_merges(cat, plan.pairs)
+    assert merge.lookups_per_item(mm) == cat.n_tables - plan.lookups_saved
+    assert mm.model.concat_floats == cat.concat_floats
+    tables = oracle.make_tables(cat, "hash", seed=4)
+    new_tables = [None] * mm.model.n_tables
+    for new, old in enumerate(mm.kept):
+        new_tables[new] = tables[old]
+    for k, (a, b) in enumerate(plan.pairs):
+        new_tables[mm.merged_ids[k]] = oracle.merge_tables(tables[a], tables[b])
+        new_tables[mm.source_ids[k][0]], new_tables[mm.source_ids[k][1]] = tables[a], tables[b]
+        assert new_tables[mm.merged_ids[k]].shape == (mm.model.tables[mm.merged_ids[k]].rows,
+                                                      mm.model.tables[mm.merged_ids[k]].dim)
+    idx = oracle.uniform_indices(cat, 64, seed=8)
+    idx[0, :] = 0                                                        # corner rows: first / last of every table
+    idx[1, :] = [t.rows - 1 for t in cat.tables]
+    idx[2, ::2] = 0
+    got = oracle.gather(mm.model, new_tables, mm.remap(idx))
+    exp = oracle.gather(cat, tables, idx)
+    assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+
+
+def test_merge_planner_respects_budget_and_int32():
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                    "gpu-fpga-recommendation-system_b200"))
+    from fleetrec import catalogue, merge
+    cat = catalogue.load("medium")
+    assert merge.plan_merges(cat, 0).pairs == []
+    small = merge.plan_merges(cat, 1 << 20)
+    big = merge.plan_merges(cat, 64 << 30)
+    assert small.extra_bytes <= 1 << 20 and len(small.pairs) <= len(big.pairs)
+    for a, b in big.pairs:
+        assert cat.tables[a].rows * cat.tables[b].rows <= merge.INT32_MAX
+    # an over-large product is refused outright (host.cpp:379-382 only warns)
+    with pytest.raises(OverflowError):
+        merge.apply_merges(cat, [(max(cat.tables, key=lambda t: t.rows).id,
+                                  sorted(cat.tables, key=lambda t: t.rows)[-2].id)])
+    mm = merge.apply_merges(cat, big.pairs[:1])
+    bad = np.zeros((1, cat.n_tables), np.int64)
+    a, b = big.pairs[0]
+    bad[0, a], bad[0, b] = 2 ** 31, 5                                    # index outside the table: remap must not wrap
+    with pytest.raises(OverflowError):
+        mm.remap(bad)
