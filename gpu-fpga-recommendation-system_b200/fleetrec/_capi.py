@@ -31,6 +31,15 @@ class ModelDesc(C.Structure):
                 ("hidden", C.c_int * 4), ("mlp_mode", C.c_int), ("precision", C.c_int), ("max_batch", C.c_int)]
 
 
+class BatcherConfig(C.Structure):
+    _fields_ = [("max_batch", C.c_int), ("max_delay_us", C.c_int), ("n_workers", C.c_int)]
+
+
+class BatcherStats(C.Structure):
+    _fields_ = [("batches", C.c_int64), ("items", C.c_int64), ("requests", C.c_int64), ("closed_by_deadline", C.c_int64),
+                ("latency_p50_us", C.c_float), ("latency_p99_us", C.c_float)]
+
+
 _P, _I, _I64, _U32 = C.c_void_p, C.c_int, C.c_int64, C.c_uint32
 # name -> (restype, argtypes); must list every symbol include/fleetrec.h declares
 SIGNATURES = {
@@ -69,6 +78,12 @@ SIGNATURES = {
     "fr_shard_read_concat": (_I, [_P, _I, _P, _P]),
     "fr_merge_index": (_I64, [_I64, _I64, _I64]),
     "fr_merge_tables": (_I, [_P, _I, _I, _I]),
+    "fr_batcher_create": (_I, [_P, C.POINTER(BatcherConfig), C.POINTER(_P)]),
+    "fr_batcher_submit": (_I, [_P, _P, _I, _P, C.POINTER(C.c_uint64)]),
+    "fr_batcher_wait": (_I, [_P, C.c_uint64]),
+    "fr_batcher_flush": (_I, [_P]),
+    "fr_batcher_get_stats": (_I, [_P, C.POINTER(BatcherStats)]),
+    "fr_batcher_destroy": (None, [_P]),
 }
 
 _LIB = None

@@ -249,5 +249,43 @@ class Engine:
         self._chk(self._L.fr_merge_tables(self._h, a, b, dst))
 
 
+class Batcher:
+    """Request-driven batch former in front of Engine.infer (fr_batcher_*):
+    replaces the reference's fixed batch hand-out (cuda_server.c:406-417).  submit() may be called
+    from any number of threads (ctypes releases the GIL)."""
+
+    def __init__(self, engine, max_batch, max_delay_us=200, n_workers=4):
+        self.engine = engine
+        cfg = _capi.BatcherConfig(max_batch, max_delay_us, n_workers)
+        h = C.c_void_p()
+        engine._chk(engine._L.fr_batcher_create(engine._h, C.byref(cfg), C.byref(h)))
+        self._h = h
+
+    def submit(self, idx, scores_out):
+        """idx [n][T] int32 (copied), scores_out [n] float32 (written later); returns a ticket."""
+        idx = np.ascontiguousarray(idx, np.int32)
+        assert scores_out.dtype == np.float32 and scores_out.flags.c_contiguous and scores_out.shape[0] == idx.shape[0]
+        t = C.c_uint64()
+        self.engine._chk(self.engine._L.fr_batcher_submit(self._h, idx.ctypes.data, idx.shape[0], scores_out.ctypes.data,
+                                                          C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        self.engine._chk(self.engine._L.fr_batcher_wait(self._h, ticket))
+
+    def flush(self):
+        self.engine._chk(self.engine._L.fr_batcher_flush(self._h))
+
+    def stats(self):
+        s = _capi.BatcherStats()
+        self.engine._chk(self.engine._L.fr_batcher_get_stats(self._h, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in s._fields_}
+
+    def close(self):
+        if self._h:
+            self.engine._L.fr_batcher_destroy(self._h)
+            self._h = None
+
+
 def merge_index(iA, iB, rowsB):
     return _capi.lib().fr_merge_index(iA, iB, rowsB)

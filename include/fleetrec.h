@@ -198,6 +198,34 @@ int64_t fr_merge_index(int64_t iA, int64_t iB, int64_t rowsB);
  * as table `dst_table` (whose desc must have rows = rowsA*rowsB, dim = dimA+dimB). */
 fr_status fr_merge_tables(fr_engine* e, int table_a, int table_b, int dst_table);
 
+/* ---- request-driven batching front-end, SURVEY.md section 8(f)2 -------------- */
+/* Replaces the reference's fixed batch hand-out (cuda_server.c:23-25,406-417: THREAD_NUM workers
+ * pull batch numbers off a mutex-guarded counter and block in read() until BATCH_SIZE items have
+ * arrived, cuda_server.c:425-461) with a batch former: requests of any size from any thread are
+ * packed into pinned staging buffers; a batch is dispatched to a worker stream when it holds
+ * max_batch items or when its oldest request has waited max_delay_us.  Host threads only; the
+ * device work is fr_infer's.  Not available on a table-sharded engine. */
+typedef struct fr_batcher fr_batcher;
+typedef struct fr_batcher_config {
+  int max_batch;     /* items per dispatched batch, <= the engine's max_batch        */
+  int max_delay_us;  /* the open batch is dispatched once its oldest request has waited this long    */
+  int n_workers;     /* worker threads = fr_streams = batches in flight (THREAD_NUM) */
+} fr_batcher_config;
+typedef struct fr_batcher_stats {
+  int64_t batches, items, requests, closed_by_deadline;
+  float latency_p50_us, latency_p99_us;   /* submit -> scores written, last <= 65536 request parts */
+} fr_batcher_stats;
+fr_status fr_batcher_create(fr_engine* e, const fr_batcher_config* cfg, fr_batcher** out);
+/* idx [n][n_tables] is copied before the call returns; scores_out[n] is written by a worker
+ * thread and valid once fr_batcher_wait(ticket) returns.  n may exceed max_batch (split). */
+fr_status fr_batcher_submit(fr_batcher* b, const int32_t* idx, int n, float* scores_out, uint64_t* ticket);
+fr_status fr_batcher_wait(fr_batcher* b, uint64_t ticket);
+/* Dispatch the open batch now, whatever it holds. */
+fr_status fr_batcher_flush(fr_batcher* b);
+fr_status fr_batcher_get_stats(fr_batcher* b, fr_batcher_stats* out);
+/* Scores everything already submitted, then stops the threads and frees the staging buffers. */
+void fr_batcher_destroy(fr_batcher* b);
+
 #ifdef __cplusplus
 }
 #endif

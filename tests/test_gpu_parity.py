@@ -357,3 +357,90 @@ def test_merge_planner_engine_matches_unmerged_engine():
     assert_bits_equal(got, exp)
     assert rel_err(eng.infer(mm.remap(idx)), oracle.mlp(exp, dims, W, b, mode=1)) <= TOL
     eng.close()
+
+
+# ---------------------------------------------------------------- request-driven batching front-end (8f-2)
+def test_batcher_many_producers_match_oracle():
+    """fr_batcher: requests of random sizes from several threads are packed into batches (full or
+    closed by the deadline), scored on worker streams, and every request gets exactly its own
+    scores back -- against the oracle on the union of all requests."""
+    import threading
+    cat = catalogue.load("small").with_row_cap(20000)
+    dims = cat.layer_dims
+    tables = oracle.make_tables(cat, "hash", seed=13)
+    W, b = oracle.make_weights(dims, seed=42)
+    eng = fleetrec.Engine(cat, max_batch=512)
+    eng.load_tables(tables)
+    eng.load_mlp(W, b)
+    bat = fleetrec.Batcher(eng, max_batch=512, max_delay_us=500, n_workers=3)
+    n_threads, per_thread = 4, 40
+    rng = np.random.default_rng(0)
+    sizes = rng.integers(1, 300, (n_threads, per_thread))
+    sizes[0, 0] = 1500                                         # larger than max_batch: split over batches
+    reqs = [[oracle.zipf_indices(cat, int(sizes[t, i]), seed=1000 * t + i) for i in range(per_thread)]
+            for t in range(n_threads)]
+    outs = [[np.full(int(sizes[t, i]), np.nan, np.float32) for i in range(per_thread)] for t in range(n_threads)]
+    errors = []
+
+    def producer(t):
+        try:
+            tickets = [bat.submit(reqs[t][i], outs[t][i]) for i in range(per_thread)]
+            for tk in tickets:
+                bat.wait(tk)
+        except Exception as ex:  # noqa: BLE001
+            errors.append(ex)
+    threads = [threading.Thread(target=producer, args=(t,)) for t in range(n_threads)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=120)
+    assert not errors, errors
+    allidx = np.concatenate([r for rs in reqs for r in rs])
+    exp = oracle.mlp(oracle.gather(cat, tables, allidx), dims, W, b, mode=1)
+    got = np.concatenate([o for os_ in outs for o in os_])
+    assert not np.isnan(got).any()
+    assert rel_err(got, exp) <= TOL
+    st = bat.stats()
+    assert st["items"] == allidx.shape[0] and st["requests"] >= n_threads * per_thread
+    assert st["batches"] >= allidx.shape[0] // 512 and st["latency_p99_us"] >= st["latency_p50_us"] > 0
+    bat.close()
+    eng.close()
+
+
+def test_batcher_deadline_flush_and_errors():
+    import time
+    cat = catalogue.load("small").with_row_cap(5000)
+    dims = cat.layer_dims
+    tables = oracle.make_tables(cat, "hash", seed=14)
+    W, b = oracle.make_weights(dims, seed=42)
+    eng = fleetrec.Engine(cat, max_batch=4096)
+    eng.load_tables(tables)
+    eng.load_mlp(W, b)
+    with pytest.raises(fleetrec.FleetRecError):
+        fleetrec.Batcher(eng, max_batch=8192)                  # above the engine's max_batch
+    bat = fleetrec.Batcher(eng, max_batch=4096, max_delay_us=3000, n_workers=2)
+    idx = oracle.zipf_indices(cat, 7, seed=1)
+    out = np.zeros(7, np.float32)
+    t0 = time.perf_counter()
+    bat.wait(bat.submit(idx, out))                             # 7 of 4096 items: only the deadline closes it
+    waited = time.perf_counter() - t0
+    assert 0.002 <= waited < 2.0, waited
+    exp = oracle.mlp(oracle.gather(cat, tables, idx), dims, W, b, mode=1)
+    assert rel_err(out, exp) <= TOL
+    assert bat.stats()["closed_by_deadline"] == 1
+    bat.close()
+    bat = fleetrec.Batcher(eng, max_batch=4096, max_delay_us=10_000_000, n_workers=1)
+    out2 = np.zeros(7, np.float32)
+    tk = bat.submit(idx, out2)
+    bat.flush()                                                # explicit flush beats a 10 s deadline
+    t0 = time.perf_counter()
+    bat.wait(tk)
+    assert time.perf_counter() - t0 < 2.0
+    assert np.array_equal(out2, out)
+    with pytest.raises(fleetrec.FleetRecError):
+        bat.wait(10 ** 9)                                      # unknown ticket
+    out3 = np.zeros(5, np.float32)
+    bat.submit(oracle.zipf_indices(cat, 5, seed=2), out3)
+    bat.close()                                                # destroy drains what was submitted
+    assert np.all(out3 > 0)
+    eng.close()
