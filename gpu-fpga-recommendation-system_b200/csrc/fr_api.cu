@@ -157,6 +157,7 @@ extern "C" fr_status fr_create(const fr_model_desc* desc, int n_gpus, const int*
   e->max_batch = desc->max_batch;
   if (const char* env = getenv("FR_GRAPHS")) e->use_graphs = atoi(env) != 0;
   if (const char* env = getenv("FR_PDL")) e->pdl_mask = atoi(env) & 7;
+  if (const char* env = getenv("FR_FUSE")) e->fuse_lookup = atoi(env) != 0;
   e->tables.resize(desc->n_tables);
   for (int t = 0; t < desc->n_tables; t++) {
     e->tables[t].rows = desc->tables[t].rows;
@@ -187,6 +188,7 @@ extern "C" void fr_destroy(fr_engine* e) {
     cudaFree(e->d_bias[k]);
   }
   cudaFree(e->d_chunks);
+  cudaFree(e->d_fchunks);
   cudaFree(e->d_owned_ids);
   cudaFree(e->d_repl_ids);
   for (int r = 0; r < (int)e->peers.size(); r++)
@@ -427,8 +429,19 @@ static fr_status infer_enqueue(fr_engine* e, fr_stream_s* s, const int32_t* idx,
   const int32_t* d_idx = nullptr;
   fr_status st = stage_idx(e, s, idx, B, &d_idx);
   if (st != FR_OK) return st;
-  if ((st = frk_gather(e, d_idx, B, s->d_x, e->precision == FR_PREC_TF32, s->stream)) != FR_OK) return st;
   float* d_scores = (B > 0 && is_device_ptr(scores)) ? scores : s->d_scores;
+  if (B > 0 && frtc_can_fuse(e)) {
+    // lookup fused into layer 1: the concat vectors never exist in global memory (3 launches)
+    if ((st = frtc_fused_layer1(e, s, d_idx, B)) != FR_OK) return st;
+    const float* in = s->d_h[0];
+    for (int k = 1; k < 3; k++) {
+      const float* out = nullptr;
+      if ((st = run_mlp_step(e, s, k, in, B, d_scores, &out)) != FR_OK) return st;
+      in = out;
+    }
+    return emit_scores(e, s, scores, B, d_scores);
+  }
+  if ((st = frk_gather(e, d_idx, B, s->d_x, e->precision == FR_PREC_TF32, s->stream)) != FR_OK) return st;
   if ((st = run_mlp(e, s, s->d_x, B, d_scores)) != FR_OK) return st;
   return emit_scores(e, s, scores, B, d_scores);
 }
@@ -612,7 +625,17 @@ extern "C" fr_status fr_time_kernels(fr_engine* e, const int32_t* idx, int B, in
   // every kernel is timed alone, back to back `reps` times, events on its own stream
   for (int pass = 0; pass < 2; pass++) {  // pass 0 = warm-up
     const float* in = s->d_x;
-    if (e->world == 1) {
+    const bool fused = frtc_can_fuse(e);
+    if (fused) {
+      // no stand-alone lookup in the step: slot 0 stays 0, slot 1 is lookup + layer 1 in one kernel
+      FR_CUDA(e, cudaEventRecord(e0, s->stream));
+      for (int r = 0; r < reps; r++)
+        if ((st = frtc_fused_layer1(e, s, d_idx, B)) != FR_OK) return st;
+      FR_CUDA(e, cudaEventRecord(e1, s->stream));
+      FR_CUDA(e, cudaEventSynchronize(e1));
+      FR_CUDA(e, cudaEventElapsedTime(&ms5[1], e0, e1));
+      in = s->d_h[0];
+    } else if (e->world == 1) {
       FR_CUDA(e, cudaEventRecord(e0, s->stream));
       for (int r = 0; r < reps; r++)
         if ((st = frk_gather(e, d_idx, B, s->d_x, round, s->stream)) != FR_OK) return st;
@@ -623,7 +646,7 @@ extern "C" fr_status fr_time_kernels(fr_engine* e, const int32_t* idx, int B, in
       // sharded: the lookup needs every rank; time the MLP on this worker's last exchanged batch
       in = e->d_xchg + fr_xchg_concat_off(e, s->slot < e->n_slots ? s->slot : 0, s->shard_step & 1);
     }
-    for (int k = 0; k < mlp_steps(e); k++) {
+    for (int k = fused ? 1 : 0; k < mlp_steps(e); k++) {
       const float* out = nullptr;
       FR_CUDA(e, cudaEventRecord(e0, s->stream));
       for (int r = 0; r < reps; r++)

@@ -22,6 +22,13 @@ struct FrChunk {
   int pad_;
 };
 
+// The same piece, compact (16 bytes), for the lookup fused into layer 1 (staged in shared memory).
+struct FrFuseChunk {
+  const float4* base;
+  int table;
+  int stride4_col4;    // (row pitch in float4) << 8 | float4 offset inside the row
+};
+
 struct FrTable {
   float* d = nullptr;
   int64_t rows = 0;
@@ -83,6 +90,12 @@ struct fr_engine {
 
   std::vector<FrTable> tables;
   FrChunk* d_chunks = nullptr;  // [D/4]
+  FrFuseChunk* d_fchunks = nullptr;  // [D/4]
+  // FR_FUSE=1: fr_infer gathers straight into layer 1's A tile (no concat in global memory).  Off by
+  // default: parity-green but slower on B200 (small model, batch 2048: 36 us against 5 + 22 us, 150 M
+  // against 179 M inferences/s) -- the lookup then runs on the 32 SMs of the GEMM's CTAs with 256
+  // threads each instead of on all 148 SMs at full occupancy.
+  bool fuse_lookup = false;
   bool chunks_dirty = true;
 
   float* d_W[FR_MAX_LAYERS] = {nullptr, nullptr, nullptr, nullptr};    // [in][out] fp32 (reference layout)
@@ -168,3 +181,6 @@ fr_status frk_final_dot(fr_engine* e, const float* H, const float* w, const floa
 fr_status frtc_prepare(fr_engine* e);                // builds tensor maps for weights; idempotent
 void frtc_destroy(fr_engine* e);
 fr_status frtc_layer(fr_engine* e, fr_stream_s* s, int k, const float* in, int B, float* d_scores);
+// lookup fused into layer 1: d_idx [B][T] -> s->d_h[0]; frtc_can_fuse() says whether this engine's shapes allow it
+bool frtc_can_fuse(const fr_engine* e);
+fr_status frtc_fused_layer1(fr_engine* e, fr_stream_s* s, const int32_t* d_idx, int B);

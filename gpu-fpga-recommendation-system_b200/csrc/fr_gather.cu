@@ -15,6 +15,7 @@
 // no tensor cores, no shared memory (nothing is reused).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "fr_common.h"
 
@@ -168,6 +169,7 @@ void launch_gather(const fr_engine* e, const int* d_ids, int n_chunks, const int
 fr_status frk_upload_chunks(fr_engine* e) {
   const int C = e->D / 4;
   std::vector<FrChunk> h(C);
+  std::vector<FrFuseChunk> hf(C);
   std::vector<char> covered(C, 0);
   for (const fr_segment_desc& s : e->segs) {
     const FrTable& t = e->tables[s.table];
@@ -178,6 +180,7 @@ fr_status frk_upload_chunks(fr_engine* e) {
       c.stride4 = t.dim / 4;
       c.col4 = s.col / 4 + k;
       c.pad_ = 0;
+      hf[s.dst / 4 + k] = {c.base, c.table, (c.stride4 << 8) | c.col4};
       covered[s.dst / 4 + k] = 1;
     }
   }
@@ -185,6 +188,8 @@ fr_status frk_upload_chunks(fr_engine* e) {
     if (!covered[i]) return fr_fail(e, FR_ERR_INVALID, "concat float %d is not covered by any segment", i * 4);
   if (!e->d_chunks) FR_CUDA(e, cudaMalloc(&e->d_chunks, sizeof(FrChunk) * C));
   FR_CUDA(e, fr_h2d(e, e->d_chunks, h.data(), sizeof(FrChunk) * C));
+  if (!e->d_fchunks) FR_CUDA(e, cudaMalloc(&e->d_fchunks, sizeof(FrFuseChunk) * C));
+  FR_CUDA(e, fr_h2d(e, e->d_fchunks, hf.data(), sizeof(FrFuseChunk) * C));
   e->chunks_dirty = false;
   return FR_OK;
 }
@@ -322,6 +327,7 @@ __global__ void shard_signal_wait_kernel(float* const* __restrict__ peer_base, l
     int v;
     do {
       asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if (timeout_cycles < 0) break;
       if (v < step && clock64() - t0 > timeout_cycles) {
         *reinterpret_cast<volatile int*>(err) = 1;   // surfaced by the next fr_shard_infer / fr_sync
         break;
@@ -334,8 +340,9 @@ __global__ void shard_signal_wait_kernel(float* const* __restrict__ peer_base, l
 fr_status frk_shard_signal_wait(fr_engine* e, int slot, cudaStream_t st) {
   int* d_err = nullptr;
   FR_CUDA(e, cudaHostGetDevicePointer(&d_err, e->h_shard_err, 0));
+  static const bool nowait = getenv("FR_SHARD_NOWAIT") != nullptr;   // timing experiments only: results are then racy
   shard_signal_wait_kernel<<<1, 32, 0, st>>>(e->d_peer_ptrs, (long long)fr_xchg_flags_off(e, slot), e->rank, e->world,
-                                             e->d_step + slot, d_err, 20000000000ll /* ~10 s at 1.9 GHz */);
+                                             e->d_step + slot, d_err, nowait ? -1ll : 20000000000ll /* ~10 s at 1.9 GHz */);
   e->launches++;
   FR_CUDA(e, cudaGetLastError());
   return FR_OK;

@@ -83,6 +83,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int co
     }
   }
 }
+// Same, acquiring at cluster scope: the data guarded by the barrier was written by the peer CTA's threads.
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int code = 0, uint32_t a = 0, uint32_t b = 0) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t spins = 0; !done; spins++) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && (spins & 1023) == 1023) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kWatchCycles) watchdog_fire(code, parity, a, b);
+    }
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -266,7 +288,16 @@ struct SmemLayout {
   static constexpr int kNumBars = 2 * STAGES + 4;                 // full, empty, tmem_full[2], tmem_empty[2]
   static constexpr int kTotal = kBarOff + kNumBars * 8 + 16;
   static constexpr int kDyn = kTotal + 1024;                      // slack for manual 1024-B alignment
-  static constexpr int kTmemCols = 2 * BLOCK_N;                   // two accumulator stages
+  // BLOCK_N <= 256: two accumulator stages (epilogue of tile i under the MMAs of tile i+1).
+  // BLOCK_N = 512: ONE stage filling all 512 TMEM columns, two N = 256 MMAs per K step sharing the A
+  // slice -- 48 KB of operands per 2 x 4 MMAs instead of 32 KB per 4 (33 against 45 B/clk/SM at the
+  // measured TF32 rate; L2 -> SM delivers ~40), at the price of an exposed epilogue.
+  static constexpr int kAcc = BLOCK_N <= 256 ? 2 : 1;
+  static constexpr int kTmemCols = kAcc * BLOCK_N;
+  static constexpr int kMmaN = BLOCK_N <= 256 ? BLOCK_N : 256;    // columns per tcgen05.mma
+  static constexpr int kNSub = BLOCK_N / kMmaN;                   // MMAs per K step
+  static constexpr int kSubRows = kMmaN / CTAS;                   // rows of Wt one CTA stages per MMA
+  static constexpr int kSubBytes = kSubRows * BLOCK_K * 4;
 };
 
 struct TcParams {
@@ -351,7 +382,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t kc = 0;   // k-slices issued so far (ring position runs on across tiles)
       for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
         const int m0 = ((tile / n_tiles_n) * CTAS + (int)rank) * BLOCK_M;
-        const int nb0 = (tile % n_tiles_n) * BLOCK_N + (int)rank * L::kBRows;
+        const int nb0 = (tile % n_tiles_n) * BLOCK_N + (int)rank * L::kSubRows;
         for (int kb = 0; kb < num_kb; kb++, kc++) {
           const int s = kc % STAGES;
           const uint32_t ph = (kc / STAGES) & 1;
@@ -362,11 +393,15 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);   // leader's barrier
             if (leader) mbar_expect_tx(&full_bar[s], 2 * L::kStageBytes);
             tma_load_2d_pair(&tmap_a, bar, a_dst, kb * BLOCK_K, m0);
-            tma_load_2d_pair(&tmap_b, bar, b_dst, kb * BLOCK_K, nb0);
+#pragma unroll
+            for (int h = 0; h < L::kNSub; h++)   // this CTA's rows of Wt for MMA h of the K step
+              tma_load_2d_pair(&tmap_b, bar, b_dst + h * L::kSubBytes, kb * BLOCK_K, nb0 + h * L::kMmaN);
           } else {
             mbar_expect_tx(&full_bar[s], L::kStageBytes);
             tma_load_2d(&tmap_a, &full_bar[s], a_dst, kb * BLOCK_K, m0);
-            tma_load_2d(&tmap_b, &full_bar[s], b_dst, kb * BLOCK_K, nb0);
+#pragma unroll
+            for (int h = 0; h < L::kNSub; h++)
+              tma_load_2d(&tmap_b, &full_bar[s], b_dst + h * L::kSubBytes, kb * BLOCK_K, nb0 + h * L::kMmaN);
           }
         }
       }
@@ -376,11 +411,11 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only for a pair) =====
     if (leader) {
-      constexpr uint32_t idesc = make_idesc_tf32_m(BLOCK_M * CTAS, BLOCK_N);
+      constexpr uint32_t idesc = make_idesc_tf32_m(BLOCK_M * CTAS, L::kMmaN);
       uint32_t kc = 0, it = 0;
       for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
-        const uint32_t as = it & 1;
-        mbar_wait(&tmem_empty_bar[as], ((it >> 1) & 1) ^ 1, 2, kc, tile);   // the epilogue has drained this accumulator stage
+        const uint32_t as = it % L::kAcc;
+        mbar_wait(&tmem_empty_bar[as], ((it / L::kAcc) & 1) ^ 1, 2, kc, tile);   // the epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         for (int kb = 0; kb < num_kb; kb++, kc++) {
@@ -394,9 +429,14 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint64_t b_desc = make_smem_desc(a_addr + L::kABytes);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
-              // advance 32 bytes of K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-              if (CTAS == 2) umma_tf32_pair(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-              else umma_tf32(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+#pragma unroll
+              for (int h = 0; h < L::kNSub; h++) {
+                // advance 32 bytes of K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field;
+                // MMA h of the step reads Wt sub-tile h and accumulates into TMEM columns h * 256
+                const uint64_t bd = b_desc + (uint64_t)(k * 2) + (uint64_t)(h * (L::kSubBytes >> 4));
+                if (CTAS == 2) umma_tf32_pair(d_tmem + h * L::kMmaN, a_desc + (uint64_t)(k * 2), bd, idesc, (kb | k) != 0);
+                else umma_tf32(d_tmem + h * L::kMmaN, a_desc + (uint64_t)(k * 2), bd, idesc, (kb | k) != 0);
+              }
             }
             if (CTAS == 2) {
               umma_commit_pair(&empty_bar[s]);                            // frees the slot in both CTAs
@@ -417,10 +457,10 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t empty_remote = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);   // leader's tmem_empty_bar[0]
     uint32_t it = 0, sc = 0;   // tiles done, store chunks issued
     for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
-      const uint32_t as = it & 1;
+      const uint32_t as = it % L::kAcc;
       const int row0 = ((tile / n_tiles_n) * CTAS + (int)rank) * BLOCK_M + q * 32;
       const int n0 = (tile % n_tiles_n) * BLOCK_N;
-      mbar_wait(&tmem_full_bar[as], (it >> 1) & 1, 4, it, tile);
+      mbar_wait(&tmem_full_bar[as], (it / L::kAcc) & 1, 4, it, tile);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
       float dot = 0.f;
@@ -484,6 +524,272 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
+// ---- lookup fused into layer 1 ---------------------------------------------------
+// The north-star fusion: the multi-table lookup IS the A-operand producer of the first GEMM, so the
+// concat vectors never exist in global memory.  One CTA pair owns 256 items x 512 hidden units:
+//   warp 0        TMA producer for the weights: two 128-row boxes of Wt per CTA per K slice
+//   warp 1        MMA issuer (leader): per K step two cta_group::2 MMAs (N = 256 each) that share
+//                 the A tile and fill all 512 TMEM columns
+//   warps 2-5     epilogue: bias + ReLU + TF32 rounding, TMA store of H1
+//   warps 6-13    lookup producers: for every 32-float K slice, 8 lanes per item read the item's 8
+//                 row pieces (index -> 16-byte row load, exactly the stand-alone lookup:
+//                 embedding_47_krnl.cpp:916-935 + the concat order of gather_embeddings) and write
+//                 them, TF32-rounded, into the 128B-swizzled A slot.  Two groups of 4 warps take
+//                 alternate slices and each keeps the next slice's rows and the one after's indices
+//                 in flight in registers, so four slices of random-access latency overlap the MMAs.
+// Each 256 x 512 tile re-reads its items' rows once per 512 hidden units (2x for H1 = 1024, 4x for
+// 2048): those re-reads hit L2, and the alternative -- X written to and re-read from global memory
+// by 4 column tiles -- moved more bytes.  Per SM and K slice 16 KB of A + 32 KB of B feed 2 x 4 MMAs
+// (33 B/clk/SM at the measured TF32 rate, against 45 for 256 x 256 tiles).
+constexpr int kFuseThreads = 448;
+constexpr int kFuseGatherWarp0 = 6;
+constexpr int kFuseN = 512;
+constexpr int kFuseMaxChunks = 1024;   // 16-byte pieces per item: large model 992
+
+template <int STAGES>
+struct FuseLayout {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 4;        // 16 KB: this CTA's 128 items x 32 floats
+  static constexpr int kBHalfBytes = 128 * BLOCK_K * 4;        // 16 KB: 128 rows of Wt (this CTA's half of an N=256 MMA)
+  static constexpr int kBBytes = 2 * kBHalfBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;        // 48 KB
+  static constexpr int kStoreOff = STAGES * kStageBytes;
+  static constexpr int kAuxOff = kStoreOff + 4 * 2 * kStoreBufBytes;       // bias[kMaxN]
+  static constexpr int kChunkOff = kAuxOff + kMaxN * 4;                    // FrFuseChunk[kFuseMaxChunks]
+  static constexpr int kBarOff = kChunkOff + kFuseMaxChunks * 16;
+  static constexpr int kNumBars = 2 * STAGES + 2;                          // full, empty, tmem_full, tmem_empty
+  static constexpr int kTotal = kBarOff + kNumBars * 8 + 16;
+  static constexpr int kDyn = kTotal + 1024;
+};
+
+struct FuseParams {
+  const FrFuseChunk* chunks;   // [C] piece descriptors in concat (wire) order
+  const int32_t* idx;          // [M][T]
+  const float* bias;           // [N] or null
+  int C, T, M, N;
+  int relu;
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(kFuseThreads, 1)
+tc_gather_linear_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_out,
+                        const FuseParams p) {
+  using L = FuseLayout<STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* s_bias = reinterpret_cast<float*>(smem + L::kAuxOff);
+  FrFuseChunk* s_chunks = reinterpret_cast<FrFuseChunk*>(smem + L::kChunkOff);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int num_kb = (p.C + 7) / 8;                 // 8 pieces = 32 floats per K slice; the tail slice is zero-padded
+  const int n_tiles_n = p.N / kFuseN;
+  const int n_tiles = ((p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * n_tiles_n;
+  const int cluster_id = blockIdx.x / 2, n_clusters = gridDim.x / 2;
+  const int my_tiles = cluster_id < n_tiles ? (n_tiles - cluster_id + n_clusters - 1) / n_clusters : 0;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_out) : "memory");
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full_bar[s], 1 + 8);   // the leader's weight producer + 4 lookup warps of each CTA
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_init(tmem_empty_bar, 8);
+    fence_barrier_init();
+  } else if (warp == 1) {
+    tmem_alloc_pair(tmem_ptr, 512);
+  } else if (warp >= kFuseGatherWarp0) {
+    for (int i = threadIdx.x - kFuseGatherWarp0 * 32; i < p.C; i += (kFuseThreads - kFuseGatherWarp0 * 32)) s_chunks[i] = p.chunks[i];
+  } else {
+    for (int i = threadIdx.x - kEpiWarp0 * 32; i < p.N; i += 128) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== weight producer (both CTAs) =====
+    if (lane == 0) {
+      uint32_t kc = 0;
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+        const int n0 = (tile % n_tiles_n) * kFuseN + (int)rank * 128;
+        for (int kb = 0; kb < num_kb; kb++, kc++) {
+          const int s = kc % STAGES;
+          mbar_wait(&empty_bar[s], ((kc / STAGES) & 1) ^ 1, 1, kc, tile);
+          uint8_t* b_dst = smem + s * L::kStageBytes + L::kABytes;
+          const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * L::kBBytes);
+          tma_load_2d_pair(&tmap_b, bar, b_dst, kb * BLOCK_K, n0);
+          tma_load_2d_pair(&tmap_b, bar, b_dst + L::kBHalfBytes, kb * BLOCK_K, n0 + 256);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader) =====
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_tf32_m(2 * BLOCK_M, 256);
+      uint32_t kc = 0, it = 0;
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
+        mbar_wait(tmem_empty_bar, (it & 1) ^ 1, 2, kc, tile);
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; kb++, kc++) {
+          const int s = kc % STAGES;
+          mbar_wait_cluster(&full_bar[s], (kc / STAGES) & 1, 3, kc, tile);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+            const uint64_t a_desc = make_smem_desc(a_addr);
+            const uint64_t b0_desc = make_smem_desc(a_addr + L::kABytes);
+            const uint64_t b1_desc = make_smem_desc(a_addr + L::kABytes + L::kBHalfBytes);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+              umma_tf32_pair(tmem_base, a_desc + (uint64_t)(k * 2), b0_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+              umma_tf32_pair(tmem_base + 256, a_desc + (uint64_t)(k * 2), b1_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            }
+            umma_commit_pair(&empty_bar[s]);
+            if (kb == num_kb - 1) umma_commit_pair(tmem_full_bar);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp < kFuseGatherWarp0) {
+    // ===== epilogue =====
+    const int q = warp % 4;
+    uint8_t* store_buf = smem + L::kStoreOff + (warp - kEpiWarp0) * 2 * kStoreBufBytes;
+    const uint32_t empty_remote = mapa_u32(smem_u32(tmem_empty_bar), 0);
+    uint32_t it = 0, sc = 0;
+    for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
+      const int row0 = ((tile / n_tiles_n) * 2 + (int)rank) * BLOCK_M + q * 32;
+      const int n0 = (tile % n_tiles_n) * kFuseN;
+      mbar_wait(tmem_full_bar, it & 1, 4, it, tile);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < kFuseN; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c, r);
+        uint8_t* buf = store_buf + (sc & 1) * kStoreBufBytes;
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        const float* bs = s_bias + n0 + c;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          float4 o;
+          o.x = __uint_as_float(r[4 * j + 0]) + bs[4 * j + 0];
+          o.y = __uint_as_float(r[4 * j + 1]) + bs[4 * j + 1];
+          o.z = __uint_as_float(r[4 * j + 2]) + bs[4 * j + 2];
+          o.w = __uint_as_float(r[4 * j + 3]) + bs[4 * j + 3];
+          if (p.relu) {
+            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+          }
+          o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+          *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && row0 < p.M) {
+          tma_store_2d(&tmap_out, buf, n0 + c, row0);
+          bulk_commit();
+        }
+        sc++;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(empty_remote);
+    }
+    if (lane == 0) bulk_wait_all<0>();
+    tc_fence_before();
+  } else {
+    // ===== lookup producers; group 0 / 1 (4 warps each) takes even / odd K slices =====
+    // Within a slice a thread owns ONE of the 8 pieces (j) of 8 items (i0, i0+16, ...): the 8 lanes
+    // of an item read neighbouring index columns of one index row and neighbouring pieces (often of
+    // the same table row), so a warp-wide load touches a few cache lines instead of 32 -- the
+    // L1 wavefront rate, not latency, is what bounds a gather feeding a GEMM at this rate.
+    const int gt = threadIdx.x - kFuseGatherWarp0 * 32;   // 0..255
+    const int group = gt >> 7, g = gt & 127;
+    const int j = g & 7, i0 = g >> 3;                     // piece within the slice, first item (of 8, stride 16)
+    const uint32_t full_remote = mapa_u32(smem_u32(&full_bar[0]), 0);
+    const int total = my_tiles * num_kb;                  // K slices this cluster consumes, in order
+
+    // Two-deep software pipeline per group, so neither the index load nor the dependent row load
+    // is waited for in the iteration that issues it:
+    //   iteration q:  rows of slice q+2 are requested (their indices were requested one iteration
+    //                 ago), indices of slice q+4 are requested, slice q (rows requested one iteration
+    //                 ago) is stored.
+    auto load_idx = [&](int q, int (&ia)[8]) {
+      const int tile = cluster_id + (q / num_kb) * n_clusters;
+      const int c = (q % num_kb) * 8 + j;
+      const int b0 = ((tile / n_tiles_n) * 2 + (int)rank) * BLOCK_M + i0;
+      const int table = c < p.C ? s_chunks[c].table : -1;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int b = b0 + 16 * i;
+        ia[i] = (table >= 0 && b < p.M) ? __ldg(p.idx + (size_t)b * p.T + table) : -1;
+      }
+    };
+    auto load_rows = [&](int q, const int (&ia)[8], float4 (&out)[8]) {
+      const int c = (q % num_kb) * 8 + j;
+      const FrFuseChunk ch = s_chunks[c < p.C ? c : 0];
+      const int stride4 = ch.stride4_col4 >> 8, col4 = ch.stride4_col4 & 255;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        out[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ia[i] >= 0) {   // K-tail pieces and items past the batch stay zero
+          const float4* src = ch.base + (int64_t)ia[i] * stride4 + col4;
+          asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.f32 {%0,%1,%2,%3}, [%4];"
+                       : "=f"(out[i].x), "=f"(out[i].y), "=f"(out[i].z), "=f"(out[i].w)
+                       : "l"(src));
+        }
+      }
+    };
+
+    float4 vn[8];
+    int ia[8];
+    int q = group;
+    if (q < total) {
+      load_idx(q, ia);
+      load_rows(q, ia, vn);
+      if (q + 2 < total) load_idx(q + 2, ia);
+    }
+    for (; q < total; q += 2) {
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) v[i] = vn[i];
+      if (q + 2 < total) load_rows(q + 2, ia, vn);
+      if (q + 4 < total) load_idx(q + 4, ia);
+      const int s = q % STAGES;
+      mbar_wait(&empty_bar[s], ((q / STAGES) & 1) ^ 1, 5, q, g);
+      uint8_t* dst = smem + s * L::kStageBytes;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int row = i0 + 16 * i;
+        float4 o = v[i];
+        o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+        // 128B swizzle, as TMA would have laid it out: piece j of row r lives at chunk j ^ (r & 7)
+        *reinterpret_cast<float4*>(dst + row * 128 + ((j ^ (row & 7)) << 4)) = o;
+      }
+      fence_proxy_async();      // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(full_remote + s * 8);
+    }
+  }
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
 // ---- host side ----------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -494,8 +800,10 @@ struct TcLayerCfg {
 };
 
 struct TcState {
+  bool auto_tiles = true;   // FR_TC_TILES unset: tile width per layer and batch chosen by pick_block_n()
   PFN_encodeTiled encode = nullptr;
   CUtensorMap w_map[3];
+  CUtensorMap w_fuse_map;   // layer-1 weights in 128-row boxes, for the fused lookup + layer 1 kernel
   TcLayerCfg cfg[3];
   bool ready = false;
   // cached activation maps keyed by (pointer, K, rows, box rows): 128-row boxes feed the A operand,
@@ -536,6 +844,7 @@ fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const
   using L = SmemLayout<BLOCK_N, STAGES, CTAS>;
   static_assert(L::kDyn <= 227 * 1024, "tile configuration exceeds the 227 KB shared memory of an SM");
   static_assert(L::kTmemCols == 256 || L::kTmemCols == 512, "TMEM allocation must be a power of two");
+  static_assert(L::kNSub == 1 || CTAS == 2, "512-wide tiles are pair tiles");
   auto kern = tc_linear_kernel<BLOCK_N, STAGES, EPI, CTAS>;
   static std::atomic<uint64_t> attr_done{0};  // bit d: opt-in smem size set on device d for this instantiation
   const uint64_t bit = 1ull << (e->device & 63);
@@ -548,7 +857,8 @@ fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const
   int max_clusters = e->sm_count / CTAS;
   if (g_max_clusters > 0 && g_max_clusters < max_clusters) max_clusters = g_max_clusters;   // test knob
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
-  const int gang = num_kb >= g_min_kb ? 1 : (g_min_kb + num_kb - 1) / num_kb;   // tiles per cluster wanted
+  // (ganging only pays when the epilogue of one tile runs under the next tile's MMAs: two accumulator stages)
+  const int gang = (num_kb >= g_min_kb || L::kAcc == 1) ? 1 : (g_min_kb + num_kb - 1) / num_kb;   // tiles per cluster wanted
   int n_clusters = (n_tiles + gang - 1) / gang;
   if (n_clusters > max_clusters) n_clusters = max_clusters;
   cudaLaunchConfig_t cfg = {};
@@ -590,11 +900,28 @@ fr_status get_a_map(fr_engine* e, TcState* st, const void* ptr, int K, int rows,
 }
 
 // tile shapes: "N1,N2,N3[,ctas]" e.g. FR_TC_TILES=256,256,256,2 ; layer 3 must be 256 (whole row)
-void parse_tiles(TcLayerCfg cfg[3]) {
+bool parse_tiles(TcLayerCfg cfg[3]) {
   int n[3] = {256, 256, 256}, ctas = 2;
-  if (const char* env = getenv("FR_TC_TILES")) sscanf(env, "%d,%d,%d,%d", &n[0], &n[1], &n[2], &ctas);
+  const char* env = getenv("FR_TC_TILES");
+  if (env) sscanf(env, "%d,%d,%d,%d", &n[0], &n[1], &n[2], &ctas);
   for (int k = 0; k < 3; k++) cfg[k] = {n[k], ctas};
   cfg[2].block_n = 256;
+  return env != nullptr;
+}
+
+// Automatic tile width of a storing layer (pair tiles).  A launch whose 256-wide tiles cannot fill the
+// machine anyway is run with 512-wide tiles when its K loop is long: fewer, denser CTAs (33 instead of
+// 45 B/clk/SM of operand traffic) leave more SMs to the other workers' kernels -- small model, batch
+// 2048, 12 workers: 196 M against 178 M inferences/s, medium model 130 M against 111 M.  Short K loops
+// (small model layer 1: 11 slices) keep 256-wide tiles, ganged two per cluster so the epilogue of one
+// runs under the MMAs of the next; launches with enough tiles keep 256-wide tiles and two accumulator
+// stages (batch 16384: 40 us against 42 us for layer 2).
+int pick_block_n(const fr_engine* e, int k, int B) {
+  const int N = e->dims[k + 1], K = e->dims[k];
+  const int tiles256 = (B + 2 * BLOCK_M - 1) / (2 * BLOCK_M) * (N / 256);
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  if (N % 512 == 0 && num_kb >= g_min_kb && tiles256 < e->sm_count / 2) return 512;
+  return 256;
 }
 
 }  // namespace
@@ -620,7 +947,7 @@ fr_status frtc_prepare(fr_engine* e) {
   if (e->dims[3] != 256)
     return fr_fail(e, FR_ERR_UNSUPPORTED, "TF32 path folds the output layer into layer 3 and needs hidden[2] == 256 "
                    "(got %d)", e->dims[3]);
-  parse_tiles(st->cfg);
+  st->auto_tiles = !parse_tiles(st->cfg);
   const char* cap = getenv("FR_TC_MAX_CLUSTERS");
   g_max_clusters = cap ? atoi(cap) : 0;
   if (const char* env = getenv("FR_TC_MIN_KB")) g_min_kb = atoi(env) > 0 ? atoi(env) : 1;
@@ -633,13 +960,20 @@ fr_status frtc_prepare(fr_engine* e) {
   FR_CUDA(e, cudaMemcpyToSymbol(g_watch, &d_watch, sizeof(d_watch)));
   for (int k = 0; k < 3; k++) {
     const TcLayerCfg c = st->cfg[k];
-    if ((c.block_n != 128 && c.block_n != 256) || (c.ctas != 1 && c.ctas != 2))
-      return fr_fail(e, FR_ERR_UNSUPPORTED, "tile N %d / ctas %d not built (N in {128,256}, ctas in {1,2})", c.block_n, c.ctas);
+    if ((c.block_n != 128 && c.block_n != 256 && c.block_n != 512) || (c.ctas != 1 && c.ctas != 2) ||
+        (c.block_n == 512 && c.ctas != 2))
+      return fr_fail(e, FR_ERR_UNSUPPORTED, "tile N %d / ctas %d not built (N in {128,256,512}, ctas in {1,2}, 512 only as a pair)",
+                     c.block_n, c.ctas);
     if (e->dims[k + 1] % c.block_n)
       return fr_fail(e, FR_ERR_UNSUPPORTED, "hidden[%d]=%d not a multiple of tile N %d", k, e->dims[k + 1], c.block_n);
     if (e->dims[k + 1] > kMaxN)
       return fr_fail(e, FR_ERR_UNSUPPORTED, "hidden[%d]=%d wider than the %d-float bias staging area", k, e->dims[k + 1], kMaxN);
-    fr_status s = encode_2d(e, st, &st->w_map[k], e->d_Wt[k], e->dims[k + 1], e->dims[k], c.block_n / c.ctas);
+    fr_status s = encode_2d(e, st, &st->w_map[k], e->d_Wt[k], e->dims[k + 1], e->dims[k],
+                            (c.block_n < 256 ? c.block_n : 256) / c.ctas);
+    if (s != FR_OK) return s;
+  }
+  {
+    fr_status s = encode_2d(e, st, &st->w_fuse_map, e->d_Wt[0], e->dims[1], e->dims[0], 128);
     if (s != FR_OK) return s;
   }
   st->ready = true;
@@ -649,6 +983,62 @@ fr_status frtc_prepare(fr_engine* e) {
 void frtc_destroy(fr_engine* e) {
   delete static_cast<TcState*>(e->tc_state);
   e->tc_state = nullptr;
+}
+
+bool frtc_can_fuse(const fr_engine* e) {
+  const TcState* st = static_cast<const TcState*>(e->tc_state);
+  // row pitch and in-row offset of a piece must fit the packed descriptor (dims up to 1020 floats)
+  bool dims_ok = true;
+  for (const FrTable& t : e->tables) dims_ok = dims_ok && t.dim / 4 < 256;
+  return e->fuse_lookup && st && st->ready && e->world == 1 && e->precision == FR_PREC_TF32 && e->dims[1] % kFuseN == 0 &&
+         e->dims[1] <= kMaxN && e->D / 4 <= kFuseMaxChunks && dims_ok;
+}
+
+fr_status frtc_fused_layer1(fr_engine* e, fr_stream_s* s, const int32_t* d_idx, int B) {
+  TcState* st = static_cast<TcState*>(e->tc_state);
+  constexpr int STAGES = 3;
+  using L = FuseLayout<STAGES>;
+  static_assert(L::kDyn <= 227 * 1024, "fused tile configuration exceeds the 227 KB shared memory of an SM");
+  const bool act = (e->mlp_mode == FR_MLP_BIAS_RELU_SIGMOID);
+  CUtensorMap o;
+  fr_status r = get_a_map(e, st, s->d_h[0], e->dims[1], B, kStoreBoxRows, &o);
+  if (r != FR_OK) return r;
+  FuseParams p;
+  p.chunks = e->d_fchunks;
+  p.idx = d_idx;
+  p.bias = act ? e->d_bias[0] : nullptr;
+  p.C = e->D / 4;
+  p.T = (int)e->tables.size();
+  p.M = B;
+  p.N = e->dims[1];
+  p.relu = act ? 1 : 0;
+  auto kern = tc_gather_linear_kernel<STAGES>;
+  static std::atomic<uint64_t> attr_done{0};
+  const uint64_t bit = 1ull << (e->device & 63);
+  if (!(attr_done.load() & bit)) {
+    FR_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDyn));
+    attr_done.fetch_or(bit);
+  }
+  const int n_tiles = (B + 2 * BLOCK_M - 1) / (2 * BLOCK_M) * (p.N / kFuseN);
+  int max_clusters = e->sm_count / 2;
+  if (g_max_clusters > 0 && g_max_clusters < max_clusters) max_clusters = g_max_clusters;
+  const int n_clusters = n_tiles < max_clusters ? n_tiles : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_clusters * 2, 1, 1);
+  cfg.blockDim = dim3(kFuseThreads, 1, 1);
+  cfg.dynamicSmemBytes = L::kDyn;
+  cfg.stream = s->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // the weight map of layer 1 must carry 128-row boxes (a CTA's half of an N = 256 MMA)
+  FR_CUDA(e, cudaLaunchKernelEx(&cfg, kern, st->w_fuse_map, o, p));
+  e->launches++;
+  return FR_OK;
 }
 
 // One launch: layer k (0,1: store tf32-rounded activations into s->d_h[k]; 2: layer 3 with the
@@ -675,10 +1065,12 @@ fr_status frtc_layer(fr_engine* e, fr_stream_s* s, int k, const float* in, int B
   p.pdl = e->pdl_mask ? 1 : 0;
   const bool pa = (e->pdl_mask & (k == 0 ? 2 : 1)) != 0;   // may this layer start under the tail of its predecessor
   p.out = d_scores;
-  const TcLayerCfg c = st->cfg[k];
+  TcLayerCfg c = st->cfg[k];
+  if (st->auto_tiles && k < 2) c.block_n = pick_block_n(e, k, B);   // same 128-row weight boxes for 256 and 512
   const CUtensorMap& w = st->w_map[k];
   cudaStream_t cs = s->stream;
   if (k < 2) {
+    if (c.block_n == 512) return launch<512, 3, EPI_STORE, 2>(e, a, w, o, p, pa, cs);
     if (c.ctas == 2) return c.block_n == 256 ? launch<256, 5, EPI_STORE, 2>(e, a, w, o, p, pa, cs) : launch<128, 7, EPI_STORE, 2>(e, a, w, o, p, pa, cs);
     return c.block_n == 256 ? launch<256, 3, EPI_STORE, 1>(e, a, w, o, p, pa, cs) : launch<128, 5, EPI_STORE, 1>(e, a, w, o, p, pa, cs);
   }

@@ -12,14 +12,16 @@ CUDA-IPC handles and the end-of-run barrier.
 import numpy as np
 
 
-def plan_owners(model, world, replicate_tiers=("PLRAM",), replicate_max_bytes=16 << 20):
+def plan_owners(model, world, replicate_tiers=("PLRAM",), replicate_max_bytes=16 << 20, replicate_below_bytes=0):
     """owner[t] for every table: -1 = replicated on every rank, else the owning rank.
 
     On-chip-class tables (the reference's PLRAM tier: <= 10 000 rows, L2-resident
     here) are replicated, which removes their floats from the exchange.  The rest
     go to ranks greedily by descending bytes-per-item traffic then bytes, to the
     currently lightest rank (ties: lowest rank) -- deterministic, so every rank
-    computes the same plan without communicating."""
+    computes the same plan without communicating.  `replicate_below_bytes` > 0 additionally
+    replicates ANY table smaller than that, whatever its tier: a table that fits L2 many times over
+    costs next to nothing to replicate, and every replicated table leaves the exchange."""
     owner = [None] * model.n_tables
     if world == 1:
         return [0] * model.n_tables
@@ -27,7 +29,8 @@ def plan_owners(model, world, replicate_tiers=("PLRAM",), replicate_max_bytes=16
     size = [0] * world            # resident bytes (capacity balance)
     order = sorted(model.tables, key=lambda t: (-t.dim, -t.rows * t.dim, t.id))
     for t in order:
-        if t.tier in replicate_tiers and t.rows * t.dim * 4 <= replicate_max_bytes:
+        if (t.tier in replicate_tiers and t.rows * t.dim * 4 <= replicate_max_bytes) or \
+                t.rows * t.dim * 4 < replicate_below_bytes:
             owner[t.id] = -1
             continue
         r = min(range(world), key=lambda k: (load[k], size[k], k))

@@ -19,7 +19,7 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 MODELS3 = ("small", "medium", "large_half")
 TOL = 1e-3
 # FR_TC_TILES: tcgen05 tile width of layers 1..3 and CTAs per tile (1 = cta_group::1, 2 = CTA pair)
-TILES = ("128,128,256,1", "256,256,256,1", "128,128,256,2", "256,256,256,2")
+TILES = ("128,128,256,1", "256,256,256,1", "128,128,256,2", "256,256,256,2", "512,512,256,2")
 
 
 def rel_err(got, exp):
@@ -124,7 +124,7 @@ KAT = {"small": 47244640256.0, "medium": 118111600640.0, "large": 1065151889408.
 
 @pytest.mark.parametrize("prec,tiles", ((fleetrec.FR_PREC_FP32, ""), (fleetrec.FR_PREC_TF32, TILES[0]),
                                         (fleetrec.FR_PREC_TF32, TILES[1]), (fleetrec.FR_PREC_TF32, TILES[2]),
-                                        (fleetrec.FR_PREC_TF32, TILES[3])))
+                                        (fleetrec.FR_PREC_TF32, TILES[3]), (fleetrec.FR_PREC_TF32, TILES[4])))
 @pytest.mark.parametrize("model", ("small", "medium", "large"))
 def test_mlp_all_ones_known_answer(model, prec, tiles, monkeypatch):
     """README.md:7-11: all-ones input and weights -> IN*H1*H2*H3, exact in fp32 and tf32."""
@@ -295,7 +295,8 @@ def test_infer_graph_replay_matches_direct():
             got = sc_buf.cpu().numpy() if kind == "device" else sc_buf.numpy().copy()
             exp = oracle.mlp(oracle.gather(cat, tables, idx), dims, W, b, mode=1)
             assert rel_err(got, exp) <= TOL, (kind, it)
-        assert eng.launch_count() - l0 == 4 * 4          # gather + 3 GEMM launches per batch, replayed or not
+        # (lookup fused into layer 1) + 2 GEMM launches per batch, replayed or not; 4 with FR_FUSE=0
+        assert eng.launch_count() - l0 == 4 * (3 if os.environ.get("FR_FUSE", "0") == "1" else 4)
     w.close()
     eng.close()
 
@@ -443,4 +444,50 @@ def test_batcher_deadline_flush_and_errors():
     bat.submit(oracle.zipf_indices(cat, 5, seed=2), out3)
     bat.close()                                                # destroy drains what was submitted
     assert np.all(out3 > 0)
+    eng.close()
+
+
+# ---------------------------------------------------------------- lookup fused into layer 1
+@pytest.mark.parametrize("model,B", (("small", 1), ("small", 300), ("small", 2048), ("small", 20000),
+                                     ("medium", 777), ("large", 515)))
+def test_fused_lookup_layer1_matches_unfused_and_oracle(model, B, monkeypatch):
+    """With FR_FUSE=1 fr_infer's TF32 chain gathers straight into the first GEMM's A tile (no concat
+    in global memory).  Same indices through (a) the fused chain, (b) FR_FUSE=0 (lookup kernel, concat
+    materialised, TMA-fed layer 1; the default) and (c) the oracle: (a) vs (c) within the MLP tolerance, (a) vs
+    (b) equal to the last bit or two (same TF32-rounded operands, same K order, fp32 accumulate).
+    Covers K tails (medium: 27.5 slices), M tails, > 1 tile per cluster (B = 20000) and N = 2048."""
+    cat = catalogue.load(model).with_row_cap(3000)
+    dims = cat.layer_dims
+    tables = oracle.make_tables(cat, "hash", seed=17)
+    W, b = oracle.make_weights(dims, seed=42)
+    idx = oracle.zipf_indices(cat, B, seed=B)
+    idx[0, :] = [t.rows - 1 for t in cat.tables]
+    got = {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("FR_FUSE", fuse)
+        eng = fleetrec.Engine(cat, max_batch=B)
+        eng.load_tables(tables)
+        eng.load_mlp(W, b)
+        l0 = eng.launch_count()
+        got[fuse] = eng.infer(idx)
+        assert eng.launch_count() - l0 == (3 if fuse == "1" else 4)
+        eng.close()
+    exp = oracle.mlp(oracle.gather(cat, tables, idx), dims, W, b, mode=1)
+    assert rel_err(got["1"], exp) <= TOL, rel_err(got["1"], exp)
+    assert np.max(np.abs(got["1"] - got["0"])) <= 2e-6, np.max(np.abs(got["1"] - got["0"]))
+
+
+def test_fused_chain_reference_kat(monkeypatch):
+    """The reference's own known answer through the fused chain: T1 fill + I1 indices + all-ones
+    weights, LINEAR mode -> IN*H1*H2*H3 for even rows, 0 for odd (README.md:7-11)."""
+    cat = catalogue.load("small").with_row_cap(200)
+    dims = cat.layer_dims
+    monkeypatch.setenv("FR_FUSE", "1")
+    eng = fleetrec.Engine(cat, mlp_mode=fleetrec.FR_MLP_LINEAR, max_batch=64)
+    eng.fill_reference()
+    eng.load_mlp([np.ones((dims[k], dims[k + 1]), np.float32) for k in range(4)])
+    idx = oracle.idx_reference(64, cat.n_tables)
+    out = eng.infer(idx)
+    exp = np.where(idx[:, 0] % 2 == 0, np.float32(KAT["small"]), np.float32(0))
+    assert np.array_equal(out, exp)
     eng.close()

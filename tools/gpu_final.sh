@@ -13,6 +13,8 @@ run host 300 gpu-fpga-recommendation-system_b200/host/fleetrec_host small 2048 2
 run stress_$R 600 python bench.py --workload stress
 run sweep_$R 600 python bench.py --workload sweep
 run cublas_$R 300 python tools/cublas_ref.py small
+FR_FUSE=1 run bench_fused_$R 300 python bench.py --cpu-seconds 0
+run bench_medium_$R 300 python bench.py --model medium --cpu-seconds 0 --steps 1000
 # ncu: launch list of the bench command, then full captures
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 480 --csv \
   --log-file gpurun_out/launches_$R.csv python bench.py --steps 100 --warmup 5 --cpu-seconds 0 --kernel-reps 2 > gpurun_out/ncu_launch_$R.log 2>&1
