@@ -309,6 +309,7 @@ struct TcParams {
   int relu, sigmoid;
   int pdl;             // issue griddepcontrol.wait / launch_dependents (no-ops unless a launch in the chain
                        // carries the programmatic-serialization attribute)
+  int latency;         // host-side hint: small batch, one tile per cluster (no ganging)
 };
 
 // kind::tf32 instruction descriptor: D=f32, A=B=tf32, both K-major, M = 128*CTAS, N = n.
@@ -804,6 +805,7 @@ struct TcState {
   PFN_encodeTiled encode = nullptr;
   CUtensorMap w_map[3];
   CUtensorMap w_fuse_map;   // layer-1 weights in 128-row boxes, for the fused lookup + layer 1 kernel
+  CUtensorMap w_map64[2];   // layers 1, 2 in 64-row boxes: 128-wide pair tiles (automatic choice for small batches)
   TcLayerCfg cfg[3];
   bool ready = false;
   // cached activation maps keyed by (pointer, K, rows, box rows): 128-row boxes feed the A operand,
@@ -858,7 +860,7 @@ fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const
   if (g_max_clusters > 0 && g_max_clusters < max_clusters) max_clusters = g_max_clusters;   // test knob
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
   // (ganging only pays when the epilogue of one tile runs under the next tile's MMAs: two accumulator stages)
-  const int gang = (num_kb >= g_min_kb || L::kAcc == 1) ? 1 : (g_min_kb + num_kb - 1) / num_kb;   // tiles per cluster wanted
+  const int gang = (num_kb >= g_min_kb || L::kAcc == 1 || p.latency) ? 1 : (g_min_kb + num_kb - 1) / num_kb;   // tiles per cluster wanted
   int n_clusters = (n_tiles + gang - 1) / gang;
   if (n_clusters > max_clusters) n_clusters = max_clusters;
   cudaLaunchConfig_t cfg = {};
@@ -916,8 +918,13 @@ bool parse_tiles(TcLayerCfg cfg[3]) {
 // (small model layer 1: 11 slices) keep 256-wide tiles, ganged two per cluster so the epilogue of one
 // runs under the MMAs of the next; launches with enough tiles keep 256-wide tiles and two accumulator
 // stages (batch 16384: 40 us against 42 us for layer 2).
+// Small batches (one or two M tiles) are latency cases -- nothing else is in flight to fill the machine
+// -- so they take 128-wide tiles, un-ganged: 2-4x more clusters, each with a quarter of the MMAs
+// (medium model, batch 1: 77 -> ~45 us per fr_infer).
+constexpr int kLatencyBatch = 512;
 int pick_block_n(const fr_engine* e, int k, int B) {
   const int N = e->dims[k + 1], K = e->dims[k];
+  if (B <= kLatencyBatch) return 128;
   const int tiles256 = (B + 2 * BLOCK_M - 1) / (2 * BLOCK_M) * (N / 256);
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
   if (N % 512 == 0 && num_kb >= g_min_kb && tiles256 < e->sm_count / 2) return 512;
@@ -975,6 +982,8 @@ fr_status frtc_prepare(fr_engine* e) {
   {
     fr_status s = encode_2d(e, st, &st->w_fuse_map, e->d_Wt[0], e->dims[1], e->dims[0], 128);
     if (s != FR_OK) return s;
+    for (int k = 0; k < 2; k++)
+      if ((s = encode_2d(e, st, &st->w_map64[k], e->d_Wt[k], e->dims[k + 1], e->dims[k], 64)) != FR_OK) return s;
   }
   st->ready = true;
   return FR_OK;
@@ -1067,7 +1076,8 @@ fr_status frtc_layer(fr_engine* e, fr_stream_s* s, int k, const float* in, int B
   p.out = d_scores;
   TcLayerCfg c = st->cfg[k];
   if (st->auto_tiles && k < 2) c.block_n = pick_block_n(e, k, B);   // same 128-row weight boxes for 256 and 512
-  const CUtensorMap& w = st->w_map[k];
+  const CUtensorMap& w = (st->auto_tiles && k < 2 && c.block_n == 128) ? st->w_map64[k] : st->w_map[k];
+  p.latency = (st->auto_tiles && B <= kLatencyBatch) ? 1 : 0;
   cudaStream_t cs = s->stream;
   if (k < 2) {
     if (c.block_n == 512) return launch<512, 3, EPI_STORE, 2>(e, a, w, o, p, pa, cs);
