@@ -415,9 +415,11 @@ def run_stress(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     T, dim, B = args.stress_tables, 64, args.gather_batch
     rows, eng = args.stress_rows, None
+    tdt = {"f32": fleetrec.FR_TABLE_F32, "f16": fleetrec.FR_TABLE_F16, "bf16": fleetrec.FR_TABLE_BF16}[args.table_dtype]
+    esize = 4 if tdt == fleetrec.FR_TABLE_F32 else 2
     while eng is None:
         cat = catalogue.synthetic(T, rows, dim)
-        eng = fleetrec.Engine(cat, device=local, max_batch=B)
+        eng = fleetrec.Engine(cat, device=local, max_batch=B, table_dtype=tdt)
         try:
             eng.fill_hash(seed=0x5EED)
         except fleetrec.FleetRecError as ex:        # HBM too small for this many rows: halve and say so
@@ -428,7 +430,9 @@ def run_stress(args):
     w = fleetrec.Worker(eng)
     out = torch.empty(B, cat.concat_floats, dtype=torch.float32, device="cuda")
     pk = peaks()
-    alg = B * cat.gather_bytes_per_item(materialised=True)
+    # algorithmic bytes per item: rows at their storage width + int32 indices + the fp32 concat written
+    per_item = T * dim * esize + T * 4 + cat.concat_floats * 4
+    alg = B * per_item
     res = {}
     for kind in ("uniform", "zipf"):
         gen = oracle.uniform_indices if kind == "uniform" else oracle.zipf_indices
@@ -436,7 +440,7 @@ def run_stress(args):
         # parity gate on a sample: bit-exact against the oracle's hash fill
         eng.gather_only_async(pool[0], out, B, w)
         eng.sync(w)
-        exp = oracle.gather_hashed(cat, 0x5EED, pool[0][:128].cpu().numpy())
+        exp = oracle.quantize_dequantize(oracle.gather_hashed(cat, 0x5EED, pool[0][:128].cpu().numpy()), tdt)
         assert np.array_equal(out[:128].cpu().numpy().view(np.uint32), exp.view(np.uint32)), "concat not bit-exact"
         for i in range(max(args.warmup, 3)):
             eng.gather_only_async(pool[i % 4], out, B, w)
@@ -459,10 +463,12 @@ def run_stress(args):
         u = res["uniform"]
         line = {"metric": "gather HBM GB/s (lookup+concat, stress tables)", "value": world * u["achieved"], "unit": "GB/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": u["ms_per_launch"],
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 rows (byte copy)",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 rows (byte copy)" if esize == 4 else f"{args.table_dtype} rows widened to f32 (exact)",
                 "data": "synthetic",
                 "config": {"workload": f"BASELINE.json configs[4] per-GPU slice: {T} tables x {rows} rows x dim {dim} "
-                                       f"({cat.table_bytes() / 1e9:.1f} GB per GPU), lookup+concat only, batch {B}",
+                                       f"({cat.table_bytes() * esize / 4 / 1e9:.1f} GB per GPU, {args.table_dtype} rows), "
+                                       f"lookup+concat only, batch {B}",
                            "rows_requested": args.stress_rows, "rows_used": rows,
                            "note": "the literal config (1000 x 10M x 64 fp32 = 2.56 TB) exceeds 8 x 180 GB; rows are "
                                    "scaled so one GPU's slice fits HBM, tables stay >> L2 (126 MB)",
@@ -470,7 +476,7 @@ def run_stress(args):
                 "gpu_launches": int(2 * (args.steps + max(args.warmup, 3) + 1)),
                 "roofline": {"bound": "hbm", "achieved": u["achieved"], "peak": pk["hbm"], "unit": "GB/s", "frac": u["frac"],
                              "traffic": None, "kernel": "gather_concat", "ms_per_launch": u["ms_per_launch"],
-                             "peak_source": pk["src"], "algorithmic_bytes_per_item": cat.gather_bytes_per_item(True)},
+                             "peak_source": pk["src"], "algorithmic_bytes_per_item": per_item},
                 "uniform": res["uniform"], "zipf": res["zipf"]}
         print(json.dumps(line))
     w.close()
@@ -582,6 +588,8 @@ def main():
                          "sweep: configs[2] latency/throughput batch sweep")
     ap.add_argument("--stress-tables", type=int, default=125)
     ap.add_argument("--stress-rows", type=int, default=4000000)
+    ap.add_argument("--table-dtype", default="f32", choices=["f32", "f16", "bf16"],
+                    help="stress workload: storage type of the tables (SURVEY.md 8(f)4)")
     ap.add_argument("--sweep-launches", type=int, default=1000)
     args = ap.parse_args()
     if args.tiles:

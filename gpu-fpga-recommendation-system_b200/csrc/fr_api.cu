@@ -11,6 +11,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "fr_common.h"
 
 // ---------------------------------------------------------------------------
@@ -55,6 +57,7 @@ extern "C" fr_status fr_model_builtin(const char* name, fr_model_desc* out) {
       out->mlp_mode = FR_MLP_BIAS_RELU_SIGMOID;
       out->precision = FR_PREC_TF32;
       out->max_batch = 16384;
+      out->table_dtype = FR_TABLE_F32;
       return FR_OK;
     }
   return fr_fail(nullptr, FR_ERR_INVALID, "fr_model_builtin: unknown model '%s' (small|medium|large_half|large)", name);
@@ -68,6 +71,8 @@ static fr_status validate_desc(const fr_model_desc* d) {
     return fr_fail(nullptr, FR_ERR_INVALID, "fr_create: concat_floats=%d must be a positive multiple of 16 (one 512-bit "
                    "network word, constants.hpp:9)", d->concat_floats);
   if (d->max_batch <= 0) return fr_fail(nullptr, FR_ERR_INVALID, "fr_create: max_batch must be > 0");
+  if (d->table_dtype < FR_TABLE_F32 || d->table_dtype > FR_TABLE_BF16)
+    return fr_fail(nullptr, FR_ERR_INVALID, "fr_create: table_dtype %d (FR_TABLE_F32 | F16 | BF16)", d->table_dtype);
   for (int t = 0; t < d->n_tables; t++) {
     const fr_table_desc& td = d->tables[t];
     if (td.dim <= 0 || td.dim % 4) return fr_fail(nullptr, FR_ERR_INVALID, "table %d: dim=%d must be a multiple of 4 "
@@ -154,6 +159,7 @@ extern "C" fr_status fr_create(const fr_model_desc* desc, int n_gpus, const int*
   for (int k = 0; k < 4; k++) e->dims[k + 1] = desc->hidden[k];
   e->mlp_mode = desc->mlp_mode;
   e->precision = desc->precision;
+  e->table_dtype = desc->table_dtype;
   e->max_batch = desc->max_batch;
   if (const char* env = getenv("FR_GRAPHS")) e->use_graphs = atoi(env) != 0;
   if (const char* env = getenv("FR_PDL")) e->pdl_mask = atoi(env) & 7;
@@ -212,7 +218,7 @@ static fr_status ensure_table_mem(fr_engine* e, int t) {
   FrTable& tb = e->tables[t];
   if (tb.d) return FR_OK;
   FR_CUDA(e, cudaSetDevice(e->device));
-  FR_CUDA(e, cudaMalloc(&tb.d, (size_t)tb.rows * tb.dim * sizeof(float)));
+  FR_CUDA(e, cudaMalloc(&tb.d, (size_t)tb.rows * tb.dim * fr_table_esize(e)));
   e->chunks_dirty = true;
   return FR_OK;
 }
@@ -237,7 +243,28 @@ extern "C" fr_status fr_load_table(fr_engine* e, int table_id, const float* host
   if (rows <= 0) return fr_fail(e, FR_ERR_INVALID, "rows must be > 0");
   tb.rows = rows;
   if ((st = ensure_table_mem(e, table_id)) != FR_OK) return st;
-  FR_CUDA(e, fr_h2d(e, tb.d, host_rows, (size_t)rows * dim * sizeof(float)));
+  if (e->table_dtype == FR_TABLE_F32) {
+    FR_CUDA(e, fr_h2d(e, tb.d, host_rows, (size_t)rows * dim * sizeof(float)));
+  } else {
+    // fp32 image -> 2-byte rows on the device, through a bounded fp32 staging buffer
+    const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)(64 << 20) / ((int64_t)dim * 4));
+    float* stage = nullptr;
+    FR_CUDA(e, cudaMalloc(&stage, (size_t)std::min(chunk_rows, rows) * dim * sizeof(float)));
+    for (int64_t r0 = 0; r0 < rows; r0 += chunk_rows) {
+      const int64_t n = std::min(chunk_rows, rows - r0) * dim;
+      cudaError_t ce = fr_h2d(e, stage, host_rows + r0 * dim, (size_t)n * sizeof(float));
+      if (ce == cudaSuccess) {
+        st = frk_quantize(e, stage, reinterpret_cast<char*>(tb.d) + (size_t)r0 * dim * 2, n, e->default_stream->stream);
+        ce = cudaStreamSynchronize(e->default_stream->stream);
+      }
+      if (ce != cudaSuccess || st != FR_OK) {
+        cudaFree(stage);
+        if (st != FR_OK) return st;
+        return fr_fail(e, FR_ERR_CUDA, "fr_load_table: %s", cudaGetErrorString(ce));
+      }
+    }
+    cudaFree(stage);
+  }
   tb.loaded = true;
   return FR_OK;
 }
@@ -272,8 +299,22 @@ extern "C" fr_status fr_read_table(fr_engine* e, int table_id, int64_t first_row
   FrTable& tb = e->tables[table_id];
   if (!tb.d || !tb.loaded) return fr_fail(e, FR_ERR_STATE, "table %d not loaded", table_id);
   if (first_row < 0 || n_rows < 0 || first_row + n_rows > tb.rows) return fr_fail(e, FR_ERR_INVALID, "row range");
-  FR_CUDA(e, cudaMemcpy(host_out, tb.d + first_row * tb.dim, (size_t)n_rows * tb.dim * sizeof(float),
-                        cudaMemcpyDeviceToHost));
+  if (e->table_dtype == FR_TABLE_F32) {
+    FR_CUDA(e, cudaMemcpy(host_out, tb.d + first_row * tb.dim, (size_t)n_rows * tb.dim * sizeof(float),
+                          cudaMemcpyDeviceToHost));
+    return FR_OK;
+  }
+  if (n_rows == 0) return FR_OK;
+  float* tmp = nullptr;
+  FR_CUDA(e, cudaMalloc(&tmp, (size_t)n_rows * tb.dim * sizeof(float)));
+  st = frk_dequantize(e, reinterpret_cast<const char*>(tb.d) + (size_t)first_row * tb.dim * 2, tmp, n_rows * tb.dim,
+                      e->default_stream->stream);
+  cudaError_t ce = st == FR_OK ? cudaStreamSynchronize(e->default_stream->stream) : cudaSuccess;
+  if (st == FR_OK && ce == cudaSuccess)
+    ce = cudaMemcpy(host_out, tmp, (size_t)n_rows * tb.dim * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(tmp);
+  if (st != FR_OK) return st;
+  if (ce != cudaSuccess) return fr_fail(e, FR_ERR_CUDA, "fr_read_table: %s", cudaGetErrorString(ce));
   return FR_OK;
 }
 
@@ -594,7 +635,7 @@ extern "C" int64_t fr_table_bytes(const fr_engine* e) {
   if (!e) return 0;
   int64_t n = 0;
   for (const FrTable& t : e->tables)
-    if (t.d) n += t.rows * t.dim * (int64_t)sizeof(float);
+    if (t.d) n += t.rows * t.dim * (int64_t)fr_table_esize(e);
   return n;
 }
 
@@ -847,6 +888,7 @@ extern "C" fr_status fr_merge_tables(fr_engine* e, int a, int b, int dst) {
     return st;
   FrTable &A = e->tables[a], &B = e->tables[b], &M = e->tables[dst];
   if (!A.loaded || !B.loaded) return fr_fail(e, FR_ERR_STATE, "merge sources not loaded");
+  if (e->table_dtype != FR_TABLE_F32) return fr_fail(e, FR_ERR_UNSUPPORTED, "fr_merge_tables builds fp32 tables only");
   if (M.dim != A.dim + B.dim || M.rows != A.rows * B.rows)
     return fr_fail(e, FR_ERR_INVALID, "merged table %d must be (%lld rows, dim %d)", dst, (long long)(A.rows * B.rows),
                    A.dim + B.dim);

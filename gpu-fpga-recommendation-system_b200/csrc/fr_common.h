@@ -30,7 +30,7 @@ struct FrFuseChunk {
 };
 
 struct FrTable {
-  float* d = nullptr;
+  float* d = nullptr;    // device image; elements are fp32, or 2-byte f16 / bf16 when the engine's table_dtype says so
   int64_t rows = 0;
   int dim = 0;
   int tier = 0;
@@ -78,6 +78,7 @@ struct fr_engine {
   int dims[FR_MAX_LAYERS + 1] = {0, 0, 0, 0, 0};
   int mlp_mode = FR_MLP_BIAS_RELU_SIGMOID;
   int precision = FR_PREC_TF32;
+  int table_dtype = FR_TABLE_F32;
   int max_batch = 0;
   bool use_graphs = true;  // FR_GRAPHS=0 disables CUDA-graph replay of fr_infer
   // Programmatic dependent launch between the kernels of a batch, FR_PDL bit mask: 1 = MLP layers 2 and 3
@@ -164,8 +165,13 @@ inline size_t fr_xchg_concat_off(const fr_engine* e, int slot, int parity) {
 inline size_t fr_xchg_flags_off(const fr_engine* e, int slot) {
   return (size_t)slot * fr_xchg_slot_floats(e) + 2 * fr_xchg_buf_floats(e);
 }
+// element size of the table storage type
+inline size_t fr_table_esize(const fr_engine* e) { return e->table_dtype == FR_TABLE_F32 ? 4 : 2; }
 fr_status frk_fill_reference(fr_engine* e, float* d, int64_t rows, int dim, int64_t debug_rows, cudaStream_t st);
 fr_status frk_fill_hash(fr_engine* e, float* d, uint32_t seed, int table, int64_t rows, int dim, cudaStream_t st);
+// fp32 -> table storage type (round to nearest even) and back (exact), n elements
+fr_status frk_quantize(fr_engine* e, const float* src, void* dst, int64_t n, cudaStream_t st);
+fr_status frk_dequantize(fr_engine* e, const void* src, float* dst, int64_t n, cudaStream_t st);
 fr_status frk_merge(fr_engine* e, const float* A, int64_t rowsA, int dimA, const float* B, int64_t rowsB, int dimB,
                     float* M, cudaStream_t st);
 fr_status frk_transpose_round_tf32(fr_engine* e, const float* W, int in, int out, float* Wt, cudaStream_t st);

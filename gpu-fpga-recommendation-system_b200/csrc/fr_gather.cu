@@ -17,6 +17,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "fr_common.h"
 
 namespace {
@@ -37,10 +40,29 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(r);
 }
 
+// One 4-float piece of a row stored as 2-byte elements (FR_TABLE_F16 / FR_TABLE_BF16): 8 bytes in,
+// widened exactly to fp32 (the stated dequant: concat == float32(float16(row))).
+template <int DT>
+__device__ __forceinline__ float4 ld_row8(const float4* base, int64_t piece) {
+  uint2 w;
+  const uint2* p = reinterpret_cast<const uint2*>(base) + piece;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v2.u32 {%0,%1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(p));
+  float4 v;
+  if (DT == FR_TABLE_F16) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+    v = make_float4(a.x, a.y, b.x, b.y);
+  } else {   // bf16 is the upper half of an fp32
+    v = make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u), __uint_as_float(w.y << 16),
+                    __uint_as_float(w.y & 0xFFFF0000u));
+  }
+  return v;
+}
+
 // PUSH = false: out4 is the local [B][C] buffer.
 // PUSH = true : peer_out[r] is rank r's exchange buffer; item b lands on rank
 //               b / items_per_rank at local row b % items_per_rank (NVLink peer stores).
-template <bool ROUND, bool PUSH>
+template <bool ROUND, bool PUSH, int DT>
 __global__ void __launch_bounds__(256) gather_concat_kernel(const FrChunk* __restrict__ chunks,
                                                             const int* __restrict__ chunk_ids, int n_chunks,
                                                             const int32_t* __restrict__ idx, int T, int b_begin,
@@ -62,7 +84,8 @@ __global__ void __launch_bounds__(256) gather_concat_kernel(const FrChunk* __res
   float4 v[kItems];
 #pragma unroll
   for (int i = 0; i < kItems; i++)  // 64-bit addressing: 100 M rows x 128 B = 12.8 GB tables
-    v[i] = ld_row16(ch.base + row[i] * ch.stride4 + ch.col4);
+    v[i] = DT == FR_TABLE_F32 ? ld_row16(ch.base + row[i] * ch.stride4 + ch.col4)
+                              : ld_row8<DT == FR_TABLE_F32 ? FR_TABLE_F16 : DT>(ch.base, row[i] * ch.stride4 + ch.col4);
   // Programmatic dependent launch: indices and tables are not written by the kernels of the
   // preceding batch, so everything above overlaps its tail; the concat buffer is (the first MLP
   // layer of the previous batch read it), so the stores wait for the grid dependency.  Both
@@ -83,6 +106,29 @@ __global__ void __launch_bounds__(256) gather_concat_kernel(const FrChunk* __res
     } else {
       out4[(size_t)b * C + c] = o;
     }
+  }
+}
+
+__device__ __forceinline__ uint16_t quant16(float x, int dt) {
+  return dt == FR_TABLE_F16 ? __half_as_ushort(__float2half_rn(x)) : __bfloat16_as_ushort(__float2bfloat16_rn(x));
+}
+__device__ __forceinline__ float dequant16(uint16_t h, int dt) {
+  return dt == FR_TABLE_F16 ? __half2float(__ushort_as_half(h)) : __uint_as_float((uint32_t)h << 16);
+}
+__global__ void quantize_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int64_t n, int dt) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = quant16(src[i], dt);
+}
+__global__ void dequantize_kernel(const uint16_t* __restrict__ src, float* __restrict__ dst, int64_t n, int dt) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = dequant16(src[i], dt);
+}
+// 2-byte variants of the two device fills: the fp32 value of the fp32 fill, rounded to nearest even
+__global__ void fill_reference16_kernel(uint16_t* __restrict__ t, int64_t n, int dim, int64_t filled_rows, int dt) {
+  const uint16_t one = quant16(1.f, dt);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / dim;
+    t[i] = (r < filled_rows && (r & 1) == 0) ? one : (uint16_t)0;
   }
 }
 
@@ -107,6 +153,11 @@ __device__ __forceinline__ uint32_t hash_bits(uint32_t seed, uint32_t table, uin
 __global__ void fill_hash_kernel(uint32_t* __restrict__ t, int64_t n, int dim, uint32_t seed, uint32_t table) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     t[i] = hash_bits(seed, table, (uint64_t)(i / dim), (uint32_t)(i % dim));
+}
+
+__global__ void fill_hash16_kernel(uint16_t* __restrict__ t, int64_t n, int dim, uint32_t seed, uint32_t table, int dt) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    t[i] = quant16(__uint_as_float(hash_bits(seed, table, (uint64_t)(i / dim), (uint32_t)(i % dim))), dt);
 }
 
 __global__ void merge_kernel(const float4* __restrict__ A, int dimA4, const float4* __restrict__ B, int64_t rowsB,
@@ -160,8 +211,11 @@ void launch_gather(const fr_engine* e, const int* d_ids, int n_chunks, const int
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = ((e->pdl_mask & 4) && !PUSH) ? 1 : 0;   // the sharded push is ordered by its own flag kernel
-  cudaLaunchKernelEx(&cfg, gather_concat_kernel<ROUND, PUSH>, (const FrChunk*)e->d_chunks, d_ids, n_chunks, d_idx,
-                     (int)e->tables.size(), b_begin, b_end, out4, peers, C, items_per_rank, peer_off4);
+  auto kern = e->table_dtype == FR_TABLE_F32 ? gather_concat_kernel<ROUND, PUSH, FR_TABLE_F32>
+              : e->table_dtype == FR_TABLE_F16 ? gather_concat_kernel<ROUND, PUSH, FR_TABLE_F16>
+                                               : gather_concat_kernel<ROUND, PUSH, FR_TABLE_BF16>;
+  cudaLaunchKernelEx(&cfg, kern, (const FrChunk*)e->d_chunks, d_ids, n_chunks, d_idx, (int)e->tables.size(), b_begin,
+                     b_end, out4, peers, C, items_per_rank, peer_off4);
 }
 
 }  // namespace
@@ -210,8 +264,12 @@ fr_status frk_fill_reference(fr_engine* e, float* d, int64_t rows, int dim, int6
   int64_t pairs = rows / 2;
   if (debug_rows > 0 && debug_rows / 2 < pairs) pairs = debug_rows / 2;
   const int64_t n4 = rows * dim / 4;
-  fill_reference_kernel<<<grid_for(n4, 256, e->sm_count), 256, 0, st>>>(reinterpret_cast<float4*>(d), n4, dim / 4,
-                                                                        pairs * 2);
+  if (e->table_dtype != FR_TABLE_F32)
+    fill_reference16_kernel<<<grid_for(rows * dim, 256, e->sm_count), 256, 0, st>>>(reinterpret_cast<uint16_t*>(d), rows * dim,
+                                                                                   dim, pairs * 2, e->table_dtype);
+  else
+    fill_reference_kernel<<<grid_for(n4, 256, e->sm_count), 256, 0, st>>>(reinterpret_cast<float4*>(d), n4, dim / 4,
+                                                                          pairs * 2);
   e->launches++;
   FR_CUDA(e, cudaGetLastError());
   return FR_OK;
@@ -219,8 +277,27 @@ fr_status frk_fill_reference(fr_engine* e, float* d, int64_t rows, int dim, int6
 
 fr_status frk_fill_hash(fr_engine* e, float* d, uint32_t seed, int table, int64_t rows, int dim, cudaStream_t st) {
   const int64_t n = rows * dim;
-  fill_hash_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(reinterpret_cast<uint32_t*>(d), n, dim, seed,
-                                                                  (uint32_t)table);
+  if (e->table_dtype != FR_TABLE_F32)
+    fill_hash16_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(reinterpret_cast<uint16_t*>(d), n, dim, seed,
+                                                                     (uint32_t)table, e->table_dtype);
+  else
+    fill_hash_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(reinterpret_cast<uint32_t*>(d), n, dim, seed,
+                                                                    (uint32_t)table);
+  e->launches++;
+  FR_CUDA(e, cudaGetLastError());
+  return FR_OK;
+}
+
+fr_status frk_quantize(fr_engine* e, const float* src, void* dst, int64_t n, cudaStream_t st) {
+  quantize_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(src, reinterpret_cast<uint16_t*>(dst), n, e->table_dtype);
+  e->launches++;
+  FR_CUDA(e, cudaGetLastError());
+  return FR_OK;
+}
+
+fr_status frk_dequantize(fr_engine* e, const void* src, float* dst, int64_t n, cudaStream_t st) {
+  dequantize_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(src), dst, n,
+                                                                  e->table_dtype);
   e->launches++;
   FR_CUDA(e, cudaGetLastError());
   return FR_OK;

@@ -999,7 +999,8 @@ bool frtc_can_fuse(const fr_engine* e) {
   // row pitch and in-row offset of a piece must fit the packed descriptor (dims up to 1020 floats)
   bool dims_ok = true;
   for (const FrTable& t : e->tables) dims_ok = dims_ok && t.dim / 4 < 256;
-  return e->fuse_lookup && st && st->ready && e->world == 1 && e->precision == FR_PREC_TF32 && e->dims[1] % kFuseN == 0 &&
+  return e->fuse_lookup && st && st->ready && e->world == 1 && e->precision == FR_PREC_TF32 &&
+         e->table_dtype == FR_TABLE_F32 && e->dims[1] % kFuseN == 0 &&
          e->dims[1] <= kMaxN && e->D / 4 <= kFuseMaxChunks && dims_ok;
 }
 

@@ -6,5 +6,5 @@ model catalogues.  Nothing here computes on the CPU.
 """
 from . import catalogue  # noqa: F401
 from ._capi import (FR_ERR_CUDA, FR_ERR_INVALID, FR_ERR_OOM, FR_ERR_STATE, FR_ERR_UNSUPPORTED, FR_MLP_BIAS_RELU_SIGMOID,  # noqa: F401
-                    FR_MLP_LINEAR, FR_OK, FR_PREC_FP32, FR_PREC_TF32)
-from .engine import Batcher, Engine, FleetRecError, Worker, merge_index  # noqa: F401
+                    FR_MLP_LINEAR, FR_OK, FR_PREC_FP32, FR_PREC_TF32, FR_TABLE_BF16, FR_TABLE_F16, FR_TABLE_F32)
+from .engine import Batcher, Engine, FleetRecError, Ingest, Worker, merge_index  # noqa: F401

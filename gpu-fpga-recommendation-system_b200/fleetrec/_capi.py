@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libfleetrec.so")
 FR_OK, FR_ERR_INVALID, FR_ERR_CUDA, FR_ERR_OOM, FR_ERR_STATE, FR_ERR_UNSUPPORTED = range(6)
 FR_MLP_LINEAR, FR_MLP_BIAS_RELU_SIGMOID = 0, 1
 FR_PREC_TF32, FR_PREC_FP32 = 0, 1
+FR_TABLE_F32, FR_TABLE_F16, FR_TABLE_BF16 = 0, 1, 2
 
 
 class TableDesc(C.Structure):
@@ -28,7 +29,8 @@ class SegmentDesc(C.Structure):
 class ModelDesc(C.Structure):
     _fields_ = [("name", C.c_char_p), ("n_tables", C.c_int), ("tables", C.POINTER(TableDesc)),
                 ("n_segments", C.c_int), ("segments", C.POINTER(SegmentDesc)), ("concat_floats", C.c_int),
-                ("hidden", C.c_int * 4), ("mlp_mode", C.c_int), ("precision", C.c_int), ("max_batch", C.c_int)]
+                ("hidden", C.c_int * 4), ("mlp_mode", C.c_int), ("precision", C.c_int), ("max_batch", C.c_int),
+                ("table_dtype", C.c_int)]
 
 
 class BatcherConfig(C.Structure):
@@ -40,6 +42,17 @@ class BatcherStats(C.Structure):
                 ("latency_p50_us", C.c_float), ("latency_p99_us", C.c_float)]
 
 
+class IngestConfig(C.Structure):
+    _fields_ = [("base_port", C.c_int), ("n_conn", C.c_int), ("batch", C.c_int), ("payload", C.c_int),
+                ("total_batches", C.c_int64), ("loopback_only", C.c_int), ("scores_out", C.c_void_p),
+                ("max_batches_per_conn", C.c_int64)]
+
+
+class IngestStats(C.Structure):
+    _fields_ = [("batches", C.c_int64), ("bytes", C.c_int64), ("seconds", C.c_double), ("connections", C.c_int)]
+
+
+FR_INGEST_CONCAT, FR_INGEST_INDICES = 0, 1
 _P, _I, _I64, _U32 = C.c_void_p, C.c_int, C.c_int64, C.c_uint32
 # name -> (restype, argtypes); must list every symbol include/fleetrec.h declares
 SIGNATURES = {
@@ -84,6 +97,10 @@ SIGNATURES = {
     "fr_batcher_flush": (_I, [_P]),
     "fr_batcher_get_stats": (_I, [_P, C.POINTER(BatcherStats)]),
     "fr_batcher_destroy": (None, [_P]),
+    "fr_ingest_start": (_I, [_P, C.POINTER(IngestConfig), C.POINTER(_P)]),
+    "fr_ingest_wait": (_I, [_P, C.POINTER(IngestStats)]),
+    "fr_ingest_last_scores": (_I, [_P, _I, _P, C.POINTER(C.c_int64)]),
+    "fr_ingest_destroy": (None, [_P]),
 }
 
 _LIB = None

@@ -37,7 +37,7 @@ def _ptr(a):
 
 
 def model_desc(model: Model, mlp_mode=_capi.FR_MLP_BIAS_RELU_SIGMOID, precision=_capi.FR_PREC_TF32,
-               max_batch=16384):
+               max_batch=16384, table_dtype=_capi.FR_TABLE_F32):
     d = _capi.ModelDesc()
     tabs = (_capi.TableDesc * model.n_tables)()
     for i, t in enumerate(model.tables):
@@ -51,6 +51,7 @@ def model_desc(model: Model, mlp_mode=_capi.FR_MLP_BIAS_RELU_SIGMOID, precision=
     d.concat_floats = model.concat_floats
     d.hidden = (C.c_int * 4)(*model.hidden)
     d.mlp_mode, d.precision, d.max_batch = mlp_mode, precision, max_batch
+    d.table_dtype = table_dtype
     d._keep = (tabs, segs)
     return d
 
@@ -76,10 +77,10 @@ class Worker:
 
 class Engine:
     def __init__(self, model: Model, device=0, mlp_mode=_capi.FR_MLP_BIAS_RELU_SIGMOID,
-                 precision=_capi.FR_PREC_TF32, max_batch=16384):
+                 precision=_capi.FR_PREC_TF32, max_batch=16384, table_dtype=_capi.FR_TABLE_F32):
         self._L = _capi.lib()
         self.model = model
-        self._desc = model_desc(model, mlp_mode, precision, max_batch)
+        self._desc = model_desc(model, mlp_mode, precision, max_batch, table_dtype)
         h = C.c_void_p()
         dev = (C.c_int * 1)(device)
         rc = self._L.fr_create(C.byref(self._desc), 1, dev, C.byref(h))
@@ -284,6 +285,40 @@ class Batcher:
     def close(self):
         if self._h:
             self.engine._L.fr_batcher_destroy(self._h)
+            self._h = None
+
+
+class Ingest:
+    """B2-compatible TCP ingest (fr_ingest_*): listens on base_port + i like the
+    reference's cuda_server.c, runs the MLP (payload='concat') or lookup + MLP (payload='indices')
+    on every block received."""
+
+    def __init__(self, engine, base_port, n_conn, batch, payload="concat", total_batches=0, max_batches_per_conn=0,
+                 loopback_only=True):
+        self.engine = engine
+        self.scores = np.zeros((n_conn, max(max_batches_per_conn, 1), batch), np.float32)
+        cfg = _capi.IngestConfig(base_port, n_conn, batch,
+                                 _capi.FR_INGEST_CONCAT if payload == "concat" else _capi.FR_INGEST_INDICES,
+                                 total_batches, int(loopback_only),
+                                 self.scores.ctypes.data if max_batches_per_conn > 0 else None, max_batches_per_conn)
+        h = C.c_void_p()
+        engine._chk(engine._L.fr_ingest_start(engine._h, C.byref(cfg), C.byref(h)))
+        self._h = h
+
+    def wait(self):
+        st = _capi.IngestStats()
+        self.engine._chk(self.engine._L.fr_ingest_wait(self._h, C.byref(st)))
+        return {f: getattr(st, f) for f, _ in st._fields_}
+
+    def last_scores(self, conn):
+        out = np.empty(self.scores.shape[2], np.float32)
+        no = C.c_int64()
+        self.engine._chk(self.engine._L.fr_ingest_last_scores(self._h, conn, out.ctypes.data, C.byref(no)))
+        return out, no.value
+
+    def close(self):
+        if self._h:
+            self.engine._L.fr_ingest_destroy(self._h)
             self._h = None
 
 

@@ -47,6 +47,13 @@ enum { FR_MLP_LINEAR = 0, FR_MLP_BIAS_RELU_SIGMOID = 1 };
  *   FP32   SIMT FFMA kernels, FP32 operands and accumulate (reference's CUBLAS_COMPUTE_32F) */
 enum { FR_PREC_TF32 = 0, FR_PREC_FP32 = 1 };
 
+/* Storage type of the embedding tables in HBM.  The reference stores
+ * fp32 (constants.hpp:4,11: one axi word = 4 floats).  F16 / BF16 halve the table bytes and the
+ * lookup's row traffic; rows are converted with round-to-nearest-even when loaded and widened
+ * exactly to fp32 by the lookup, so the concat vector is bit-exact AFTER THE STATED DEQUANT:
+ * concat == float32(float16(row)) element for element.  Everything after the lookup is unchanged. */
+enum { FR_TABLE_F32 = 0, FR_TABLE_F16 = 1, FR_TABLE_BF16 = 2 };
+
 typedef struct fr_table_desc {
   int tier;          /* FR_TIER_*                                              */
   int tier_index;    /* i of TABLE_SIZE_<tier>_<i>                             */
@@ -74,6 +81,7 @@ typedef struct fr_model_desc {
   int mlp_mode;                     /* FR_MLP_*                                */
   int precision;                    /* FR_PREC_*                               */
   int max_batch;                    /* largest B a stream will be given        */
+  int table_dtype;                  /* FR_TABLE_* (0 = fp32, the reference)    */
 } fr_model_desc;
 
 typedef struct fr_engine fr_engine;
@@ -100,7 +108,8 @@ const char* fr_last_error(const fr_engine* e);
  * memory-capped runs use the real dims with fewer rows). */
 fr_status fr_set_table_rows(fr_engine* e, int table_id, int64_t rows);
 
-/* Copy a host table image [rows][dim] fp32 into HBM; caller keeps ownership.
+/* Copy a host table image [rows][dim] fp32 into HBM (converted to the engine's table_dtype on the
+ * device, round-to-nearest-even); caller keeps ownership.
  * Replaces host.cpp:324-423,592-750 (vector alloc + init + migrate). */
 fr_status fr_load_table(fr_engine* e, int table_id, const float* host_rows, int64_t rows, int dim);
 /* Device-side fills, bit-identical to the oracle's:
@@ -109,7 +118,7 @@ fr_status fr_load_table(fr_engine* e, int table_id, const float* host_rows, int6
  *   hash:      every float a distinct finite normal derived from (seed, table, row, col). */
 fr_status fr_fill_table_reference(fr_engine* e, int table_id, int64_t debug_rows);
 fr_status fr_fill_table_hash(fr_engine* e, int table_id, uint32_t seed);
-/* Read rows back (tests): copies [n_rows][dim] starting at first_row to host. */
+/* Read rows back (tests): copies [n_rows][dim] starting at first_row to host, widened to fp32. */
 fr_status fr_read_table(fr_engine* e, int table_id, int64_t first_row, int64_t n_rows, float* host_out);
 
 /* Layer k in 0..3.  W is the reference's layout: column-major out_k x in_k with
@@ -225,6 +234,39 @@ fr_status fr_batcher_flush(fr_batcher* b);
 fr_status fr_batcher_get_stats(fr_batcher* b, fr_batcher_stats* out);
 /* Scores everything already submitted, then stops the threads and frees the staging buffers. */
 void fr_batcher_destroy(fr_batcher* b);
+
+/* ---- B2-compatible streaming ingest, SURVEY.md section 8(f)3 ------------------ */
+/* Accepts the byte stream the reference's senders produce (sendData() embedding_47_krnl.cpp:45-147,
+ * multiple_connections_network_client_sender.c:55-100): connection i on base_port + i, raw
+ * little-endian fp32, exactly batch * concat_floats * 4 bytes per batch, no header -- what
+ * thread_consume() read()s (cuda_server.c:360-461, constant.h:33-41) -- and runs fr_mlp_only on every
+ * block; batch numbers come off one counter shared by all connections (global_batch_count).
+ * FR_INGEST_INDICES takes batch * n_tables int32 per block instead and runs fr_infer. */
+enum { FR_INGEST_CONCAT = 0, FR_INGEST_INDICES = 1 };
+typedef struct fr_ingest fr_ingest;
+typedef struct fr_ingest_config {
+  int base_port;                 /* PORT (constant.h:39)                                        */
+  int n_conn;                    /* THREAD_NUM: listeners, one accepted connection each         */
+  int batch;                     /* BATCH_SIZE                                                  */
+  int payload;                   /* FR_INGEST_*                                                 */
+  int64_t total_batches;         /* TOTAL_BATCH_NUM over all connections; 0 = until senders close */
+  int loopback_only;             /* bind 127.0.0.1 instead of INADDR_ANY                        */
+  float* scores_out;             /* optional sink [n_conn][max_batches_per_conn][batch]: scores of
+                                    connection c's k-th block (the reference discards all but the
+                                    first outputs, cuda_server.c:499-502)                       */
+  int64_t max_batches_per_conn;
+} fr_ingest_config;
+typedef struct fr_ingest_stats {
+  int64_t batches, bytes;
+  double seconds;                /* start -> last connection finished                           */
+  int connections;
+} fr_ingest_stats;
+/* Binds and listens on every port before returning, then accepts/receives on its own threads. */
+fr_status fr_ingest_start(fr_engine* e, const fr_ingest_config* cfg, fr_ingest** out);
+/* Blocks until every connection has ended (sender closed, or total_batches reached). */
+fr_status fr_ingest_wait(fr_ingest* g, fr_ingest_stats* stats);
+fr_status fr_ingest_last_scores(fr_ingest* g, int conn, float* scores /* [batch] */, int64_t* batch_no);
+void fr_ingest_destroy(fr_ingest* g);
 
 #ifdef __cplusplus
 }

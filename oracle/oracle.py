@@ -206,3 +206,22 @@ def gather_hashed(model, seed, idx):
             cache[s.table] = hash_rows(seed, s.table, idx[:, s.table], model.tables[s.table].dim)
         out[:, s.dst:s.dst + s.len] = cache[s.table][:, s.col:s.col + s.len]
     return out
+
+
+# ---- reduced-precision table storage: the STATED dequant --------------------
+def quantize_dequantize(x, table_dtype):
+    """What a table stored as f16 / bf16 returns for fp32 contents x: round to nearest even into
+    the 2-byte type, widen exactly back to fp32.  table_dtype: 0 fp32 (identity), 1 f16, 2 bf16.
+    Quantisation is element-wise, so it commutes with the lookup: gather(quantised tables) ==
+    quantize_dequantize(gather(fp32 tables))."""
+    x = np.ascontiguousarray(x, np.float32)
+    if table_dtype == 0:
+        return x
+    if table_dtype == 1:
+        with np.errstate(over="ignore"):
+            return x.astype(np.float16).astype(np.float32)
+    if table_dtype == 2:
+        b = x.view(np.uint32).astype(np.uint64)
+        r = (b + 0x7FFF + ((b >> 16) & 1)) & 0xFFFF0000            # RNE on the upper 16 bits
+        return r.astype(np.uint32).view(np.float32).reshape(x.shape)
+    raise ValueError(table_dtype)

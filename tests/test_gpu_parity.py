@@ -491,3 +491,135 @@ def test_fused_chain_reference_kat(monkeypatch):
     exp = np.where(idx[:, 0] % 2 == 0, np.float32(KAT["small"]), np.float32(0))
     assert np.array_equal(out, exp)
     eng.close()
+
+
+# ---------------------------------------------------------------- reduced-precision table storage (8f-4)
+@pytest.mark.parametrize("dt", (fleetrec.FR_TABLE_F16, fleetrec.FR_TABLE_BF16))
+def test_reduced_precision_tables_bit_exact_after_stated_dequant(dt):
+    """Tables stored as f16 / bf16 in HBM: rows uploaded as fp32 are converted on the device (RNE),
+    device fills produce the same 2-byte values, the lookup widens exactly -- concat ==
+    float32(round(rows)) bit for bit, scores within the MLP tolerance of the oracle run on the
+    dequantised concat.  Table bytes halve."""
+    cat = catalogue.load("medium").with_row_cap(3000)
+    dims = cat.layer_dims
+    tables = oracle.make_tables(cat, "hash", seed=0x5EED)
+    W, b = oracle.make_weights(dims, seed=42)
+    idx = oracle.zipf_indices(cat, 700, seed=2)
+    idx[0, :] = [t.rows - 1 for t in cat.tables]
+    exp = oracle.quantize_dequantize(oracle.gather(cat, tables, idx), dt)
+    eng = fleetrec.Engine(cat, max_batch=1024, table_dtype=dt)
+    eng.load_tables(tables)                                     # fp32 in, converted on the device
+    assert eng.table_bytes() == cat.table_bytes() // 2
+    assert_bits_equal(eng.gather_only(idx), exp)
+    assert_bits_equal(eng.read_table(5, 10, 20), oracle.quantize_dequantize(tables[5][10:30], dt))
+    eng.load_mlp(W, b)
+    assert rel_err(eng.infer(idx), oracle.mlp(exp, dims, W, b, mode=1)) <= TOL
+    eng.close()
+    eng = fleetrec.Engine(cat, max_batch=1024, table_dtype=dt)
+    eng.fill_hash(seed=0x5EED)                                  # device-side fill: same values
+    assert_bits_equal(eng.gather_only(idx), exp)
+    eng.close()
+    eng = fleetrec.Engine(cat, max_batch=64, table_dtype=dt)
+    eng.fill_reference()                                        # 1.0 / 0.0 are exact in both types
+    i1 = oracle.idx_reference(32, cat.n_tables)
+    assert_bits_equal(eng.gather_only(i1), oracle.gather(cat, oracle.make_tables(cat, "reference"), i1))
+    with pytest.raises(fleetrec.FleetRecError):
+        eng.merge_tables(0, 1, 2)                               # merged images are built in fp32 only
+    eng.close()
+
+
+# ---------------------------------------------------------------- B2-compatible TCP ingest (8f-3)
+def _send_blocks(port, blocks):
+    """What multiple_connections_network_client_sender.c:55-100 does: connect, then send() raw
+    little-endian bytes block after block, no header."""
+    import socket
+    with socket.create_connection(("127.0.0.1", port), timeout=30) as s:
+        for blk in blocks:
+            s.sendall(blk.tobytes())
+
+
+def _free_base_port(n):
+    import socket
+    for base in range(18080, 28080, 97):
+        try:
+            socks = []
+            for i in range(n):
+                s = socket.socket()
+                s.bind(("127.0.0.1", base + i))
+                socks.append(s)
+            for s in socks:
+                s.close()
+            return base
+        except OSError:
+            for s in socks:
+                s.close()
+    pytest.skip("no free port range")
+
+
+@pytest.mark.parametrize("payload", ("concat", "indices"))
+def test_ingest_accepts_the_reference_wire_format(payload):
+    """Senders speaking the reference's B2 format (raw fp32 [item][INPUT_SIZE] on PORT+i, or raw int32
+    index rows) against fr_ingest on loopback: every block of every connection is scored, in order,
+    against the oracle; batch numbers come off one shared counter."""
+    import threading
+    cat = catalogue.load("small").with_row_cap(20000)
+    dims = cat.layer_dims
+    tables = oracle.make_tables(cat, "hash", seed=19)
+    W, b = oracle.make_weights(dims, seed=42)
+    eng = fleetrec.Engine(cat, max_batch=128)
+    eng.load_tables(tables)
+    eng.load_mlp(W, b)
+    n_conn, per_conn, B = 3, 5, 128
+    base = _free_base_port(n_conn)
+    ing = fleetrec.Ingest(eng, base, n_conn, B, payload=payload, max_batches_per_conn=per_conn)
+    idx = [[oracle.zipf_indices(cat, B, seed=100 * c + k) for k in range(per_conn)] for c in range(n_conn)]
+    x = [[oracle.gather(cat, tables, idx[c][k]) for k in range(per_conn)] for c in range(n_conn)]
+    blocks = x if payload == "concat" else idx
+    th = [threading.Thread(target=_send_blocks, args=(base + c, blocks[c])) for c in range(n_conn)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=60)
+    st = ing.wait()
+    assert st["batches"] == n_conn * per_conn and st["connections"] == n_conn
+    assert st["bytes"] == n_conn * per_conn * blocks[0][0].nbytes
+    for c in range(n_conn):
+        for k in range(per_conn):
+            exp = oracle.mlp(x[c][k], dims, W, b, mode=1)
+            assert rel_err(ing.scores[c, k], exp) <= TOL, (c, k)
+        last, no = ing.last_scores(c)
+        assert np.array_equal(last, ing.scores[c, per_conn - 1]) and 0 <= no < n_conn * per_conn
+    ing.close()
+    eng.close()
+
+
+def test_ingest_total_batches_and_truncated_stream():
+    import threading
+    cat = catalogue.load("small").with_row_cap(64)
+    dims = cat.layer_dims
+    eng = fleetrec.Engine(cat, mlp_mode=fleetrec.FR_MLP_LINEAR, max_batch=32)
+    eng.load_mlp([np.ones((dims[k], dims[k + 1]), np.float32) for k in range(4)])
+    base = _free_base_port(2)
+    # TOTAL_BATCH_NUM = 3 over two connections: the shared counter stops the servers (cuda_server.c:408-412)
+    ing = fleetrec.Ingest(eng, base, 2, 32, total_batches=3, max_batches_per_conn=4)
+    ones = np.ones((32, dims[0]), np.float32)                 # the reference's own traffic: all-ones vectors
+    th = [threading.Thread(target=_send_blocks, args=(base + c, [ones, ones])) for c in range(2)]
+    for t in th:
+        t.start()
+    st = ing.wait()
+    for t in th:
+        t.join(timeout=30)
+    assert st["batches"] == 3
+    assert np.all(ing.scores[0, 0] == np.float32(KAT["small"]))                       # README.md:7-11 known answer
+    ing.close()
+    # a sender that dies inside a block is an error, not a hang and not a silently short batch
+    base = _free_base_port(1)
+    ing = fleetrec.Ingest(eng, base, 1, 32, max_batches_per_conn=2)
+    t = threading.Thread(target=_send_blocks, args=(base, [ones, ones[:5]]))
+    t.start()
+    t.join(timeout=30)
+    with pytest.raises(fleetrec.FleetRecError):
+        ing.wait()
+    assert np.all(ing.scores[0, 0] == np.float32(KAT["small"]))
+    ing.close()
+    eng.close()

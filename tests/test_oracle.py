@@ -227,3 +227,18 @@ def test_merge_planner_respects_budget_and_int32():
     bad[0, a], bad[0, b] = 2 ** 31, 5                                    # index outside the table: remap must not wrap
     with pytest.raises(OverflowError):
         mm.remap(bad)
+
+
+def test_stated_dequant_is_rne_and_idempotent():
+    """SURVEY.md 8(f)4 parity contract: f16 / bf16 table storage returns float32(round_to_nearest_even(x))."""
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(-1, 1, 4096).astype(np.float32), oracle.fill_hash(3, 7, 64, 16).ravel(),
+                        np.float32([0.0, 1.0, -1.0, 0.5, 2.0 ** -9, 1 + 2.0 ** -8, 1 + 2.0 ** -11, 1 + 3 * 2.0 ** -11])])
+    for dt, mant in ((1, 10), (2, 7)):
+        q = oracle.quantize_dequantize(x, dt)
+        assert np.array_equal(oracle.quantize_dequantize(q, dt), q)                       # idempotent
+        assert np.all(np.abs(q - x) <= np.abs(x) * 2.0 ** -(mant + 1) + 1e-30)          # half an ulp
+        assert np.array_equal(q.view(np.uint32) & ((1 << (23 - mant)) - 1), np.zeros(q.shape, np.uint32))
+    assert oracle.quantize_dequantize(np.float32([1 + 2.0 ** -8]), 2)[0] == np.float32(1.0)            # tie -> even
+    assert oracle.quantize_dequantize(np.float32([1 + 3 * 2.0 ** -8]), 2)[0] == np.float32(1 + 2.0 ** -6)
+    assert np.array_equal(oracle.quantize_dequantize(x, 0), x)
