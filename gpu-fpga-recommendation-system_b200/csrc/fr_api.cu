@@ -202,6 +202,7 @@ extern "C" void fr_destroy(fr_engine* e) {
   cudaFree(e->d_peer_ptrs);
   cudaFree(e->d_xchg);
   cudaFree(e->d_step);
+  cudaFree(e->d_done);
   if (e->h_shard_err) cudaFreeHost(e->h_shard_err);
   if (e->h_watch) cudaFreeHost(e->h_watch);
   delete e;
@@ -734,6 +735,8 @@ extern "C" fr_status fr_shard_init(fr_engine* e, int rank, int world, const int*
   FR_CUDA(e, cudaMemsetAsync(e->d_xchg, 0, bytes, e->default_stream->stream));
   FR_CUDA(e, cudaMalloc(&e->d_step, sizeof(int) * e->n_slots));
   FR_CUDA(e, cudaMemsetAsync(e->d_step, 0, sizeof(int) * e->n_slots, e->default_stream->stream));
+  FR_CUDA(e, cudaMalloc(&e->d_done, sizeof(int) * e->n_slots));
+  FR_CUDA(e, cudaMemsetAsync(e->d_done, 0, sizeof(int) * e->n_slots, e->default_stream->stream));
   FR_CUDA(e, cudaHostAlloc(&e->h_shard_err, sizeof(int), cudaHostAllocMapped));
   *e->h_shard_err = 0;
   FR_CUDA(e, cudaStreamSynchronize(e->default_stream->stream));
@@ -857,8 +860,13 @@ static fr_status shard_infer_enqueue(fr_engine* e, fr_stream_s* s, const int32_t
   const int32_t* d_idx = nullptr;
   fr_status st = stage_idx(e, s, idx, B_global, &d_idx);
   if (st != FR_OK) return st;
-  if ((st = frk_gather_push(e, d_idx, B_global, s->slot, parity, s->stream)) != FR_OK) return st;
-  if ((st = frk_shard_signal_wait(e, s->slot, s->stream)) != FR_OK) return st;
+  static const bool one_launch = getenv("FR_SHARD_ONE_LAUNCH") && atoi(getenv("FR_SHARD_ONE_LAUNCH")) != 0;
+  if (one_launch) {
+    if ((st = frk_shard_push_sync(e, d_idx, B_global, s->slot, parity, s->stream)) != FR_OK) return st;
+  } else {
+    if ((st = frk_gather_push(e, d_idx, B_global, s->slot, parity, s->stream)) != FR_OK) return st;
+    if ((st = frk_shard_signal_wait(e, s->slot, s->stream)) != FR_OK) return st;
+  }
   const int Bl = B_global / e->world;
   float* d_scores = is_device_ptr(scores) ? scores : s->d_scores;
   const float* x = e->d_xchg + fr_xchg_concat_off(e, s->slot, parity);

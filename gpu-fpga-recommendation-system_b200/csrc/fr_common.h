@@ -116,6 +116,7 @@ struct fr_engine {
   int n_slots = 0;               // in-flight sharded steps (one per worker stream), FR_SHARD_SLOTS
   int next_slot = 0;             // slot handed to the next stream created
   int* d_step = nullptr;         // [n_slots] device-side step counters (the flag kernel increments its slot's)
+  int* d_done = nullptr;         // [n_slots] blocks of the running exchange kernel that have finished their stores
   std::vector<FrPeer> peers;     // [world]
   float** d_peer_ptrs = nullptr; // device copy of peers[].concat
   int* d_owned_ids = nullptr;    // concat pieces this rank produces for every item
@@ -155,6 +156,8 @@ fr_status frk_gather(fr_engine* e, const int32_t* d_idx, int B, float* d_out, bo
 fr_status frk_gather_push(fr_engine* e, const int32_t* d_idx, int B_global, int slot, int parity, cudaStream_t st);
 // publish "this rank finished pushing the next step of `slot`" to every peer, then wait for all peers' flags
 fr_status frk_shard_signal_wait(fr_engine* e, int slot, cudaStream_t st);
+// push + replicated lookup + flags in one launch (the exchange of fr_shard_infer)
+fr_status frk_shard_push_sync(fr_engine* e, const int32_t* d_idx, int B_global, int slot, int parity, cudaStream_t st);
 
 // exchange-region geometry (floats): one slot = two concat buffers + a flag block
 inline size_t fr_xchg_buf_floats(const fr_engine* e) { return (size_t)(e->max_batch / e->world) * e->D; }

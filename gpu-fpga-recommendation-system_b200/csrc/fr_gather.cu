@@ -414,6 +414,121 @@ __global__ void shard_signal_wait_kernel(float* const* __restrict__ peer_base, l
 }
 }  // namespace
 
+// ---- the whole exchange of a sharded step in ONE launch ---------------------------------------
+// Blocks [0, g1): this rank's OWNED pieces for every item of the global batch, stored straight into
+// the concat buffer of the rank that owns the item (NVLink peer stores).  Blocks [g1, g1 + g2): the
+// REPLICATED (on-chip class) pieces for this rank's own items.  The block that finishes last (a
+// device-wide counter, the classic threadfence reduction) publishes "rank r pushed step n of this
+// slot" into every peer's flag block and waits until all peers have published n: the kernel does not
+// complete before every rank's rows have landed here, so the MLP simply follows it in the stream.
+// Against push + replicated lookup + flag kernel this is 4 launches per step instead of 6.
+namespace {
+template <bool ROUND, int DT>
+__global__ void __launch_bounds__(256)
+shard_push_sync_kernel(const FrChunk* __restrict__ chunks, const int* __restrict__ owned_ids, int n_owned,
+                       const int* __restrict__ repl_ids, int n_repl, const int32_t* __restrict__ idx, int T,
+                       int B_global, int per, int rank, int world, float4* const* __restrict__ peer_out, int C,
+                       long long peer_off4, int g1, int gx1, int gx2, float* const* __restrict__ peer_base,
+                       long long flags_off_floats, int* step_counter, int* done_counter, int* err,
+                       long long timeout_cycles) {
+  const int part = (int)blockIdx.x < g1 ? 0 : 1;
+  const int lb = part ? (int)blockIdx.x - g1 : (int)blockIdx.x;
+  const int gx = part ? gx2 : gx1;
+  const int n_chunks = part ? n_repl : n_owned;
+  const int* ids = part ? repl_ids : owned_ids;
+  const int b_end = part ? (rank + 1) * per : B_global;
+  const int ci = (lb % gx) * 32 + threadIdx.x;
+  const int b0 = (part ? rank * per : 0) + ((lb / gx) * 8 + threadIdx.y) * kItems;
+  if (ci < n_chunks) {
+    const int c = ids[ci];
+    const FrChunk ch = chunks[c];
+    int64_t row[kItems];
+#pragma unroll
+    for (int i = 0; i < kItems; i++) row[i] = (b0 + i < b_end) ? (int64_t)__ldg(idx + (size_t)(b0 + i) * T + ch.table) : 0;
+    float4 v[kItems];
+#pragma unroll
+    for (int i = 0; i < kItems; i++)
+      v[i] = DT == FR_TABLE_F32 ? ld_row16(ch.base + row[i] * ch.stride4 + ch.col4)
+                                : ld_row8<DT == FR_TABLE_F32 ? FR_TABLE_F16 : DT>(ch.base, row[i] * ch.stride4 + ch.col4);
+#pragma unroll
+    for (int i = 0; i < kItems; i++) {
+      const int b = b0 + i;
+      if (b >= b_end) break;
+      float4 o = v[i];
+      if (ROUND) {
+        o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+      }
+      const int r = part ? rank : b / per;
+      peer_out[r][peer_off4 + (size_t)(b - r * per) * C + c] = o;
+    }
+  }
+  // ---- last block out publishes and waits ----
+  __shared__ int s_last;
+  __syncthreads();                             // the block's stores are ordered before thread 0's fence (CTA barrier),
+  if (threadIdx.x == 0 && threadIdx.y == 0) {  // and the fence is cumulative: one system fence per block, not 256
+    __threadfence_system();
+    s_last = (atomicAdd(done_counter, 1) == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.y != 0) return;
+  __threadfence_system();                      // every other block's stores, ordered before their atomicAdd
+  const int t = threadIdx.x;
+  const int step = *step_counter + 1;          // launches of one slot are stream-ordered: no race
+  __syncwarp();
+  if (t == 0) {
+    *done_counter = 0;
+    *step_counter = step;
+  }
+  if (t < world) {
+    int* f = reinterpret_cast<int*>(peer_base[t] + flags_off_floats) + rank;
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f), "r"(step) : "memory");
+    const int* mine = reinterpret_cast<const int*>(peer_base[rank] + flags_off_floats) + t;
+    const long long t0 = clock64();
+    int v;
+    do {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if (v < step && clock64() - t0 > timeout_cycles) {
+        *reinterpret_cast<volatile int*>(err) = 1;   // surfaced by the next fr_shard_infer / fr_sync
+        break;
+      }
+    } while (v < step);
+  }
+}
+}  // namespace
+
+fr_status frk_shard_push_sync(fr_engine* e, const int32_t* d_idx, int B_global, int slot, int parity, cudaStream_t st) {
+  if (!e->shard_lists_built) {
+    std::lock_guard<std::mutex> g(e->mu);
+    if (!e->shard_lists_built) {
+      fr_status s = build_shard_lists(e);
+      if (s != FR_OK) return s;
+    }
+  }
+  const int per = B_global / e->world;
+  const int gx1 = (e->n_owned + 31) / 32, gy1 = e->n_owned ? (B_global + 8 * kItems - 1) / (8 * kItems) : 0;
+  const int gx2 = (e->n_repl + 31) / 32, gy2 = e->n_repl ? (per + 8 * kItems - 1) / (8 * kItems) : 0;
+  const int g1 = gx1 * gy1, g2 = gx2 * gy2;
+  if (g1 + g2 == 0) return fr_fail(e, FR_ERR_STATE, "this rank holds no table at all");
+  int* d_err = nullptr;
+  FR_CUDA(e, cudaHostGetDevicePointer(&d_err, e->h_shard_err, 0));
+  const bool round = (e->precision == FR_PREC_TF32);
+  auto kern = round ? (e->table_dtype == FR_TABLE_F32   ? shard_push_sync_kernel<true, FR_TABLE_F32>
+                       : e->table_dtype == FR_TABLE_F16 ? shard_push_sync_kernel<true, FR_TABLE_F16>
+                                                        : shard_push_sync_kernel<true, FR_TABLE_BF16>)
+                    : (e->table_dtype == FR_TABLE_F32   ? shard_push_sync_kernel<false, FR_TABLE_F32>
+                       : e->table_dtype == FR_TABLE_F16 ? shard_push_sync_kernel<false, FR_TABLE_F16>
+                                                        : shard_push_sync_kernel<false, FR_TABLE_BF16>);
+  kern<<<g1 + g2, dim3(32, 8), 0, st>>>(e->d_chunks, e->d_owned_ids, e->n_owned, e->d_repl_ids, e->n_repl, d_idx,
+                                        (int)e->tables.size(), B_global, per, e->rank, e->world,
+                                        reinterpret_cast<float4* const*>(e->d_peer_ptrs), e->D / 4,
+                                        (long long)(fr_xchg_concat_off(e, slot, parity) / 4), g1, gx1 ? gx1 : 1,
+                                        gx2 ? gx2 : 1, e->d_peer_ptrs, (long long)fr_xchg_flags_off(e, slot),
+                                        e->d_step + slot, e->d_done + slot, d_err, 20000000000ll /* ~10 s at 1.9 GHz */);
+  e->launches++;
+  FR_CUDA(e, cudaGetLastError());
+  return FR_OK;
+}
+
 fr_status frk_shard_signal_wait(fr_engine* e, int slot, cudaStream_t st) {
   int* d_err = nullptr;
   FR_CUDA(e, cudaHostGetDevicePointer(&d_err, e->h_shard_err, 0));
