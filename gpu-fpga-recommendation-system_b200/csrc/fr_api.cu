@@ -164,6 +164,7 @@ extern "C" fr_status fr_create(const fr_model_desc* desc, int n_gpus, const int*
   if (const char* env = getenv("FR_GRAPHS")) e->use_graphs = atoi(env) != 0;
   if (const char* env = getenv("FR_PDL")) e->pdl_mask = atoi(env) & 7;
   if (const char* env = getenv("FR_FUSE")) e->fuse_lookup = atoi(env) != 0;
+  if (const char* env = getenv("FR_ZEROCOPY")) e->zero_copy = atoi(env) != 0;
   e->tables.resize(desc->n_tables);
   for (int t = 0; t < desc->n_tables; t++) {
     e->tables[t].rows = desc->tables[t].rows;
@@ -388,6 +389,18 @@ static bool is_device_ptr(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// The device-side alias of a page-locked, mapped host buffer (cudaHostAlloc / cudaHostRegister under UVA),
+// null for pageable or device memory.
+static void* mapped_host_alias(const fr_engine* e, const void* p) {
+  if (!e->zero_copy || !p) return nullptr;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
 static fr_status prep(fr_engine* e, fr_stream* s, int B, bool need_tables, bool need_mlp) {
   if (!e) return fr_fail(nullptr, FR_ERR_INVALID, "null engine");
   if (B < 0 || B > e->max_batch) return fr_fail(e, FR_ERR_INVALID, "B=%d outside [0, max_batch=%d]", B, e->max_batch);
@@ -422,10 +435,24 @@ static fr_status stage_idx(fr_engine* e, fr_stream_s* s, const int32_t* idx, int
     *d_idx = idx;
     return FR_OK;
   }
-  FR_CUDA(e, cudaMemcpyAsync(s->d_idx, idx, (size_t)B * e->tables.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
-                             s->stream));
+  const size_t bytes = (size_t)B * e->tables.size() * sizeof(int32_t);
   *d_idx = s->d_idx;
+  // page-locked caller buffer: the SMs fetch it (no copy-engine node); pageable: the driver's staged copy
+  const void* alias = mapped_host_alias(e, idx);
+  if (alias && bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(alias) & 15) == 0)
+    return frk_stage_idx(e, alias, s->d_idx, bytes, s->stream);
+  FR_CUDA(e, cudaMemcpyAsync(s->d_idx, idx, bytes, cudaMemcpyHostToDevice, s->stream));
   return FR_OK;
+}
+
+// Where the last MLP kernel writes the scores: the caller's buffer when the device can address it (device
+// memory, or page-locked host memory written over PCIe by the epilogue itself), else the worker's buffer,
+// which emit_scores() then copies out.
+static float* score_target(const fr_engine* e, fr_stream_s* s, float* scores, int B) {
+  if (B <= 0 || !scores) return s->d_scores;
+  if (is_device_ptr(scores)) return scores;
+  void* alias = mapped_host_alias(e, scores);
+  return alias ? static_cast<float*>(alias) : s->d_scores;
 }
 
 // Launch `step` of the MLP chain on a worker stream (cuda_server.c:468-491).  TF32: 3 launches
@@ -450,6 +477,7 @@ static fr_status run_mlp_step(fr_engine* e, fr_stream_s* s, int step, const floa
 
 static fr_status run_mlp(fr_engine* e, fr_stream_s* s, const float* d_x, int B, float* d_scores) {
   if (B == 0) return FR_OK;
+  if (frtc_can_chain(e, B)) return frtc_chain(e, s, d_x, B, d_scores);   // all layers in one persistent launch
   const float* in = d_x;
   for (int k = 0; k < mlp_steps(e); k++) {
     const float* out = nullptr;
@@ -461,7 +489,7 @@ static fr_status run_mlp(fr_engine* e, fr_stream_s* s, const float* d_x, int B, 
 }
 
 static fr_status emit_scores(fr_engine* e, fr_stream_s* s, float* scores, int B, float* d_scores) {
-  if (d_scores != scores && B > 0)
+  if (d_scores == s->d_scores && d_scores != scores && B > 0)
     FR_CUDA(e, cudaMemcpyAsync(scores, d_scores, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
   return FR_OK;
 }
@@ -471,7 +499,7 @@ static fr_status infer_enqueue(fr_engine* e, fr_stream_s* s, const int32_t* idx,
   const int32_t* d_idx = nullptr;
   fr_status st = stage_idx(e, s, idx, B, &d_idx);
   if (st != FR_OK) return st;
-  float* d_scores = (B > 0 && is_device_ptr(scores)) ? scores : s->d_scores;
+  float* d_scores = score_target(e, s, scores, B);
   if (B > 0 && frtc_can_fuse(e)) {
     // lookup fused into layer 1: the concat vectors never exist in global memory (3 launches)
     if ((st = frtc_fused_layer1(e, s, d_idx, B)) != FR_OK) return st;
@@ -592,7 +620,7 @@ extern "C" fr_status fr_mlp_only(fr_engine* e, const float* x, int B, float* sco
     FR_CUDA(e, cudaMemcpyAsync(s->d_x, x, (size_t)B * e->D * sizeof(float), cudaMemcpyHostToDevice, s->stream));
     d_x = s->d_x;
   }
-  float* d_scores = is_device_ptr(scores) ? scores : s->d_scores;
+  float* d_scores = score_target(e, s, scores, B);
   if ((st = run_mlp(e, s, d_x, B, d_scores)) != FR_OK) return st;
   return emit_scores(e, s, scores, B, d_scores);
 }
@@ -687,6 +715,16 @@ extern "C" fr_status fr_time_kernels(fr_engine* e, const int32_t* idx, int B, in
     } else {
       // sharded: the lookup needs every rank; time the MLP on this worker's last exchanged batch
       in = e->d_xchg + fr_xchg_concat_off(e, s->slot < e->n_slots ? s->slot : 0, s->shard_step & 1);
+    }
+    if (!fused && frtc_can_chain(e, B)) {
+      // the MLP of this batch size is ONE launch: slot 1 carries it, slots 2..4 stay 0
+      FR_CUDA(e, cudaEventRecord(e0, s->stream));
+      for (int r = 0; r < reps; r++)
+        if ((st = frtc_chain(e, s, in, B, s->d_scores)) != FR_OK) return st;
+      FR_CUDA(e, cudaEventRecord(e1, s->stream));
+      FR_CUDA(e, cudaEventSynchronize(e1));
+      FR_CUDA(e, cudaEventElapsedTime(&ms5[1], e0, e1));
+      continue;
     }
     for (int k = fused ? 1 : 0; k < mlp_steps(e); k++) {
       const float* out = nullptr;
@@ -868,7 +906,7 @@ static fr_status shard_infer_enqueue(fr_engine* e, fr_stream_s* s, const int32_t
     if ((st = frk_shard_signal_wait(e, s->slot, s->stream)) != FR_OK) return st;
   }
   const int Bl = B_global / e->world;
-  float* d_scores = is_device_ptr(scores) ? scores : s->d_scores;
+  float* d_scores = score_target(e, s, scores, Bl);
   const float* x = e->d_xchg + fr_xchg_concat_off(e, s->slot, parity);
   if ((st = run_mlp(e, s, x, Bl, d_scores)) != FR_OK) return st;
   return emit_scores(e, s, scores, Bl, d_scores);

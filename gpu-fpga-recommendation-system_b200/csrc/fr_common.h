@@ -88,6 +88,12 @@ struct fr_engine {
   // deadlocked on the device intermittently on B200 / driver 580 (bit 0: 8 of 12 runs; mask 6: 1 of ~12),
   // never without them; with 8 workers in flight the edges buy <= 2% anyway (10% with 4 workers).
   int pdl_mask = 0;
+  // FR_ZEROCOPY=1: page-locked (mapped) caller buffers are read / written by the kernels themselves over
+  // PCIe instead of through memcpy nodes -- indices by a staging kernel, scores by the last MLP kernel.
+  // Off by default: measured slower than the copy engine on B200 (small model, batch 2048, 12 workers:
+  // 13.1 against 12.3 us per step end to end; both are bound by moving 385 KB of indices per step over PCIe,
+  // ~31 GB/s), although it takes 1.6 us of host enqueue time off every step.
+  bool zero_copy = false;
 
   std::vector<FrTable> tables;
   FrChunk* d_chunks = nullptr;  // [D/4]
@@ -153,6 +159,8 @@ inline cudaError_t fr_h2d(fr_engine* e, void* dst, const void* src, size_t bytes
 // ---- kernels (each returns after enqueueing; bumps e->launches) -----------
 fr_status frk_upload_chunks(fr_engine* e);
 fr_status frk_gather(fr_engine* e, const int32_t* d_idx, int B, float* d_out, bool round_tf32, cudaStream_t st);
+// copy `bytes` (a multiple of 16) of indices from a mapped page-locked host buffer into device memory with SM loads
+fr_status frk_stage_idx(fr_engine* e, const void* mapped_src, int32_t* d_dst, size_t bytes, cudaStream_t st);
 fr_status frk_gather_push(fr_engine* e, const int32_t* d_idx, int B_global, int slot, int parity, cudaStream_t st);
 // publish "this rank finished pushing the next step of `slot`" to every peer, then wait for all peers' flags
 fr_status frk_shard_signal_wait(fr_engine* e, int slot, cudaStream_t st);
@@ -190,6 +198,9 @@ fr_status frk_final_dot(fr_engine* e, const float* H, const float* w, const floa
 fr_status frtc_prepare(fr_engine* e);                // builds tensor maps for weights; idempotent
 void frtc_destroy(fr_engine* e);
 fr_status frtc_layer(fr_engine* e, fr_stream_s* s, int k, const float* in, int B, float* d_scores);
+// the whole MLP (3 GEMMs + output layer) as ONE persistent launch: in [B][dims[0]] -> d_scores [B]; uses s->d_h[0..1]
+bool frtc_can_chain(const fr_engine* e, int B);
+fr_status frtc_chain(fr_engine* e, fr_stream_s* s, const float* in, int B, float* d_scores);
 // lookup fused into layer 1: d_idx [B][T] -> s->d_h[0]; frtc_can_fuse() says whether this engine's shapes allow it
 bool frtc_can_fuse(const fr_engine* e);
 fr_status frtc_fused_layer1(fr_engine* e, fr_stream_s* s, const int32_t* d_idx, int B);

@@ -259,6 +259,26 @@ fr_status frk_gather(fr_engine* e, const int32_t* d_idx, int B, float* d_out, bo
   return FR_OK;
 }
 
+// Index staging without the copy engine (replaces the read() + cudaMemcpyAsync of cuda_server.c:425-461 for
+// page-locked caller buffers): the SMs read the caller's mapped host buffer over PCIe with 16-byte loads,
+// every element exactly once, one load per thread so the whole batch is one round trip deep, and write it to
+// the worker's device index buffer.  A memcpy node costs the copy engine ~2-3 us of set-up per batch and the
+// batches of all workers queue on that one engine; kernels of different workers overlap.
+// ld.cv: the same host buffer carries new indices on every replay -- never serve it from a cache.
+__global__ void stage_idx_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n16) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = __ldcv(src + i);
+}
+
+fr_status frk_stage_idx(fr_engine* e, const void* mapped_src, int32_t* d_dst, size_t bytes, cudaStream_t st) {
+  const int n16 = (int)(bytes / 16);
+  int blocks = (n16 + 255) / 256;
+  if (blocks > 8 * e->sm_count) blocks = 8 * e->sm_count;
+  stage_idx_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(mapped_src), reinterpret_cast<uint4*>(d_dst), n16);
+  e->launches++;
+  FR_CUDA(e, cudaGetLastError());
+  return FR_OK;
+}
+
 fr_status frk_fill_reference(fr_engine* e, float* d, int64_t rows, int dim, int64_t debug_rows, cudaStream_t st) {
   // host.cpp:66-88: pairs (2i, 2i+1) for i < rows/2 (or < debug_rows/2 with DEBUG)
   int64_t pairs = rows / 2;

@@ -171,10 +171,74 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// fp32 -> tf32, round to nearest with ties away from zero (what cvt.rna.tf32.f32 computes for finite
+// values): add half an ulp of the 10-bit mantissa to the magnitude and clear the 13 low bits.  Two
+// full-rate integer instructions; the cvt runs at 16 / clk / SM, which made it the largest single cost
+// of the store epilogue (128 x 512 conversions per tile).
 __device__ __forceinline__ float round_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
+// Explicit shared-space accesses.  The dynamic smem base is aligned through an integer cast, after which
+// the compiler no longer knows the pointers are shared: it emitted generic LD.E / ST.E and, unable to
+// prove the bias loads independent of the staging stores, serialised them (load, wait, 4 FADDs, store,
+// next load ...: ~720 cycles per 32-column chunk).  These keep the accesses LDS / STS, and the callers
+// issue all loads of a chunk before its stores.
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// One epilogue chunk of the storing layers: 32 accumulator columns of this thread's row + bias -> ReLU ->
+// TF32 rounding -> this warp's 128B-swizzled 4 KB staging buffer (16-byte piece j of row `lane` lives at
+// piece j ^ (lane & 7), the layout the TMA store box expects).  bias_addr / buf_addr: shared-space addresses.
+__device__ __forceinline__ void epi_chunk_to_smem(const uint32_t (&r)[32], uint32_t bias_addr, uint32_t buf_addr,
+                                                  int lane, int relu) {
+  float4 bv[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) bv[j] = lds128(bias_addr + j * 16);
+  const uint32_t row = buf_addr + lane * 128;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    float4 o;
+    o.x = __uint_as_float(r[4 * j + 0]) + bv[j].x;
+    o.y = __uint_as_float(r[4 * j + 1]) + bv[j].y;
+    o.z = __uint_as_float(r[4 * j + 2]) + bv[j].z;
+    o.w = __uint_as_float(r[4 * j + 3]) + bv[j].w;
+    if (relu) {
+      o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+    }
+    o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+    sts128(row + ((j ^ (lane & 7)) << 4), o);
+  }
+}
+
+// One epilogue chunk of layer 3: dot += sum_j act(acc[j] + bias[j]) * w4[j] over 32 columns, in column order.
+__device__ __forceinline__ float epi_chunk_dot(const uint32_t (&r)[32], uint32_t bias_addr, uint32_t w4_addr, int relu,
+                                               float dot) {
+  float4 bv[8], wv[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    bv[j] = lds128(bias_addr + j * 16);
+    wv[j] = lds128(w4_addr + j * 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    float v0 = __uint_as_float(r[4 * j + 0]) + bv[j].x, v1 = __uint_as_float(r[4 * j + 1]) + bv[j].y;
+    float v2 = __uint_as_float(r[4 * j + 2]) + bv[j].z, v3 = __uint_as_float(r[4 * j + 3]) + bv[j].w;
+    if (relu) {
+      v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
+    }
+    dot = fmaf(v0, wv[j].x, dot);
+    dot = fmaf(v1, wv[j].y, dot);
+    dot = fmaf(v2, wv[j].z, dot);
+    dot = fmaf(v3, wv[j].w, dot);
+  }
+  return dot;
 }
 
 // K-major, 128B-swizzled operand tile: rows are 128 bytes, 8-row groups are 1024 bytes
@@ -473,21 +537,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint8_t* buf = store_buf + (sc & 1) * kStoreBufBytes;
           if (lane == 0) bulk_wait_read<1>();   // the store issued two chunks ago no longer reads `buf`
           __syncwarp();
-          const float* bs = s_bias + n0 + c;
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            float4 o;
-            o.x = __uint_as_float(r[4 * j + 0]) + bs[4 * j + 0];
-            o.y = __uint_as_float(r[4 * j + 1]) + bs[4 * j + 1];
-            o.z = __uint_as_float(r[4 * j + 2]) + bs[4 * j + 2];
-            o.w = __uint_as_float(r[4 * j + 3]) + bs[4 * j + 3];
-            if (p.relu) {
-              o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-            }
-            o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
-            // 128B swizzle: 16-byte chunk j of row `lane` lives at chunk j ^ (lane & 7)
-            *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
-          }
+          epi_chunk_to_smem(r, smem_u32(s_bias + n0 + c), smem_u32(buf), lane, p.relu);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0 && row0 < p.M) {   // rows past M inside the box are clipped by the TMA unit
@@ -496,12 +546,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           sc++;
         } else {
-#pragma unroll
-          for (int j = 0; j < 32; j++) {
-            float v = __uint_as_float(r[j]) + s_bias[c + j];
-            if (p.relu) v = fmaxf(v, 0.f);
-            dot = fmaf(v, s_w4[c + j], dot);
-          }
+          dot = epi_chunk_dot(r, smem_u32(s_bias + c), smem_u32(s_w4 + c), p.relu, dot);
         }
       }
       // this warp's quarter of the accumulator stage has been read: hand it back to the MMA issuer
@@ -522,6 +567,300 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tc_fence_after();
     if (CTAS == 2) tmem_dealloc_pair(tmem_base, L::kTmemCols);
     else tmem_dealloc(tmem_base, L::kTmemCols);
+  }
+}
+
+// ---- the whole MLP in one persistent launch ---------------------------------------
+// tc_linear_kernel pays its fixed cost (TMEM allocation, barrier set-up, pipeline fill, the last
+// epilogue, teardown: ~6 us) once per layer, and at batch 2048 a layer is only 8..32 tiles: a third
+// to a half of every launch is that fixed cost (small model, 12 batches in flight: 47 % of the TF32
+// peak for the whole step).  Here a CTA pair owns 256 ITEMS and walks them through all the layers
+// (cuda_server.c:468-491, the four cublasLtMatmul calls, become the phases of one kernel):
+//   layer 1   N1/512 phases   D[256 x 512] = X[256 x K0] . Wt1[chunk]^T    -> H1 (tf32-rounded, TMA store)
+//   layer 2   N2/512 phases   D[256 x 512] = H1[256 x N1] . Wt2[chunk]^T   -> H2
+//   layer 3   1 phase         D[256 x 256] = H2 . Wt3^T, output layer + sigmoid folded -> score
+// The accumulator is ONE TMEM stage of 512 columns (two N = 256 MMAs per K step sharing the A slice,
+// 33 B/clk/SM of operand fill), drained by EIGHT epilogue warps (two per TMEM lane quarter, half the
+// columns each).  H1 / H2 make a round trip through global memory (L2-resident: 1 MB + 0.5 MB per
+// pair) because 128 rows x 1024 fp32 do not fit an SM; the rows a CTA stores are the rows the same
+// CTA loads again, so the dependency is CTA-local: an epilogue warp waits for its bulk stores to
+// COMPLETE (cp.async.bulk.wait_group, not .read) and arrives on ready[layer][chunk]; the producer
+// waits on that barrier only before the first K slice that reads the chunk.  Weight slices never
+// wait: the producer runs ahead into the next phase while the epilogue drains, and layer 2's first
+// 16 K slices read the H1 chunk that was stored one phase earlier, so the only exposed gaps are the
+// TMEM hand-overs (~1 us each) and the H2 turn-around before layer 3.
+constexpr int kChainThreads = 320;     // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
+constexpr int kChainEpiWarps = 8;
+constexpr int kChainMaxBias = 3072;    // N1 + N2 + N3 floats staged in smem (large model: 2048 + 512 + 256)
+constexpr int kChainMaxChunks = 4;     // 512-wide chunks of the widest storing layer (2048)
+constexpr int kChainW = 512;           // phase width of the storing layers
+
+template <int STAGES>
+struct ChainLayout {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 4;          // 16 KB: this CTA's 128 items x 32 floats
+  static constexpr int kBSubBytes = 128 * BLOCK_K * 4;           // 16 KB: this CTA's 128 rows of Wt for one N = 256 MMA
+  static constexpr int kStageBytes = kABytes + 2 * kBSubBytes;   // 48 KB
+  static constexpr int kStoreOff = STAGES * kStageBytes;
+  static constexpr int kAuxOff = kStoreOff + kChainEpiWarps * 2 * kStoreBufBytes;   // bias[kChainMaxBias], w4[256]
+  static constexpr int kBarOff = kAuxOff + (kChainMaxBias + 256) * 4;
+  static constexpr int kNumBars = 2 * STAGES + 2 + 2 * kChainMaxChunks;   // full, empty, tmem_full, tmem_empty, ready[2][4]
+  static constexpr int kTotal = kBarOff + kNumBars * 8 + 16;
+  static constexpr int kDyn = kTotal + 1024;
+};
+
+struct ChainMaps {
+  CUtensorMap a[3];   // X, H1, H2 as A operands: 128-row x 32-float boxes
+  CUtensorMap o[2];   // H1, H2 as store targets: 32-row x 32-float boxes
+  CUtensorMap w[3];   // Wt1, Wt2, Wt3: 128-row boxes (one CTA's half of an N = 256 MMA)
+};
+
+struct ChainParams {
+  const float* bias[3];   // null in LINEAR mode
+  const float* w4;        // output-layer weights [256]
+  const float* b4;        // output-layer bias [1] or null
+  float* out;             // scores [M]
+  int M;
+  int dims[4];            // K0, N1, N2, N3 (= 256)
+  int relu, sigmoid;
+  long long* prof;        // FR_CHAIN_PROF=1: clock64 stamps of CTA 0's first item tiles (kProf* below), else null
+};
+
+// timeline of CTA 0: prof[((item tile iteration * kProfPhases) + phase) * kProfSlots + slot]
+constexpr int kProfIters = 4, kProfPhases = 8, kProfSlots = 8;
+enum { PROF_MMA_TMEM_FREE = 0, PROF_MMA_FIRST_FULL, PROF_MMA_LAST_ISSUED, PROF_EPI_FULL_SEEN, PROF_EPI_TMEM_RELEASED,
+       PROF_EPI_STORES_DONE, PROF_PROD_READY_WAIT, PROF_PROD_READY_OK };
+__device__ __forceinline__ void prof_stamp(long long* prof, uint32_t it, int ph, int slot) {
+  if (prof && it < (uint32_t)kProfIters && ph < kProfPhases) prof[((int)it * kProfPhases + ph) * kProfSlots + slot] = clock64();
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(kChainThreads, 1)
+tc_mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
+  using L = ChainLayout<STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* s_bias = reinterpret_cast<float*>(smem + L::kAuxOff);
+  float* s_w4 = s_bias + kChainMaxBias;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 1;
+  uint64_t* ready_bar = tmem_empty_bar + 1;          // [2][kChainMaxChunks]: chunk c of layer l's output is in global memory
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ready_bar + 2 * kChainMaxChunks);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int n_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);   // item tiles of 256
+  const int cluster_id = blockIdx.x / 2, n_clusters = gridDim.x / 2;
+  long long* const prof = (blockIdx.x == 0 && lane == 0) ? p.prof : nullptr;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 3; i++) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[i]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w[i]) : "memory");
+      if (i < 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.o[i]) : "memory");
+    }
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full_bar[s], 1);    // the leader's producer arrives once; bytes of both CTAs are expected
+      mbar_init(&empty_bar[s], 1);   // one multicast tcgen05.commit per use
+    }
+    mbar_init(tmem_full_bar, 1);                        // one multicast tcgen05.commit per phase
+    mbar_init(tmem_empty_bar, 2 * kChainEpiWarps);      // every epilogue warp of both CTAs
+    for (int i = 0; i < 2 * kChainMaxChunks; i++) mbar_init(&ready_bar[i], kChainEpiWarps);   // this CTA's epilogue warps
+    fence_barrier_init();
+  } else if (warp == 1) {
+    tmem_alloc_pair(tmem_ptr, 512);
+  } else if (warp >= kEpiWarp0) {
+    const int et = threadIdx.x - kEpiWarp0 * 32;   // 0..255
+    int off = 0;
+    for (int l = 0; l < 3; l++) {
+      const int N = p.dims[l + 1];
+      for (int i = et; i < N; i += kChainEpiWarps * 32) s_bias[off + i] = p.bias[l] ? p.bias[l][i] : 0.f;
+      off += N;
+    }
+    for (int i = et; i < 256; i += kChainEpiWarps * 32) s_w4[i] = p.w4[i];
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): weights run ahead, activations wait for their chunk =====
+    if (lane == 0) {
+      const uint32_t bar0 = mapa_u32(smem_u32(&full_bar[0]), 0);   // the leader's full barriers
+      uint32_t kc = 0, it = 0;
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
+        const int m0 = (tile * 2 + (int)rank) * BLOCK_M;
+        int ph = 0;
+        for (int l = 0; l < 3; l++) {
+          const int num_kb = (p.dims[l] + BLOCK_K - 1) / BLOCK_K;
+          const int width = l < 2 ? kChainW : 256;
+          const int nsub = width / 256;
+          const int n_chunks = p.dims[l + 1] / width;
+          int ready_upto = 0;   // chunks of layer l-1's output known to be in global memory (this item tile)
+          for (int c = 0; c < n_chunks; c++, ph++) {
+            const int nb0 = c * width + (int)rank * 128;
+            for (int kb = 0; kb < num_kb; kb++, kc++) {
+              const int s = kc % STAGES;
+              mbar_wait(&empty_bar[s], ((kc / STAGES) & 1) ^ 1, 1, kc, tile);
+              uint8_t* a_dst = smem + s * L::kStageBytes;
+              uint8_t* b_dst = a_dst + L::kABytes;
+              const uint32_t bar = bar0 + s * 8;
+              if (leader) mbar_expect_tx(&full_bar[s], 2 * (L::kABytes + nsub * L::kBSubBytes));
+              for (int h = 0; h < nsub; h++)
+                tma_load_2d_pair(&maps.w[l], bar, b_dst + h * L::kBSubBytes, kb * BLOCK_K, nb0 + h * 256);
+              if (l > 0) {
+                const int need = (kb * BLOCK_K) / kChainW;   // chunk of the previous layer this K slice reads
+                while (ready_upto <= need) {
+                  prof_stamp(prof, it, ph, PROF_PROD_READY_WAIT);
+                  mbar_wait(&ready_bar[(l - 1) * kChainMaxChunks + ready_upto], it & 1, 6, kc, tile);
+                  prof_stamp(prof, it, ph, PROF_PROD_READY_OK);
+                  ready_upto++;
+                }
+                // the rows were written by this CTA's bulk stores (async proxy) and ordered before us by
+                // generic-proxy barrier operations: order our async-proxy reads after those
+                asm volatile("fence.proxy.async;" ::: "memory");
+              }
+              tma_load_2d_pair(&maps.a[l], bar, a_dst, kb * BLOCK_K, m0);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA) =====
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_tf32_m(2 * BLOCK_M, 256);
+      uint32_t kc = 0, pc = 0, it = 0;   // K slices consumed, phases started, item tiles started
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
+        int ph = 0;
+        for (int l = 0; l < 3; l++) {
+          const int num_kb = (p.dims[l] + BLOCK_K - 1) / BLOCK_K;
+          const int width = l < 2 ? kChainW : 256;
+          const int nsub = width / 256;
+          const int n_chunks = p.dims[l + 1] / width;
+          for (int c = 0; c < n_chunks; c++, pc++, ph++) {
+            mbar_wait(tmem_empty_bar, (pc & 1) ^ 1, 2, kc, tile);   // the epilogue has drained the accumulator
+            tc_fence_after();
+            prof_stamp(prof, it, ph, PROF_MMA_TMEM_FREE);
+            for (int kb = 0; kb < num_kb; kb++, kc++) {
+              const int s = kc % STAGES;
+              mbar_wait(&full_bar[s], (kc / STAGES) & 1, 3, kc, tile);
+              tc_fence_after();
+              if (kb == 0) prof_stamp(prof, it, ph, PROF_MMA_FIRST_FULL);
+              if (elect_one()) {
+                const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+                const uint64_t a_desc = make_smem_desc(a_addr);
+                const uint64_t b_desc = make_smem_desc(a_addr + L::kABytes);
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+                  umma_tf32_pair(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                  if (nsub == 2)
+                    umma_tf32_pair(tmem_base + 256, a_desc + (uint64_t)(k * 2),
+                                   b_desc + (uint64_t)(k * 2) + (uint64_t)(L::kBSubBytes >> 4), idesc, (kb | k) != 0);
+                }
+                umma_commit_pair(&empty_bar[s]);
+                if (kb == num_kb - 1) umma_commit_pair(tmem_full_bar);
+              }
+              __syncwarp();
+            }
+            prof_stamp(prof, it, ph, PROF_MMA_LAST_ISSUED);
+          }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+    const int q = warp % 4, half = (warp - kEpiWarp0) / 4;
+    uint8_t* store_buf = smem + L::kStoreOff + (warp - kEpiWarp0) * 2 * kStoreBufBytes;
+    const uint32_t empty_remote = mapa_u32(smem_u32(tmem_empty_bar), 0);   // the leader's
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t pc = 0, sc = 0, it = 0;
+    long long* const eprof = (warp == kEpiWarp0) ? prof : nullptr;   // one epilogue warp keeps the timeline
+    for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
+      const int row0 = (tile * 2 + (int)rank) * BLOCK_M + q * 32;
+      int boff = 0, ph = 0;
+      for (int l = 0; l < 2; l++) {
+        const int n_chunks = p.dims[l + 1] / kChainW;
+        for (int c = 0; c < n_chunks; c++, pc++, ph++) {
+          mbar_wait(tmem_full_bar, pc & 1, 4, pc, tile);
+          tc_fence_after();
+          prof_stamp(eprof, it, ph, PROF_EPI_FULL_SEEN);
+          long long t_ld = 0, t_wr = 0, t_st = 0, t_fe = 0, t_is = 0;   // FR_CHAIN_PROF: where this warp's epilogue time goes
+#pragma unroll 1
+          for (int cc = half * 256; cc < half * 256 + 256; cc += 32) {
+            uint32_t r[32];
+            const long long c0 = eprof ? clock64() : 0;
+            tmem_ld32(taddr + cc, r);
+            const long long c1 = eprof ? clock64() : 0;
+            uint8_t* buf = store_buf + (sc & 1) * kStoreBufBytes;
+            if (lane == 0) bulk_wait_read<1>();   // the store issued two chunks ago no longer reads `buf`
+            __syncwarp();
+            const long long c2 = eprof ? clock64() : 0;
+            epi_chunk_to_smem(r, smem_u32(s_bias + boff + c * kChainW + cc), smem_u32(buf), lane, p.relu);
+            const long long c2b = eprof ? clock64() : 0;
+            fence_proxy_async();
+            __syncwarp();
+            const long long c3 = eprof ? clock64() : 0;
+            if (lane == 0 && row0 < p.M) {
+              tma_store_2d(&maps.o[l], buf, c * kChainW + cc, row0);
+              bulk_commit();
+            }
+            sc++;
+            if (eprof) {
+              t_ld += c1 - c0; t_wr += c2 - c1; t_st += c2b - c2; t_fe += c3 - c2b; t_is += clock64() - c3;
+            }
+          }
+          if (eprof && it == 0 && ph < 4) {   // rows 4..7 of iteration 0 carry the breakdown of phases 0..3
+            long long* a = eprof + (4 + ph) * kProfSlots;
+            a[0] = t_ld; a[1] = t_wr; a[2] = t_st; a[3] = t_is; a[4] = t_fe;
+          }
+          // accumulator read: hand TMEM back first, then wait for this warp's rows to be in global memory
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_cluster(empty_remote);
+            prof_stamp(eprof, it, ph, PROF_EPI_TMEM_RELEASED);
+            bulk_wait_all<0>();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ready_bar[l * kChainMaxChunks + c])) : "memory");
+            prof_stamp(eprof, it, ph, PROF_EPI_STORES_DONE);
+          }
+        }
+        boff += p.dims[l + 1];
+      }
+      // layer 3: the 256-wide row stays in TMEM; output layer + sigmoid folded (warps of column half 0)
+      mbar_wait(tmem_full_bar, pc & 1, 4, pc, tile);
+      tc_fence_after();
+      prof_stamp(eprof, it, ph, PROF_EPI_FULL_SEEN);
+      float dot = 0.f;
+      if (half == 0) {
+#pragma unroll 1
+        for (int cc = 0; cc < 256; cc += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + cc, r);
+          dot = epi_chunk_dot(r, smem_u32(s_bias + boff + cc), smem_u32(s_w4 + cc), p.relu, dot);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(empty_remote);
+      prof_stamp(eprof, it, ph, PROF_EPI_TMEM_RELEASED);
+      if (half == 0 && row0 + lane < p.M) {
+        if (p.b4) dot += p.b4[0];
+        p.out[row0 + lane] = p.sigmoid ? 1.f / (1.f + __expf(-dot)) : dot;
+      }
+      pc++;
+    }
+    tc_fence_before();
+  }
+  cluster_sync_all();   // the peer's smem / TMEM must stay alive until the pair is done
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
   }
 }
 
@@ -682,20 +1021,7 @@ tc_gather_linear_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid
         uint8_t* buf = store_buf + (sc & 1) * kStoreBufBytes;
         if (lane == 0) bulk_wait_read<1>();
         __syncwarp();
-        const float* bs = s_bias + n0 + c;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-          float4 o;
-          o.x = __uint_as_float(r[4 * j + 0]) + bs[4 * j + 0];
-          o.y = __uint_as_float(r[4 * j + 1]) + bs[4 * j + 1];
-          o.z = __uint_as_float(r[4 * j + 2]) + bs[4 * j + 2];
-          o.w = __uint_as_float(r[4 * j + 3]) + bs[4 * j + 3];
-          if (p.relu) {
-            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-          }
-          o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
-          *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
-        }
+        epi_chunk_to_smem(r, smem_u32(s_bias + n0 + c), smem_u32(buf), lane, p.relu);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0 && row0 < p.M) {
@@ -806,6 +1132,13 @@ struct TcState {
   CUtensorMap w_map[3];
   CUtensorMap w_fuse_map;   // layer-1 weights in 128-row boxes, for the fused lookup + layer 1 kernel
   CUtensorMap w_map64[2];   // layers 1, 2 in 64-row boxes: 128-wide pair tiles (automatic choice for small batches)
+  CUtensorMap w_map128[3];  // every layer in 128-row boxes: the one-launch chain (a CTA's half of an N = 256 MMA)
+  // FR_CHAIN=1: the whole MLP as one launch where the chain kernel applies.  Off by default: parity-green
+  // (bit-identical to the per-layer kernels) but slower -- with ONE 512-column TMEM stage every epilogue is
+  // exposed (3 x 5 us + 1 us per 256-item tile) and the TMA unit, which sustains ~33 B/clk/SM here, carries
+  // the stores and the next phase's prefetch in that window: 65 us per tile, 192 against 223 M inferences/s.
+  bool chain = false;
+  long long* d_prof = nullptr;   // FR_CHAIN_PROF=1: the chain kernel's CTA 0 writes its phase timeline here
   TcLayerCfg cfg[3];
   bool ready = false;
   // cached activation maps keyed by (pointer, K, rows, box rows): 128-row boxes feed the A operand,
@@ -824,8 +1157,12 @@ fr_status encode_2d(fr_engine* e, TcState* st, CUtensorMap* map, const void* bas
   const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
   const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
+  static const int promo = getenv("FR_TMA_L2PROMO") ? atoi(getenv("FR_TMA_L2PROMO")) : 3;   // experiment knob
+  const CUtensorMapL2promotion l2p = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                     : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                     : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   CUresult r = st->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fr_fail(e, FR_ERR_CUDA, "cuTensorMapEncodeTiled(rows=%d K=%d box=%d) failed: CUresult %d", rows, K, box_rows,
@@ -836,9 +1173,10 @@ fr_status encode_2d(fr_engine* e, TcState* st, CUtensorMap* map, const void* bas
 int g_max_clusters = 0;   // FR_TC_MAX_CLUSTERS: cap the persistent grid (tests force several tiles per cluster)
 // A cluster's fixed cost (pipeline fill, last epilogue, teardown: ~4 us) is only hidden behind further
 // tiles, so short tiles are ganged: every cluster gets at least this many K-slices of main loop
-// (FR_TC_MIN_KB; small model layer 1 has 11 per tile -> two tiles per cluster, +10% batches/s with 8
-// workers in flight, at +5 us latency of that layer).
-int g_min_kb = 16;
+// (FR_TC_MIN_KB; small model layer 1 has 11 per tile -> three tiles per cluster, layer 3 has 16 -> two).
+// Measured with 12 workers in flight, small model, batch 2048: 16 -> 214, 32 -> 223, 48 -> 212, 64 -> 201 M
+// inferences/s (a longer gang leaves too few clusters per launch to keep 148 SMs busy).
+int g_min_kb = 32;
 
 template <int BLOCK_N, int STAGES, int EPI, int CTAS>
 fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const TcParams& p,
@@ -922,12 +1260,13 @@ bool parse_tiles(TcLayerCfg cfg[3]) {
 // -- so they take 128-wide tiles, un-ganged: 2-4x more clusters, each with a quarter of the MMAs
 // (medium model, batch 1: 77 -> ~45 us per fr_infer).
 constexpr int kLatencyBatch = 512;
+constexpr int kWideMinKb = 16;   // K slices from which a 512-wide single-stage tile beats two 256-wide ones
 int pick_block_n(const fr_engine* e, int k, int B) {
   const int N = e->dims[k + 1], K = e->dims[k];
   if (B <= kLatencyBatch) return 128;
   const int tiles256 = (B + 2 * BLOCK_M - 1) / (2 * BLOCK_M) * (N / 256);
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
-  if (N % 512 == 0 && num_kb >= g_min_kb && tiles256 < e->sm_count / 2) return 512;
+  if (N % 512 == 0 && num_kb >= kWideMinKb && tiles256 < e->sm_count / 2) return 512;
   return 256;
 }
 
@@ -984,12 +1323,31 @@ fr_status frtc_prepare(fr_engine* e) {
     if (s != FR_OK) return s;
     for (int k = 0; k < 2; k++)
       if ((s = encode_2d(e, st, &st->w_map64[k], e->d_Wt[k], e->dims[k + 1], e->dims[k], 64)) != FR_OK) return s;
+    for (int k = 0; k < 3; k++)
+      if ((s = encode_2d(e, st, &st->w_map128[k], e->d_Wt[k], e->dims[k + 1], e->dims[k], 128)) != FR_OK) return s;
+    if (const char* env = getenv("FR_CHAIN")) st->chain = atoi(env) != 0;
+    if (getenv("FR_CHAIN_PROF") && atoi(getenv("FR_CHAIN_PROF")) != 0 && !st->d_prof) {
+      FR_CUDA(e, cudaMalloc(&st->d_prof, kProfIters * kProfPhases * kProfSlots * sizeof(long long)));
+      FR_CUDA(e, cudaMemset(st->d_prof, 0, kProfIters * kProfPhases * kProfSlots * sizeof(long long)));
+    }
   }
   st->ready = true;
   return FR_OK;
 }
 
+// Debug hook (not part of the ABI in include/fleetrec.h; tools/chain_timeline.py binds it by name): the clock64
+// stamps the last chain launch's CTA 0 wrote, [kProfIters][kProfPhases][kProfSlots]; returns the number of values.
+extern "C" int frdbg_chain_timeline(fr_engine* e, long long* out, int n) {
+  TcState* st = e ? static_cast<TcState*>(e->tc_state) : nullptr;
+  const int total = kProfIters * kProfPhases * kProfSlots;
+  if (!st || !st->d_prof || !out || n < total) return 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return 0;
+  if (cudaMemcpy(out, st->d_prof, total * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  return total;
+}
+
 void frtc_destroy(fr_engine* e) {
+  if (TcState* st = static_cast<TcState*>(e->tc_state)) cudaFree(st->d_prof);
   delete static_cast<TcState*>(e->tc_state);
   e->tc_state = nullptr;
 }
@@ -1049,6 +1407,77 @@ fr_status frtc_fused_layer1(fr_engine* e, fr_stream_s* s, const int32_t* d_idx, 
   FR_CUDA(e, cudaLaunchKernelEx(&cfg, kern, st->w_fuse_map, o, p));
   e->launches++;
   return FR_OK;
+}
+
+// The whole MLP as one launch (tc_mlp_chain_kernel) applies to throughput-sized batches of models whose
+// storing layers are multiples of 512 wide (small / medium: 1024-512-256, large: 2048-512-256) when the
+// tile shapes are not pinned by FR_TC_TILES; batches <= kLatencyBatch keep the per-layer 128-wide tiles,
+// which spread one small batch over more SMs.
+bool frtc_can_chain(const fr_engine* e, int B) {
+  const TcState* st = static_cast<const TcState*>(e->tc_state);
+  if (!st || !st->ready || !st->chain || !st->auto_tiles || e->precision != FR_PREC_TF32) return false;
+  if (B <= kLatencyBatch || e->dims[3] != 256) return false;
+  for (int k = 1; k <= 2; k++)
+    if (e->dims[k] % kChainW || e->dims[k] / kChainW > kChainMaxChunks) return false;
+  return e->dims[1] + e->dims[2] + e->dims[3] <= kChainMaxBias;
+}
+
+template <int STAGES>
+static fr_status launch_chain(fr_engine* e, cudaStream_t stream, const ChainMaps& maps, const ChainParams& p) {
+  using L = ChainLayout<STAGES>;
+  static_assert(L::kDyn <= 227 * 1024, "chain configuration exceeds the 227 KB shared memory of an SM");
+  auto kern = tc_mlp_chain_kernel<STAGES>;
+  static std::atomic<uint64_t> attr_done{0};
+  const uint64_t bit = 1ull << (e->device & 63);
+  if (!(attr_done.load() & bit)) {
+    FR_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDyn));
+    attr_done.fetch_or(bit);
+  }
+  const int n_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  int max_clusters = e->sm_count / 2;
+  if (g_max_clusters > 0 && g_max_clusters < max_clusters) max_clusters = g_max_clusters;
+  const int n_clusters = n_tiles < max_clusters ? n_tiles : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_clusters * 2, 1, 1);
+  cfg.blockDim = dim3(kChainThreads, 1, 1);
+  cfg.dynamicSmemBytes = L::kDyn;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FR_CUDA(e, cudaLaunchKernelEx(&cfg, kern, maps, p));
+  e->launches++;
+  return FR_OK;
+}
+
+fr_status frtc_chain(fr_engine* e, fr_stream_s* s, const float* in, int B, float* d_scores) {
+  TcState* st = static_cast<TcState*>(e->tc_state);
+  const bool act = (e->mlp_mode == FR_MLP_BIAS_RELU_SIGMOID);
+  ChainMaps maps;
+  const float* acts[3] = {in, s->d_h[0], s->d_h[1]};
+  fr_status r;
+  for (int l = 0; l < 3; l++) {
+    if ((r = get_a_map(e, st, acts[l], e->dims[l], B, BLOCK_M, &maps.a[l])) != FR_OK) return r;
+    if (l > 0 && (r = get_a_map(e, st, acts[l], e->dims[l], B, kStoreBoxRows, &maps.o[l - 1])) != FR_OK) return r;
+    maps.w[l] = st->w_map128[l];
+  }
+  ChainParams p;
+  for (int l = 0; l < 3; l++) p.bias[l] = act ? e->d_bias[l] : nullptr;
+  p.w4 = e->d_W[3];
+  p.b4 = act ? e->d_bias[3] : nullptr;
+  p.out = d_scores;
+  p.M = B;
+  for (int l = 0; l < 4; l++) p.dims[l] = e->dims[l];
+  p.relu = act ? 1 : 0;
+  p.sigmoid = act ? 1 : 0;
+  p.prof = st->d_prof;
+  static const int stages = getenv("FR_CHAIN_STAGES") ? atoi(getenv("FR_CHAIN_STAGES")) : 3;   // experiment knob
+  if (stages == 2) return launch_chain<2>(e, s->stream, maps, p);
+  return launch_chain<3>(e, s->stream, maps, p);
 }
 
 // One launch: layer k (0,1: store tf32-rounded activations into s->d_h[k]; 2: layer 3 with the

@@ -295,10 +295,51 @@ def test_infer_graph_replay_matches_direct():
             got = sc_buf.cpu().numpy() if kind == "device" else sc_buf.numpy().copy()
             exp = oracle.mlp(oracle.gather(cat, tables, idx), dims, W, b, mode=1)
             assert rel_err(got, exp) <= TOL, (kind, it)
-        # (lookup fused into layer 1) + 2 GEMM launches per batch, replayed or not; 4 with FR_FUSE=0
-        assert eng.launch_count() - l0 == 4 * (3 if os.environ.get("FR_FUSE", "0") == "1" else 4)
+        # (lookup fused into layer 1) + 2 GEMM launches per batch, replayed or not; 4 with FR_FUSE=0;
+        # page-locked index buffers are fetched by a staging kernel instead of a memcpy node (+1)
+        per = (3 if os.environ.get("FR_FUSE", "0") == "1" else 4) + \
+              (1 if kind == "pinned" and os.environ.get("FR_ZEROCOPY", "0") == "1" else 0)
+        assert eng.launch_count() - l0 == 4 * per
     w.close()
     eng.close()
+
+
+@pytest.mark.parametrize("B", (1, 333, 2048))
+def test_pinned_buffers_without_copy_engine_match_memcpy_path(B, monkeypatch):
+    """Page-locked caller buffers: indices are fetched over PCIe by a staging kernel and the scores are written
+    to the host buffer by the last MLP kernel itself (no memcpy nodes) with FR_ZEROCOPY=1; 0 = cudaMemcpyAsync.
+    Both must give the same bits, direct and graph-replayed, with new index contents in the same buffer
+    (B * 47 * 4 bytes is a multiple of 16 only for some B: the others take the memcpy path for the indices)."""
+    import torch
+    cat = catalogue.load("small").with_row_cap(5000)
+    dims = cat.layer_dims
+    tables = oracle.make_tables(cat, "hash", seed=5)
+    W, b = oracle.make_weights(dims, seed=42)
+    got = {}
+    for zc in ("1", "0"):
+        monkeypatch.setenv("FR_ZEROCOPY", zc)
+        eng = fleetrec.Engine(cat, max_batch=B)
+        eng.load_tables(tables)
+        eng.load_mlp(W, b)
+        w = fleetrec.Worker(eng)
+        idx_buf = torch.empty((B, 47), dtype=torch.int32).pin_memory()
+        sc_buf = torch.zeros(B, dtype=torch.float32).pin_memory()
+        outs = []
+        for it in range(4):     # calls 2.. replay the captured graph
+            idx = oracle.zipf_indices(cat, B, seed=40 + it)
+            idx_buf.copy_(torch.from_numpy(idx))
+            eng.infer_async(idx_buf.numpy(), sc_buf.numpy(), B, w)
+            eng.sync(w)
+            outs.append(sc_buf.numpy().copy())
+            if zc == "1":
+                exp = oracle.mlp(oracle.gather(cat, tables, idx), dims, W, b, mode=1)
+                assert rel_err(outs[-1], exp) <= TOL, it
+        got[zc] = outs
+        w.close()
+        eng.close()
+    monkeypatch.delenv("FR_ZEROCOPY", raising=False)
+    for a, c in zip(got["1"], got["0"]):
+        assert_bits_equal(a, c)
 
 
 @pytest.mark.parametrize("tiles", TILES)
@@ -334,6 +375,45 @@ def test_tf32_persistent_tile_loop(tiles, clusters, pdl, monkeypatch):
     assert rel_err(got, oracle.mlp(x, dims, W, b, mode=1)) <= TOL
     eng.close()
     monkeypatch.delenv("FR_TC_MAX_CLUSTERS", raising=False)
+
+
+@pytest.mark.parametrize("model,B,clusters", (("small", 513, 0), ("small", 2048, 0), ("small", 1300, 1),
+                                              ("medium", 3000, 2), ("large", 2304, 3), ("small", 40000, 0)))
+def test_tf32_chain_kernel_bit_identical_to_per_layer_kernels(model, B, clusters, monkeypatch):
+    """FR_CHAIN=1: batches above 512 run the whole MLP as ONE persistent launch (tc_mlp_chain_kernel): a CTA pair
+    walks its 256 items through every layer, H1 / H2 stored with TMA and re-loaded by the same CTA behind
+    `ready` barriers.  The K order of every accumulation is that of the per-layer kernels, so the scores
+    must be IDENTICAL bit for bit (a stale H1 / H2 row, i.e. a broken store -> load hand-over, could not
+    be); capped grids make one pair run many item tiles (barrier parities wrap), B = 40000 is the
+    production grid with more item tiles than CTA pairs.  Also against the oracle and the README KAT."""
+    if clusters:
+        monkeypatch.setenv("FR_TC_MAX_CLUSTERS", str(clusters))
+    else:
+        monkeypatch.delenv("FR_TC_MAX_CLUSTERS", raising=False)
+    cat = catalogue.load(model).with_row_cap(64)
+    dims = cat.layer_dims
+    W, b = oracle.make_weights(dims, seed=21)
+    x = np.random.default_rng(B).uniform(-1, 1, (B, dims[0])).astype(np.float32)
+    got = {}
+    for chain in ("1", "0"):
+        monkeypatch.setenv("FR_CHAIN", chain)
+        eng = fleetrec.Engine(cat, max_batch=B)
+        eng.load_mlp(W, b)
+        l0 = eng.launch_count()
+        for _ in range(3):   # back to back on one stream: the next launch overwrites H1 / H2 of the previous one
+            got[chain] = eng.mlp_only(x)
+        assert eng.launch_count() - l0 == 3 * (1 if chain == "1" else 3)
+        if chain == "1":     # reference KAT through the chain (LINEAR mode, all-ones): exact
+            eng.close()
+            eng = fleetrec.Engine(cat, mlp_mode=fleetrec.FR_MLP_LINEAR, max_batch=B)
+            eng.load_mlp([np.ones((dims[k], dims[k + 1]), np.float32) for k in range(4)])
+            out = eng.mlp_only(np.ones((min(B, 1000), dims[0]), np.float32))
+            assert np.all(out == np.float32(KAT[model])), out[:4]
+        eng.close()
+    monkeypatch.delenv("FR_CHAIN", raising=False)
+    monkeypatch.delenv("FR_TC_MAX_CLUSTERS", raising=False)
+    assert_bits_equal(got["1"], got["0"])
+    assert rel_err(got["1"], oracle.mlp(x, dims, W, b, mode=1)) <= TOL
 
 
 def test_merge_planner_engine_matches_unmerged_engine():
@@ -470,7 +550,9 @@ def test_fused_lookup_layer1_matches_unfused_and_oracle(model, B, monkeypatch):
         eng.load_mlp(W, b)
         l0 = eng.launch_count()
         got[fuse] = eng.infer(idx)
-        assert eng.launch_count() - l0 == (3 if fuse == "1" else 4)
+        # lookup fused into layer 1 + layers 2, 3; else lookup + (one chain launch above 512 items | 3 layers)
+        chain = os.environ.get("FR_CHAIN", "0") == "1" and B > 512
+        assert eng.launch_count() - l0 == (3 if fuse == "1" else (2 if chain else 4))
         eng.close()
     exp = oracle.mlp(oracle.gather(cat, tables, idx), dims, W, b, mode=1)
     assert rel_err(got["1"], exp) <= TOL, rel_err(got["1"], exp)

@@ -233,8 +233,8 @@ def test_sharded_multi_worker_graph_replay(world):
             assert err <= 1e-3, (step, w, err)
     # same kernels per step whether launched directly or replayed from the graph
     per_step = (engs[0].launch_count() - l0[0]) / (7 * n_workers)
-    # push (+ replicated lookup) + flags + 3 GEMM launches; 4 with FR_SHARD_ONE_LAUNCH=1
-    assert per_step in (4, 5, 6), per_step
+    # [index staging kernel] + push (+ replicated lookup) + flags + 3 GEMM launches (or one chain launch)
+    assert per_step == int(per_step) and 3 <= per_step <= 7, per_step
     for r, e in enumerate(engs):
         for w in workers[r]:
             w.close()
