@@ -164,7 +164,10 @@ extern "C" fr_status fr_create(const fr_model_desc* desc, int n_gpus, const int*
   if (const char* env = getenv("FR_GRAPHS")) e->use_graphs = atoi(env) != 0;
   if (const char* env = getenv("FR_PDL")) e->pdl_mask = atoi(env) & 7;
   if (const char* env = getenv("FR_FUSE")) e->fuse_lookup = atoi(env) != 0;
-  if (const char* env = getenv("FR_ZEROCOPY")) e->zero_copy = atoi(env) != 0;
+  if (const char* env = getenv("FR_ZEROCOPY")) {
+    const int v = atoi(env);
+    e->zero_copy_pct = v == 1 ? 100 : (v < 0 ? 0 : (v > 100 ? 100 : v));
+  }
   e->tables.resize(desc->n_tables);
   for (int t = 0; t < desc->n_tables; t++) {
     e->tables[t].rows = desc->tables[t].rows;
@@ -392,7 +395,7 @@ static bool is_device_ptr(const void* p) {
 // The device-side alias of a page-locked, mapped host buffer (cudaHostAlloc / cudaHostRegister under UVA),
 // null for pageable or device memory.
 static void* mapped_host_alias(const fr_engine* e, const void* p) {
-  if (!e->zero_copy || !p) return nullptr;
+  if (e->zero_copy_pct <= 0 || !p) return nullptr;
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
     cudaGetLastError();
@@ -437,11 +440,16 @@ static fr_status stage_idx(fr_engine* e, fr_stream_s* s, const int32_t* idx, int
   }
   const size_t bytes = (size_t)B * e->tables.size() * sizeof(int32_t);
   *d_idx = s->d_idx;
-  // page-locked caller buffer: the SMs fetch it (no copy-engine node); pageable: the driver's staged copy
-  const void* alias = mapped_host_alias(e, idx);
-  if (alias && bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(alias) & 15) == 0)
-    return frk_stage_idx(e, alias, s->d_idx, bytes, s->stream);
-  FR_CUDA(e, cudaMemcpyAsync(s->d_idx, idx, bytes, cudaMemcpyHostToDevice, s->stream));
+  // page-locked caller buffer: the copy engine moves the head of the batch, the SMs fetch the tail over PCIe
+  // (zero_copy_pct of it, in 16-byte units); pageable buffer: the driver's staged copy
+  const char* alias = static_cast<const char*>(mapped_host_alias(e, idx));
+  size_t head = bytes;
+  if (alias && (reinterpret_cast<uintptr_t>(alias) & 15) == 0 && bytes % 16 == 0)
+    head = (bytes / 16) * (size_t)(100 - e->zero_copy_pct) / 100 * 16;
+  if (head > 0) FR_CUDA(e, cudaMemcpyAsync(s->d_idx, idx, head, cudaMemcpyHostToDevice, s->stream));
+  if (head < bytes)
+    return frk_stage_idx(e, alias + head, reinterpret_cast<int32_t*>(reinterpret_cast<char*>(s->d_idx) + head), bytes - head,
+                         s->stream);
   return FR_OK;
 }
 

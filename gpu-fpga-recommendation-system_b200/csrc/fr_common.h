@@ -88,12 +88,14 @@ struct fr_engine {
   // deadlocked on the device intermittently on B200 / driver 580 (bit 0: 8 of 12 runs; mask 6: 1 of ~12),
   // never without them; with 8 workers in flight the edges buy <= 2% anyway (10% with 4 workers).
   int pdl_mask = 0;
-  // FR_ZEROCOPY=1: page-locked (mapped) caller buffers are read / written by the kernels themselves over
-  // PCIe instead of through memcpy nodes -- indices by a staging kernel, scores by the last MLP kernel.
-  // Off by default: measured slower than the copy engine on B200 (small model, batch 2048, 12 workers:
-  // 13.1 against 12.3 us per step end to end; both are bound by moving 385 KB of indices per step over PCIe,
-  // ~31 GB/s), although it takes 1.6 us of host enqueue time off every step.
-  bool zero_copy = false;
+  // Page-locked (mapped) caller buffers can be read / written by the kernels themselves over PCIe instead of
+  // through memcpy nodes: indices by a staging kernel, scores by the last MLP kernel.  On this box one 385 KB
+  // index copy occupies the copy engine for ~12.5 us (7 us of transfer at 55 GB/s + ~5 us of fixed cost per copy,
+  // whatever the number of streams), and SM reads of host memory alone sustain ~29 GB/s (13.1 us per batch), so
+  // neither path alone keeps up with the kernels (9.2 us per batch).  zero_copy_pct = the share of every index
+  // batch the SMs fetch while the copy engine moves the rest (FR_ZEROCOPY=0..100; 1 means 100); the two run in
+  // parallel across the worker streams.  0 = cudaMemcpyAsync only.
+  int zero_copy_pct = 0;
 
   std::vector<FrTable> tables;
   FrChunk* d_chunks = nullptr;  // [D/4]

@@ -278,6 +278,19 @@ __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_
       "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
       : "memory");
 }
+// The same, delivered to this CTA and to every CTA of `mask` at the same smem offset (the pairs of a 4-CTA
+// cluster that multiply the same weight slice).  `bar_own` is THIS CTA's barrier address with the pair bit
+// (bit 24 of a shared-window address) cleared: the byte count is posted on the barrier at that offset in the
+// LEADER of each destination CTA's pair.
+__device__ __forceinline__ void tma_load_2d_pair_mcast(const CUtensorMap* map, uint32_t bar_own, void* smem, int c0, int c1,
+                                                       uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], "
+      "[%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem)),
+      "l"(map), "r"(bar_own), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the pair bit of a shared-window address: "the leader's"
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
                : "memory");
@@ -308,6 +321,15 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
       : "memory");
 }
 
+// The same, arriving in every CTA of `mask` (cluster ranks).
+__device__ __forceinline__ void umma_commit_mask(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+
 // ---- TMA store / programmatic dependent launch ----------------------------------
 // smem (128B-swizzled box) -> global; completion tracked by this thread's bulk async-groups.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem, int c0, int c1) {
@@ -333,6 +355,20 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
 
+// 16-byte asynchronous copy global -> shared through the LSU (LDGSTS), bypassing L1; src_bytes = 0 writes zeros
+// (rows past the batch, pieces past K) without touching `src`.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+constexpr int kLoaderWarp0 = 6;      // A_LSU kernels: warps 6..9 load the A operand with cp.async
+constexpr int kLoaderWarps = 4;
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 constexpr int kMaxN = 2048;          // widest layer whose bias vector is staged in smem (large model H1)
 constexpr int kStoreBoxRows = 32;    // TMA store box: one epilogue warp's 32 rows x 32 fp32 columns
 constexpr int kStoreBufBytes = kStoreBoxRows * BLOCK_K * 4;   // 4 KB, 128B-swizzled
@@ -349,7 +385,7 @@ struct SmemLayout {
   static constexpr int kStoreOff = STAGES * kStageBytes;          // 4 epilogue warps x 2 store buffers
   static constexpr int kAuxOff = kStoreOff + 4 * 2 * kStoreBufBytes;   // bias[kMaxN], w4[256]
   static constexpr int kBarOff = kAuxOff + (kMaxN + 256) * 4;
-  static constexpr int kNumBars = 2 * STAGES + 4;                 // full, empty, tmem_full[2], tmem_empty[2]
+  static constexpr int kNumBars = 3 * STAGES + 4;                 // full, empty, tmem_full[2], tmem_empty[2], a_full
   static constexpr int kTotal = kBarOff + kNumBars * 8 + 16;
   static constexpr int kDyn = kTotal + 1024;                      // slack for manual 1024-B alignment
   // BLOCK_N <= 256: two accumulator stages (epilogue of tile i under the MMAs of tile i+1).
@@ -365,6 +401,7 @@ struct SmemLayout {
 };
 
 struct TcParams {
+  const float* a;      // [M][K] activations (A_LSU kernels read them with cp.async; the others through tmap_a)
   const float* bias;   // [N] or null
   float* out;          // EPI_DOT: scores [M]  (EPI_STORE writes through tmap_out)
   const float* w4;     // EPI_DOT: output-layer weights [N]
@@ -387,10 +424,30 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32_m(int m, int n) {
 //   TMEM        tmem_full/empty   MMA issuer    <-> epilogue   (two accumulator stages, so the
 //                                 epilogue of tile i overlaps the MMAs of tile i+1)
 //   store bufs  bulk async-groups epilogue warp <-> TMA store  (two 4 KB buffers per warp)
-template <int BLOCK_N, int STAGES, int EPI, int CTAS>
-__global__ void __launch_bounds__(kThreads, 1)
+// PAIRS = 2 (CTAS = 2 only): a cluster of FOUR CTAs, two MMA pairs working on adjacent 256-row tiles of the
+// same N tile in lockstep.  Both pairs multiply the same weight slice, so every CTA loads only HALF of its
+// share of it and TMA-multicasts that half to the CTA of the same parity in the other pair: per K slice a
+// CTA issues 16 + 16 KB (512-wide) or 16 + 8 KB (256-wide) of loads instead of 16 + 32 / 16 + 16, and the L2
+// serves every weight byte once per cluster.  The TMA unit of an SM sustains ~33 B/clk here while the MMAs of
+// a 512-wide tile want 49, so issued bytes per SM are what bounds the main loop.  A smem slot may be refilled
+// only when BOTH pairs have consumed it (the neighbour's load writes into it): the empty barrier counts two
+// multicast commits.
+//
+// A_LSU: the A operand (activations) does not go through the TMA unit.  An SM takes in ~33 B/clk through TMA
+// whatever the box shape, stage count, L2 promotion or multicast (all measured), and a 512-wide tile wants 49;
+// but 16-byte LDGSTS copies through the LSU run beside it (a probe streaming 38 GB/s per SM next to the TMA
+// feed slowed the main loop by 8 %).  So four more warps (6..9) copy the 128 x 32 A slice with cp.async.cg into
+// the same 128B-swizzled slot layout TMA would have produced (16-byte piece j of row r at piece j ^ (r & 7));
+// every loader thread posts cp.async.mbarrier.arrive.noinc on the slot's a_full barrier, so the arrival fires
+// when its copies have landed and the loaders only ever wait for free slots (all slots can be in flight).
+// The leader's MMA issuer waits for its own CTA's a_full; the peer CTA's otherwise idle warp 1 waits for the
+// peer's and relays it as one remote arrival on the leader's full barrier.  TMA then carries the weights
+// only: 32 KB per K slice of a 512-wide tile (0.49 us at the measured rate, the MMAs take 0.5).
+template <int BLOCK_N, int STAGES, int EPI, int CTAS, int PAIRS, bool A_LSU>
+__global__ void __launch_bounds__(kThreads + (A_LSU ? kLoaderWarps * 32 : 0), 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const TcParams p) {
+  static_assert(!A_LSU || (CTAS == 2 && PAIRS == 1), "the cp.async A loader is built for plain CTA pairs");
   using L = SmemLayout<BLOCK_N, STAGES, CTAS>;
   extern __shared__ uint8_t smem_raw[];
   // the dynamic-smem base offset is identical in both CTAs of a pair, so is the aligned layout
@@ -401,23 +458,29 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2], the leader's are the ones used
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* a_full_bar = tmem_empty_bar + 2;        // [STAGES], A_LSU: this CTA's A slice has landed (cp.async arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_full_bar + STAGES);
 
+  static_assert(PAIRS == 1 || CTAS == 2, "multicast clusters are made of CTA pairs");
+  constexpr int CS = CTAS * PAIRS;   // CTAs per cluster
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const uint32_t rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+  const uint32_t crank = (CTAS == 2) ? cluster_ctarank() : 0u;   // rank in the cluster
+  const uint32_t rank = crank & 1u, pair = crank >> 1;            // rank in the MMA pair, pair in the cluster
   const bool leader = (rank == 0);
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int n_tiles_n = p.N / BLOCK_N;
-  const int n_tiles = ((p.M + BLOCK_M * CTAS - 1) / (BLOCK_M * CTAS)) * n_tiles_n;
-  const int cluster_id = blockIdx.x / CTAS, n_clusters = gridDim.x / CTAS;
+  const int n_tiles = ((p.M + BLOCK_M * CS - 1) / (BLOCK_M * CS)) * n_tiles_n;   // a tile = (BLOCK_M * CS) rows x BLOCK_N
+  const int cluster_id = blockIdx.x / CS, n_clusters = gridDim.x / CS;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
     if (EPI == EPI_STORE) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_out) : "memory");
     for (int s = 0; s < STAGES; s++) {
-      mbar_init(&full_bar[s], 1);   // the leader's producer arrives once; bytes of both CTAs are expected
-      mbar_init(&empty_bar[s], 1);  // one (multicast) tcgen05.commit per use
+      // the leader's producer arrives once, bytes of both CTAs are expected; A_LSU: + the peer CTA's relay
+      mbar_init(&full_bar[s], 1 + (A_LSU ? 1 : 0));
+      mbar_init(&a_full_bar[s], kLoaderWarps * 32);   // A_LSU: one cp.async-completion arrival per loader thread
+      mbar_init(&empty_bar[s], PAIRS);  // one (multicast) tcgen05.commit per use from every pair that reads the slot
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(&tmem_full_bar[a], 1);          // one (multicast) tcgen05.commit per tile
@@ -427,7 +490,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp == 1) {
     if (CTAS == 2) tmem_alloc_pair(tmem_ptr, L::kTmemCols);
     else tmem_alloc(tmem_ptr, L::kTmemCols);
-  } else if (warp >= kEpiWarp0) {
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
     // weights, not produced by the preceding kernel: staged before the grid dependency resolves
     const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..127
     for (int i = et; i < p.N; i += 128) s_bias[i] = p.bias ? p.bias[i] : 0.f;
@@ -446,7 +509,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       uint32_t kc = 0;   // k-slices issued so far (ring position runs on across tiles)
       for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
-        const int m0 = ((tile / n_tiles_n) * CTAS + (int)rank) * BLOCK_M;
+        const int m0 = (((tile / n_tiles_n) * PAIRS + (int)pair) * CTAS + (int)rank) * BLOCK_M;
         const int nb0 = (tile % n_tiles_n) * BLOCK_N + (int)rank * L::kSubRows;
         for (int kb = 0; kb < num_kb; kb++, kc++) {
           const int s = kc % STAGES;
@@ -454,10 +517,20 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&empty_bar[s], ph ^ 1, 1, kc, tile);
           uint8_t* a_dst = smem + s * L::kStageBytes;
           uint8_t* b_dst = a_dst + L::kABytes;
-          if (CTAS == 2) {
-            const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);   // leader's barrier
+          if (PAIRS == 2) {
+            // this CTA's rows of Wt for the K step, in smem order: sub-tile h, row r <-> Wt row nb0 + h * kMmaN + r.
+            // It loads part `pair` of them and multicasts it to the CTA of its parity in both pairs.
+            constexpr int kPartRows = L::kNSub * L::kSubRows / PAIRS;
+            const int r0 = (int)pair * kPartRows;
+            const uint32_t bar = smem_u32(&full_bar[s]) & kPeerBitMask;   // "my pair leader's", in every destination
             if (leader) mbar_expect_tx(&full_bar[s], 2 * L::kStageBytes);
             tma_load_2d_pair(&tmap_a, bar, a_dst, kb * BLOCK_K, m0);
+            tma_load_2d_pair_mcast(&tmap_b, bar, b_dst + r0 * (BLOCK_K * 4), kb * BLOCK_K,
+                                   nb0 + (r0 / L::kSubRows) * L::kMmaN + r0 % L::kSubRows, (uint16_t)(0x5u << rank));
+          } else if (CTAS == 2) {
+            const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);   // leader's barrier
+            if (leader) mbar_expect_tx(&full_bar[s], 2 * (L::kStageBytes - (A_LSU ? L::kABytes : 0)));
+            if (!A_LSU) tma_load_2d_pair(&tmap_a, bar, a_dst, kb * BLOCK_K, m0);
 #pragma unroll
             for (int h = 0; h < L::kNSub; h++)   // this CTA's rows of Wt for MMA h of the K step
               tma_load_2d_pair(&tmap_b, bar, b_dst + h * L::kSubBytes, kb * BLOCK_K, nb0 + h * L::kMmaN);
@@ -475,6 +548,21 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only for a pair) =====
+    if (A_LSU && !leader) {
+      // the peer CTA's warp 1 has no MMAs to issue: it relays "my A slice has landed" to the leader
+      const uint32_t full_remote = mapa_u32(smem_u32(&full_bar[0]), 0);
+      uint32_t kc = 0;
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters)
+        for (int kb = 0; kb < num_kb; kb++, kc++) {
+          const int s = kc % STAGES;
+          mbar_wait(&a_full_bar[s], (kc / STAGES) & 1, 7, kc, tile);
+          if (lane == 0) {
+            fence_proxy_async();
+            mbar_arrive_cluster(full_remote + s * 8);
+          }
+          __syncwarp();
+        }
+    }
     if (leader) {
       constexpr uint32_t idesc = make_idesc_tf32_m(BLOCK_M * CTAS, L::kMmaN);
       uint32_t kc = 0, it = 0;
@@ -486,7 +574,14 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int kb = 0; kb < num_kb; kb++, kc++) {
           const int s = kc % STAGES;
           const uint32_t ph = (kc / STAGES) & 1;
-          mbar_wait(&full_bar[s], ph, 3, kc, tile);
+          if (A_LSU) {
+            mbar_wait_cluster(&full_bar[s], ph, 3, kc, tile);   // weights of both CTAs + the peer's A slice (relayed)
+            mbar_wait(&a_full_bar[s], ph, 7, kc, tile);         // this CTA's A slice
+            // (no fence.proxy.async here: issued by the thread that has MMAs in flight it drains them, one K slice
+            // at a time -- 0.9 us per slice; cp.async completion -> mbarrier -> tcgen05.mma is ordered as it is)
+          } else {
+            mbar_wait(&full_bar[s], ph, 3, kc, tile);
+          }
           tc_fence_after();
           if (elect_one()) {
             const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
@@ -503,7 +598,10 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 else umma_tf32(d_tmem + h * L::kMmaN, a_desc + (uint64_t)(k * 2), bd, idesc, (kb | k) != 0);
               }
             }
-            if (CTAS == 2) {
+            if (PAIRS == 2) {
+              umma_commit_mask(&empty_bar[s], 0xF);                                        // one of the two releases, in all four CTAs
+              if (kb == num_kb - 1) umma_commit_mask(&tmem_full_bar[as], (uint16_t)(0x3u << (2 * pair)));
+            } else if (CTAS == 2) {
               umma_commit_pair(&empty_bar[s]);                            // frees the slot in both CTAs
               if (kb == num_kb - 1) umma_commit_pair(&tmem_full_bar[as]);  // accumulators complete in both CTAs
             } else {
@@ -515,15 +613,40 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
     }
+  } else if (A_LSU && warp >= kLoaderWarp0) {
+    // ===== A loaders: thread t copies piece j = t % 8 of rows t / 8 + 16 i (i < 8) of every K slice =====
+    const int t = threadIdx.x - kLoaderWarp0 * 32;   // 0..127
+    const int j = t & 7, r0 = t >> 3;
+    const float* A = p.a;
+    uint32_t kc = 0;      // K slices issued
+    for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+      const int m0 = ((tile / n_tiles_n) * CTAS + (int)rank) * BLOCK_M;
+      for (int kb = 0; kb < num_kb; kb++, kc++) {
+        const int s = kc % STAGES;
+        mbar_wait(&empty_bar[s], ((kc / STAGES) & 1) ^ 1, 5, kc, tile);
+        const uint32_t slot = smem_u32(smem + s * L::kStageBytes);
+        const int col = kb * BLOCK_K + j * 4;
+        const bool col_ok = col < p.K;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int r = r0 + 16 * i, row = m0 + r;
+          const bool ok = col_ok && row < p.M;
+          cp_async16(slot + r * 128 + ((j ^ (r & 7)) << 4), ok ? A + (size_t)row * p.K + col : A, ok ? 16u : 0u);
+        }
+        // fires when this thread's copies above have landed
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&a_full_bar[s])) : "memory");
+      }
+    }
+    cp_async_wait_all();   // nothing of this thread is still in flight when the CTA retires
   } else {
     // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
     const int q = warp % 4;
     uint8_t* store_buf = smem + L::kStoreOff + (warp - kEpiWarp0) * 2 * kStoreBufBytes;
-    const uint32_t empty_remote = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);   // leader's tmem_empty_bar[0]
+    const uint32_t empty_remote = mapa_u32(smem_u32(&tmem_empty_bar[0]), crank & ~1u);   // my pair leader's tmem_empty_bar[0]
     uint32_t it = 0, sc = 0;   // tiles done, store chunks issued
     for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
       const uint32_t as = it % L::kAcc;
-      const int row0 = ((tile / n_tiles_n) * CTAS + (int)rank) * BLOCK_M + q * 32;
+      const int row0 = (((tile / n_tiles_n) * PAIRS + (int)pair) * CTAS + (int)rank) * BLOCK_M + q * 32;
       const int n0 = (tile % n_tiles_n) * BLOCK_N;
       mbar_wait(&tmem_full_bar[as], (it / L::kAcc) & 1, 4, it, tile);
       tc_fence_after();
@@ -623,6 +746,8 @@ struct ChainParams {
   int dims[4];            // K0, N1, N2, N3 (= 256)
   int relu, sigmoid;
   long long* prof;        // FR_CHAIN_PROF=1: clock64 stamps of CTA 0's first item tiles (kProf* below), else null
+  const float* probe_src; // PROBE: buffer the probe warps stream (L2-resident)
+  uint32_t probe_vecs;    // its size in float4
 };
 
 // timeline of CTA 0: prof[((item tile iteration * kProfPhases) + phase) * kProfSlots + slot]
@@ -633,8 +758,10 @@ __device__ __forceinline__ void prof_stamp(long long* prof, uint32_t it, int ph,
   if (prof && it < (uint32_t)kProfIters && ph < kProfPhases) prof[((int)it * kProfPhases + ph) * kProfSlots + slot] = clock64();
 }
 
-template <int STAGES>
-__global__ void __launch_bounds__(kChainThreads, 1)
+// PROBE (experiment, FR_CHAIN_PROBE=1): four extra warps stream 16-byte L2 loads through the LSU while the TMA
+// unit feeds the MMAs, to see whether the two paths into an SM share one ingest limit (tools/chain_timeline.py).
+template <int STAGES, bool PROBE>
+__global__ void __launch_bounds__(kChainThreads + (PROBE ? 128 : 0), 1)
 tc_mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   using L = ChainLayout<STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -647,11 +774,13 @@ tc_mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p)
   uint64_t* tmem_empty_bar = tmem_full_bar + 1;
   uint64_t* ready_bar = tmem_empty_bar + 1;          // [2][kChainMaxChunks]: chunk c of layer l's output is in global memory
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ready_bar + 2 * kChainMaxChunks);
+  volatile uint32_t* probe_done = tmem_ptr + 1;
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const uint32_t rank = cluster_ctarank();
   const bool leader = (rank == 0);
   const int n_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);   // item tiles of 256
+  if (PROBE && threadIdx.x == 0) *probe_done = 0;
   const int cluster_id = blockIdx.x / 2, n_clusters = gridDim.x / 2;
   long long* const prof = (blockIdx.x == 0 && lane == 0) ? p.prof : nullptr;
 
@@ -728,8 +857,32 @@ tc_mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p)
           }
         }
       }
+      if (PROBE) *probe_done = 1;
     }
     __syncwarp();
+  } else if (PROBE && warp >= kEpiWarp0 + kChainEpiWarps) {
+    // ===== probe warps: 16 KB of L2 loads per iteration through the LSU until the producer is done =====
+    const int t = threadIdx.x - (kEpiWarp0 + kChainEpiWarps) * 32;   // 0..127
+    const float4* src = reinterpret_cast<const float4*>(p.probe_src);
+    const uint32_t nvec = p.probe_vecs;
+    uint32_t base = (blockIdx.x * 8191u) % nvec, iters = 0;
+    float acc = 0.f;
+    const long long t0 = clock64();
+    while (*probe_done == 0) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        float4 v;
+        const float4* a = src + (base + u * 128 + t) % nvec;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a));
+        acc += v.x + v.y + v.z + v.w;
+      }
+      base = (base + 1024) % nvec;
+      iters++;
+    }
+    if (p.prof && blockIdx.x == 0 && t == 0) {
+      long long* a = p.prof + (kProfIters - 1) * kProfPhases * kProfSlots + 7 * kProfSlots;   // last row of the buffer
+      a[0] = iters; a[1] = clock64() - t0; a[2] = (long long)acc;
+    }
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA) =====
     if (leader) {
@@ -1131,7 +1284,15 @@ struct TcState {
   PFN_encodeTiled encode = nullptr;
   CUtensorMap w_map[3];
   CUtensorMap w_fuse_map;   // layer-1 weights in 128-row boxes, for the fused lookup + layer 1 kernel
-  CUtensorMap w_map64[2];   // layers 1, 2 in 64-row boxes: 128-wide pair tiles (automatic choice for small batches)
+  CUtensorMap w_map64[3];   // 64-row boxes: 128-wide pair tiles (small batches); a CTA's multicast half of a 256-wide tile
+  // FR_TC_MCAST=1: 4-CTA multicast clusters for throughput-sized batches.  Off by default: parity-green, but not
+  // faster -- halving the bytes every SM ISSUES changed nothing (layer 2, batch 2048: 28.8 us either way; batch
+  // 16384: 37.8 against 34.7 us), so the ~33 B/clk an SM takes in is an ingest limit, and 4-CTA clusters pack worse.
+  bool mcast = false;
+  // FR_TC_ALSU=1: the A operand of throughput-sized batches through cp.async (LSU) instead of TMA.  Off by default:
+  // parity-green (bit-identical) but slower -- 0.85 us per K slice whatever the stage count (layer 2, batch 2048:
+  // 35.0 against 28.8 us; layer 3: 30.8 against 16.5), i.e. ~19 GB/s per SM of LDGSTS next to the TMA weight feed.
+  bool a_lsu = false;
   CUtensorMap w_map128[3];  // every layer in 128-row boxes: the one-launch chain (a CTA's half of an N = 256 MMA)
   // FR_CHAIN=1: the whole MLP as one launch where the chain kernel applies.  Off by default: parity-green
   // (bit-identical to the per-layer kernels) but slower -- with ONE 512-column TMEM stage every epilogue is
@@ -1178,14 +1339,15 @@ int g_max_clusters = 0;   // FR_TC_MAX_CLUSTERS: cap the persistent grid (tests 
 // inferences/s (a longer gang leaves too few clusters per launch to keep 148 SMs busy).
 int g_min_kb = 32;
 
-template <int BLOCK_N, int STAGES, int EPI, int CTAS>
+template <int BLOCK_N, int STAGES, int EPI, int CTAS, int PAIRS = 1, bool A_LSU = false>
 fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const TcParams& p,
                  bool pdl_attr, cudaStream_t st) {
   using L = SmemLayout<BLOCK_N, STAGES, CTAS>;
+  constexpr int CS = CTAS * PAIRS;
   static_assert(L::kDyn <= 227 * 1024, "tile configuration exceeds the 227 KB shared memory of an SM");
   static_assert(L::kTmemCols == 256 || L::kTmemCols == 512, "TMEM allocation must be a power of two");
   static_assert(L::kNSub == 1 || CTAS == 2, "512-wide tiles are pair tiles");
-  auto kern = tc_linear_kernel<BLOCK_N, STAGES, EPI, CTAS>;
+  auto kern = tc_linear_kernel<BLOCK_N, STAGES, EPI, CTAS, PAIRS, A_LSU>;
   static std::atomic<uint64_t> attr_done{0};  // bit d: opt-in smem size set on device d for this instantiation
   const uint64_t bit = 1ull << (e->device & 63);
   if (!(attr_done.load() & bit)) {
@@ -1193,8 +1355,8 @@ fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const
     attr_done.fetch_or(bit);
   }
   // persistent: one cluster per tile up to one CTA per SM
-  const int n_tiles = (p.M + BLOCK_M * CTAS - 1) / (BLOCK_M * CTAS) * (p.N / BLOCK_N);
-  int max_clusters = e->sm_count / CTAS;
+  const int n_tiles = (p.M + BLOCK_M * CS - 1) / (BLOCK_M * CS) * (p.N / BLOCK_N);
+  int max_clusters = e->sm_count / CS;
   if (g_max_clusters > 0 && g_max_clusters < max_clusters) max_clusters = g_max_clusters;   // test knob
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
   // (ganging only pays when the epilogue of one tile runs under the next tile's MMAs: two accumulator stages)
@@ -1202,13 +1364,13 @@ fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const
   int n_clusters = (n_tiles + gang - 1) / gang;
   if (n_clusters > max_clusters) n_clusters = max_clusters;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(n_clusters * CTAS, 1, 1);
-  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.gridDim = dim3(n_clusters * CS, 1, 1);
+  cfg.blockDim = dim3(kThreads + (A_LSU ? kLoaderWarps * 32 : 0), 1, 1);
   cfg.dynamicSmemBytes = L::kDyn;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.x = CS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1321,8 +1483,10 @@ fr_status frtc_prepare(fr_engine* e) {
   {
     fr_status s = encode_2d(e, st, &st->w_fuse_map, e->d_Wt[0], e->dims[1], e->dims[0], 128);
     if (s != FR_OK) return s;
-    for (int k = 0; k < 2; k++)
+    for (int k = 0; k < 3; k++)
       if ((s = encode_2d(e, st, &st->w_map64[k], e->d_Wt[k], e->dims[k + 1], e->dims[k], 64)) != FR_OK) return s;
+    if (const char* env = getenv("FR_TC_MCAST")) st->mcast = atoi(env) != 0;
+    if (const char* env = getenv("FR_TC_ALSU")) st->a_lsu = atoi(env) != 0;
     for (int k = 0; k < 3; k++)
       if ((s = encode_2d(e, st, &st->w_map128[k], e->d_Wt[k], e->dims[k + 1], e->dims[k], 128)) != FR_OK) return s;
     if (const char* env = getenv("FR_CHAIN")) st->chain = atoi(env) != 0;
@@ -1422,11 +1586,11 @@ bool frtc_can_chain(const fr_engine* e, int B) {
   return e->dims[1] + e->dims[2] + e->dims[3] <= kChainMaxBias;
 }
 
-template <int STAGES>
+template <int STAGES, bool PROBE = false>
 static fr_status launch_chain(fr_engine* e, cudaStream_t stream, const ChainMaps& maps, const ChainParams& p) {
   using L = ChainLayout<STAGES>;
   static_assert(L::kDyn <= 227 * 1024, "chain configuration exceeds the 227 KB shared memory of an SM");
-  auto kern = tc_mlp_chain_kernel<STAGES>;
+  auto kern = tc_mlp_chain_kernel<STAGES, PROBE>;
   static std::atomic<uint64_t> attr_done{0};
   const uint64_t bit = 1ull << (e->device & 63);
   if (!(attr_done.load() & bit)) {
@@ -1439,7 +1603,7 @@ static fr_status launch_chain(fr_engine* e, cudaStream_t stream, const ChainMaps
   const int n_clusters = n_tiles < max_clusters ? n_tiles : max_clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n_clusters * 2, 1, 1);
-  cfg.blockDim = dim3(kChainThreads, 1, 1);
+  cfg.blockDim = dim3(kChainThreads + (PROBE ? 128 : 0), 1, 1);
   cfg.dynamicSmemBytes = L::kDyn;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -1475,6 +1639,10 @@ fr_status frtc_chain(fr_engine* e, fr_stream_s* s, const float* in, int B, float
   p.relu = act ? 1 : 0;
   p.sigmoid = act ? 1 : 0;
   p.prof = st->d_prof;
+  p.probe_src = in;
+  p.probe_vecs = (uint32_t)((size_t)B * e->dims[0] / 4);
+  static const bool probe = getenv("FR_CHAIN_PROBE") && atoi(getenv("FR_CHAIN_PROBE")) != 0;
+  if (probe) return launch_chain<3, true>(e, s->stream, maps, p);
   static const int stages = getenv("FR_CHAIN_STAGES") ? atoi(getenv("FR_CHAIN_STAGES")) : 3;   // experiment knob
   if (stages == 2) return launch_chain<2>(e, s->stream, maps, p);
   return launch_chain<3>(e, s->stream, maps, p);
@@ -1493,6 +1661,7 @@ fr_status frtc_layer(fr_engine* e, fr_stream_s* s, int k, const float* in, int B
   o = a;
   if (k < 2 && (r = get_a_map(e, st, s->d_h[k], e->dims[k + 1], B, kStoreBoxRows, &o)) != FR_OK) return r;
   TcParams p;
+  p.a = in;
   p.bias = act ? e->d_bias[k] : nullptr;
   p.M = B;
   p.N = e->dims[k + 1];
@@ -1509,6 +1678,19 @@ fr_status frtc_layer(fr_engine* e, fr_stream_s* s, int k, const float* in, int B
   const CUtensorMap& w = (st->auto_tiles && k < 2 && c.block_n == 128) ? st->w_map64[k] : st->w_map[k];
   p.latency = (st->auto_tiles && B <= kLatencyBatch) ? 1 : 0;
   cudaStream_t cs = s->stream;
+  // throughput-sized batches: two pairs per cluster share every weight slice by TMA multicast (each CTA loads
+  // half of its share: 128-row boxes for 512-wide tiles, 64-row boxes for 256-wide ones)
+  if (st->mcast && st->auto_tiles && B > kLatencyBatch && c.ctas == 2 && c.block_n >= 256) {
+    if (k < 2 && c.block_n == 512) return launch<512, 3, EPI_STORE, 2, 2>(e, a, st->w_map128[k], o, p, pa, cs);
+    if (k < 2) return launch<256, 5, EPI_STORE, 2, 2>(e, a, st->w_map64[k], o, p, pa, cs);
+    return launch<256, 5, EPI_DOT, 2, 2>(e, a, st->w_map64[k], o, p, pa, cs);
+  }
+  // throughput-sized batches on plain pairs: the A operand goes through the LSU (cp.async), TMA carries the weights
+  if (st->a_lsu && st->auto_tiles && B > kLatencyBatch && c.ctas == 2 && c.block_n >= 256) {
+    if (k < 2 && c.block_n == 512) return launch<512, 3, EPI_STORE, 2, 1, true>(e, a, w, o, p, pa, cs);
+    if (k < 2) return launch<256, 5, EPI_STORE, 2, 1, true>(e, a, w, o, p, pa, cs);
+    return launch<256, 5, EPI_DOT, 2, 1, true>(e, a, w, o, p, pa, cs);
+  }
   if (k < 2) {
     if (c.block_n == 512) return launch<512, 3, EPI_STORE, 2>(e, a, w, o, p, pa, cs);
     if (c.ctas == 2) return c.block_n == 256 ? launch<256, 5, EPI_STORE, 2>(e, a, w, o, p, pa, cs) : launch<128, 7, EPI_STORE, 2>(e, a, w, o, p, pa, cs);

@@ -298,10 +298,71 @@ def test_infer_graph_replay_matches_direct():
         # (lookup fused into layer 1) + 2 GEMM launches per batch, replayed or not; 4 with FR_FUSE=0;
         # page-locked index buffers are fetched by a staging kernel instead of a memcpy node (+1)
         per = (3 if os.environ.get("FR_FUSE", "0") == "1" else 4) + \
-              (1 if kind == "pinned" and os.environ.get("FR_ZEROCOPY", "0") == "1" else 0)
+              (1 if kind == "pinned" and os.environ.get("FR_ZEROCOPY", "0") != "0" else 0)
         assert eng.launch_count() - l0 == 4 * per
     w.close()
     eng.close()
+
+
+@pytest.mark.parametrize("model,B,clusters", (("small", 513, 0), ("small", 2048, 0), ("small", 1300, 1),
+                                              ("medium", 4099, 2), ("large", 2304, 3), ("small", 40000, 0)))
+def test_tf32_cp_async_a_operand_bit_identical_to_tma(model, B, clusters, monkeypatch):
+    """Throughput-sized batches feed the A operand through the LSU: four loader warps copy every 128 x 32
+    activation slice with 16-byte cp.async into the 128B-swizzled slot TMA would have filled (zero fill past
+    the batch and past K: medium has K = 880 = 27.5 slices), post one arrival per warp on the pair leader's
+    full barrier after fence.proxy.async, and TMA carries the weights only.  Same MMAs, same order: the scores
+    must be identical bit for bit to FR_TC_ALSU=0 (everything through TMA); capped grids wrap the ring."""
+    if clusters:
+        monkeypatch.setenv("FR_TC_MAX_CLUSTERS", str(clusters))
+    else:
+        monkeypatch.delenv("FR_TC_MAX_CLUSTERS", raising=False)
+    cat = catalogue.load(model).with_row_cap(64)
+    dims = cat.layer_dims
+    W, b = oracle.make_weights(dims, seed=33)
+    x = np.random.default_rng(B).uniform(-1, 1, (B, dims[0])).astype(np.float32)
+    got = {}
+    for v in ("1", "0"):
+        monkeypatch.setenv("FR_TC_ALSU", v)
+        eng = fleetrec.Engine(cat, max_batch=B)
+        eng.load_mlp(W, b)
+        for _ in range(3):
+            got[v] = eng.mlp_only(x)
+        eng.close()
+    monkeypatch.delenv("FR_TC_ALSU", raising=False)
+    monkeypatch.delenv("FR_TC_MAX_CLUSTERS", raising=False)
+    assert_bits_equal(got["1"], got["0"])
+    assert rel_err(got["1"], oracle.mlp(x, dims, W, b, mode=1)) <= TOL
+
+
+@pytest.mark.parametrize("model,B,clusters", (("small", 513, 0), ("small", 2048, 0), ("small", 1300, 1),
+                                              ("medium", 4099, 2), ("large", 2304, 3), ("small", 40000, 0)))
+def test_tf32_multicast_clusters_bit_identical_to_pair_clusters(model, B, clusters, monkeypatch):
+    """FR_TC_MCAST=1: throughput-sized batches run in 4-CTA clusters: two MMA pairs on adjacent 256-row tiles share every
+    weight slice by TMA multicast (each CTA loads half of its share and multicasts it to the CTA of its
+    parity in the other pair; a smem slot is refilled only after BOTH pairs released it).  Same MMAs in the
+    same K order as the 2-CTA clusters, so the scores must be identical bit for bit; odd numbers of 256-row
+    tiles leave the second pair of the last cluster with no rows (TMA zero fill / clipped stores); capped
+    grids make the barrier parities wrap."""
+    if clusters:
+        monkeypatch.setenv("FR_TC_MAX_CLUSTERS", str(clusters))
+    else:
+        monkeypatch.delenv("FR_TC_MAX_CLUSTERS", raising=False)
+    cat = catalogue.load(model).with_row_cap(64)
+    dims = cat.layer_dims
+    W, b = oracle.make_weights(dims, seed=31)
+    x = np.random.default_rng(B).uniform(-1, 1, (B, dims[0])).astype(np.float32)
+    got = {}
+    for mc in ("1", "0"):
+        monkeypatch.setenv("FR_TC_MCAST", mc)
+        eng = fleetrec.Engine(cat, max_batch=B)
+        eng.load_mlp(W, b)
+        for _ in range(3):
+            got[mc] = eng.mlp_only(x)
+        eng.close()
+    monkeypatch.delenv("FR_TC_MCAST", raising=False)
+    monkeypatch.delenv("FR_TC_MAX_CLUSTERS", raising=False)
+    assert_bits_equal(got["1"], got["0"])
+    assert rel_err(got["1"], oracle.mlp(x, dims, W, b, mode=1)) <= TOL
 
 
 @pytest.mark.parametrize("B", (1, 333, 2048))
@@ -316,7 +377,7 @@ def test_pinned_buffers_without_copy_engine_match_memcpy_path(B, monkeypatch):
     tables = oracle.make_tables(cat, "hash", seed=5)
     W, b = oracle.make_weights(dims, seed=42)
     got = {}
-    for zc in ("1", "0"):
+    for zc in ("1", "0", "55"):     # all over PCIe by the SMs | all by the copy engine | split
         monkeypatch.setenv("FR_ZEROCOPY", zc)
         eng = fleetrec.Engine(cat, max_batch=B)
         eng.load_tables(tables)
@@ -338,8 +399,9 @@ def test_pinned_buffers_without_copy_engine_match_memcpy_path(B, monkeypatch):
         w.close()
         eng.close()
     monkeypatch.delenv("FR_ZEROCOPY", raising=False)
-    for a, c in zip(got["1"], got["0"]):
+    for a, c, d in zip(got["1"], got["0"], got["55"]):
         assert_bits_equal(a, c)
+        assert_bits_equal(d, c)
 
 
 @pytest.mark.parametrize("tiles", TILES)

@@ -42,6 +42,8 @@ buf = (C.c_longlong * 256)()
 n = raw.frdbg_chain_timeline(eng._h, buf, 256)
 assert n == 256, "no timeline (FR_CHAIN_PROF / chain kernel not used?)"
 t = np.array(buf[:], dtype=np.int64).reshape(4, 8, 8)
+probe = t[3, 7, :3].copy()
+t[3, 7, :] = 0
 brk = t[0, 4:8, :5].copy()      # iteration 0, rows 4..7: epilogue breakdown of phases 0..3 (cycles, warp 2)
 t[0, 4:8, :] = 0
 t0 = t[t > 0].min()
@@ -58,4 +60,7 @@ print("epilogue warp 2, iteration 0, us per phase: tmem_ld+wait | wait_read<1> |
 for ph in range(4):
     if brk[ph].any():
         print(f"   ph {ph}: " + "  ".join(f"{v / 1965.0:6.2f}" for v in brk[ph]))
+if probe[0]:
+    print(f"probe warps of CTA 0: {probe[0]} iterations x 16 KB in {probe[1] / 1965.0:.1f} us = "
+          f"{probe[0] * 16384 / (probe[1] / 1.965):.1f} GB/s through the LSU")
 eng.close()

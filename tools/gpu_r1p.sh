@@ -1,4 +1,11 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -n 5
+export BENCH_HARD_LIMIT_S=300
+timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "pinned_buffers or graph_replay" 2>&1 | tail -n 5
+summ='import json,sys
+j=json.loads(sys.stdin.read()); print("value %.1f e2e %.1f M/s  step %.2f us e2e %.2f us" % (j["value"]/1e6, j["e2e"]["value"]/1e6, j["ms_per_step"]*1e3, j["e2e"]["ms_per_step"]*1e3), j["host_enqueue_us_per_step"])'
+for z in 30 45 60 75; do
+  echo "=== bench FR_ZEROCOPY=$z"
+  FR_ZEROCOPY=$z timeout 400 python bench.py --cpu-seconds 0 --gather-batch 2048 > gpurun_out/bench_tmp.log 2>&1; echo "exit $?"; tail -n 1 gpurun_out/bench_tmp.log | python -c "$summ"
+done
