@@ -51,6 +51,30 @@ def peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback (B200_PROFILING.md)")
 
 
+def ncu_traffic(kernel_substr):
+    """DRAM bytes per launch (read + write) of the newest committed `ncu --set full` capture of a kernel whose
+    name contains `kernel_substr` (profiles/*_step.csv / *_gather_stress.csv, written by tools/ncu_summary.py);
+    None when no capture is committed.  The capture is of the same command at the same batch size."""
+    import csv
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_step.csv")) +
+                       glob.glob(os.path.join(ROOT, "profiles", "r*_gather_stress.csv"))):
+        rows = list(csv.reader(open(path)))
+        if len(rows) < 2:
+            continue
+        hdr = rows[0]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        cols = []
+        for i, h in enumerate(hdr):
+            if h.startswith("dram__bytes_read.sum") or h.startswith("dram__bytes_write.sum"):
+                cols.append((i, scale.get(h[h.index("[") + 1:-1], 1.0)))
+        vals = [sum(float(r[i]) * k for i, k in cols) for r in rows[1:] if kernel_substr in r[0]]
+        if vals and len(cols) == 2:
+            best = dict(bytes_per_launch=sum(vals) / len(vals), source=os.path.relpath(path, ROOT), launches=len(vals))
+    return best
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -154,8 +178,8 @@ def workload_config(args, n):
             "model_tables": args.model, "batch": args.batch, "global_batch": args.batch * n,
             "streams": args.streams, "mlp_mode": "bias_relu_sigmoid", "precision": args.precision,
             "sharding": "single GPU" if n == 1 else (
-                "tables sharded across ranks (on-chip-class tables replicated), pieces pushed over NVLink by the "
-                "lookup kernel, batch-parallel MLP" if args.shard == "tables" else "replicated tables, independent batches"),
+                "tables sharded across ranks (on-chip-class tables replicated), every rank fed the index columns of its "
+                "own tables, pieces pushed over NVLink by the lookup kernel, batch-parallel MLP" if args.shard == "tables" else "replicated tables, independent batches"),
             "l2": "tables (1.4 GB) exceed L2; a pool of distinct index batches is rotated so no step repeats "
                   "the previous step's inputs"}
 
@@ -212,6 +236,21 @@ def run_ours(args):
     idx_host = [torch.from_numpy(oracle.zipf_indices(cat, Bg, seed=1234 + (0 if sharded else 1000 * rank) + i))
                 .pin_memory() for i in range(pool)]
     idx_dev = [t.cuda(non_blocking=True) for t in idx_host]
+    # sharded: every rank is fed the column slices it needs (fr_shard_infer_sliced) -- the indices of the tables it
+    # owns for ALL items and of the replicated tables for its own items -- sliced on the host outside the timed
+    # region, as the reference's index source feeds every FPGA only its own tables' indices
+    sl_host = sl_dev = None
+    if sharded:
+        def packed(t):   # one pinned buffer, the replicated block right behind the owned one: ONE copy per step
+            o, r = shard.slice_indices(t.numpy(), owner, world, rank)
+            n_o = (o.size + 3) // 4 * 4
+            buf = torch.empty(n_o + r.size, dtype=torch.int32).pin_memory()
+            buf[:o.size] = torch.from_numpy(o.reshape(-1))
+            buf[n_o:] = torch.from_numpy(r.reshape(-1))
+            return buf, (buf[:o.size], buf[n_o:])
+        sl_bufs = [packed(t) for t in idx_host]          # keep the buffers alive
+        sl_host = [views for _, views in sl_bufs]
+        sl_dev = [tuple(a.cuda(non_blocking=True) for a in pair) for pair in sl_host]
     sc_dev = [torch.empty(B, dtype=torch.float32, device="cuda") for _ in range(args.streams)]
     sc_host = [torch.empty(B, dtype=torch.float32).pin_memory() for _ in range(args.streams)]
     torch.cuda.synchronize()
@@ -222,7 +261,7 @@ def run_ours(args):
     lo, hi = (rank * B, (rank + 1) * B) if sharded else (0, B)
     exp_x = oracle.gather_hashed(cat, 0x5EED, i0[lo:hi])
     if sharded:
-        eng.shard_infer(idx_host[0].numpy(), Bg, sc_host[0].numpy(), workers[0])
+        eng.shard_infer_sliced(sl_host[0][0].numpy(), sl_host[0][1].numpy(), Bg, sc_host[0].numpy(), workers[0])
         eng.sync(workers[0])
         dist.barrier()
     else:
@@ -276,18 +315,21 @@ def run_ours(args):
     # attribute lookups (the buffers stay referenced by the lists above)
     p_idx_dev, p_idx_host = [t.data_ptr() for t in idx_dev], [t.data_ptr() for t in idx_host]
     p_sc_dev, p_sc_host = [t.data_ptr() for t in sc_dev], [t.data_ptr() for t in sc_host]
+    if sharded:
+        p_sl_dev = [(a.data_ptr(), r.data_ptr()) for a, r in sl_dev]
+        p_sl_host = [(a.data_ptr(), r.data_ptr()) for a, r in sl_host]
 
     def step_dev(i):
         w = i % args.streams
         if sharded:
-            eng.shard_infer(p_idx_dev[i % pool], Bg, p_sc_dev[w], workers[w])
+            eng.shard_infer_sliced(p_sl_dev[i % pool][0], p_sl_dev[i % pool][1], Bg, p_sc_dev[w], workers[w])
         else:
             eng.infer_async(p_idx_dev[i % pool], p_sc_dev[w], B, workers[w])
 
     def step_e2e(i):
         w = i % args.streams
         if sharded:
-            eng.shard_infer(p_idx_host[i % pool], Bg, p_sc_host[w], workers[w])
+            eng.shard_infer_sliced(p_sl_host[i % pool][0], p_sl_host[i % pool][1], Bg, p_sc_host[w], workers[w])
         else:
             eng.infer_async(p_idx_host[i % pool], p_sc_host[w], B, workers[w])
 
@@ -328,8 +370,17 @@ def run_ours(args):
     names_k, flops_k = per_kernel(kms, flops)
     gather_bytes = B * cat.gather_bytes_per_item(materialised=True)
     tensor_peak = pk["bf16"] / 2 if args.precision == "tf32" else 2 * 148 * 128 * 1.965e-3   # TF/s
+    # SMs every MLP launch occupies (one CTA per SM): a 2048-item batch is 8..32 tiles, so a kernel timed ALONE runs
+    # on 8..32 of the 148 SMs -- `frac` (the contract's definition, against the whole device) is small by
+    # construction; `frac_of_occupied_sms` relates it to the tensor peak of the SMs it actually held, and
+    # roofline.whole_step to what the device sustains with `--streams` batches in flight.
+    import ctypes as C
+    from fleetrec import _capi
+    raw = C.CDLL(_capi.LIB_PATH)
+    raw.frdbg_layer_ctas.argtypes = [C.c_void_p, C.c_int]
+    ctas = [0] + [int(raw.frdbg_layer_ctas(eng._h, k)) for k in range(3)] + [0]
     kernels = []
-    for n, ms, fl in zip(names_k, kms, flops_k):
+    for ki, (n, ms, fl) in enumerate(zip(names_k, kms, flops_k)):
         if ms <= 0:
             continue
         if n == "gather_concat":
@@ -337,16 +388,24 @@ def run_ours(args):
             kernels.append(dict(name=n, ms=ms, bound="hbm", achieved=a, peak=pk["hbm"], unit="GB/s", frac=a / pk["hbm"]))
         else:
             a = fl / (ms * 1e-3) / 1e12
-            kernels.append(dict(name=n, ms=ms, bound="tensor", achieved=a, peak=tensor_peak, unit="TFLOP/s",
-                                frac=a / tensor_peak))
+            k = dict(name=n, ms=ms, bound="tensor", achieved=a, peak=tensor_peak, unit="TFLOP/s", frac=a / tensor_peak)
+            if ctas[ki] > 0 and "chain" not in n:
+                k.update(sms_occupied=ctas[ki], frac_of_occupied_sms=a / (tensor_peak * ctas[ki] / 148.0))
+            kernels.append(k)
     if kms[0] <= 0 and not sharded:            # FR_FUSE=1: no stand-alone lookup, layer 1's kernel does it
         kernels[0]["name"] = "lookup+mlp_layer1 (fused)"
     dom = max(kernels, key=lambda k: k["ms"])
+    # the committed ncu --set full capture of the same command: which kernel instance is the dominant one
+    ncu_name = {"gather_concat": "gather_concat_kernel", "mlp_layer1": "tc_linear_kernel<256, 5, 0",
+                "mlp_layer2": "tc_linear_kernel<512, 3, 0", "mlp_layer3+out": "tc_linear_kernel<256, 5, 1"}.get(dom["name"])
+    tr = ncu_traffic(ncu_name) if (ncu_name and args.model == "small" and B == 2048 and not sharded) else None
     roofline = dict(bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"], unit=dom["unit"], frac=dom["frac"],
-                    traffic=None, kernel=dom["name"], ms_per_launch=dom["ms"],
+                    traffic=tr["bytes_per_launch"] if tr else None, traffic_source=tr["source"] if tr else None,
+                    kernel=dom["name"], ms_per_launch=dom["ms"],
                     peak_source=pk["src"] + ("; tf32 tensor peak taken as half the measured dense bf16 rate"
                                              if dom["bound"] == "tensor" and args.precision == "tf32" else ""),
-                    share_of_step=dom["ms"] / sum(k["ms"] for k in kernels))
+                    share_of_step=dom["ms"] / sum(k["ms"] for k in kernels),
+                    sms_occupied=dom.get("sms_occupied"), frac_of_occupied_sms=dom.get("frac_of_occupied_sms"))
     # the step as a whole: its kernels overlap across the worker streams, so the dominant kernel timed
     # alone (above) understates what the device sustains -- all MLP FLOPs of a step over the step time
     step_tf = world * step_flops / (ms_dev / args.steps * 1e-3) / 1e12 / world
@@ -391,12 +450,18 @@ def run_ours(args):
     eng.close()
     cpu, _ = cpu_port_run(args, 10 ** 9, 1, budget_s=args.cpu_seconds) if args.cpu_seconds > 0 else (None, None)
 
+    # bytes uploaded per (global) step, all ranks together, counted from the tensors copied
+    if sharded:
+        per_rank = [(Bg * len(shard.rank_tables(owner, r)[0]) + B * len(shard.rank_tables(owner, r)[1])) * 4 for r in range(world)]
+    else:
+        per_rank = [B * T * 4] * world
+    h2d_bytes, h2d_rank_max = sum(per_rank), max(per_rank)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "tf32 (fp32 storage, fp32 accumulate)" if args.precision == "tf32" else "f32",
             "data": "synthetic", "config": workload_config(args, world),
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": Bg * T * 4, "d2h_bytes_per_step": B * 4,
-                    "ms_per_step": ms_e2e / args.steps},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": B * 4 * world,
+                    "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_rank_max": h2d_rank_max},
             "gpu_launches": int(launches), "host_enqueue_us_per_step": host_us, "clocks": clocks, "roofline": roofline, "kernels": kernels,
             "gather_standalone": gather, "mlp_large_batch": large, "cpu_baseline": cpu}
     print(json.dumps(line))
@@ -488,6 +553,7 @@ def run_stress(args):
                            "l2": "uniform indices over tables far larger than L2; a pool of 4 index batches rotates"},
                 "gpu_launches": int(2 * (args.steps + max(args.warmup, 3) + 1)),
                 "roofline": {"bound": "hbm", "achieved": u["achieved"], "peak": pk["hbm"], "unit": "GB/s", "frac": u["frac"],
+                             "traffic_ncu": ncu_traffic("gather_concat_kernel<0"),
                              "traffic": None, "kernel": "gather_concat", "ms_per_launch": u["ms_per_launch"],
                              "peak_source": pk["src"], "algorithmic_bytes_per_item": per_item},
                 "uniform": res["uniform"], "zipf": res["zipf"]}

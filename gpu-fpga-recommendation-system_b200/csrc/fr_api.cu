@@ -201,6 +201,7 @@ extern "C" void fr_destroy(fr_engine* e) {
   cudaFree(e->d_fchunks);
   cudaFree(e->d_owned_ids);
   cudaFree(e->d_repl_ids);
+  cudaFree(e->d_chunks_sliced);
   for (int r = 0; r < (int)e->peers.size(); r++)
     if (e->peers[r].ipc && e->peers[r].concat) cudaIpcCloseMemHandle(e->peers[r].concat);
   cudaFree(e->d_peer_ptrs);
@@ -539,12 +540,12 @@ static bool is_capturable_ptr(const void* p) {
 // graph.  `enqueue` issues the step's work on s->stream (it is called directly, or under capture).
 template <class F>
 static fr_status run_or_replay(fr_engine* e, fr_stream_s* s, const void* idx, const void* scores, int B, int variant,
-                               F&& enqueue) {
+                               F&& enqueue, const void* idx2 = nullptr) {
   if (!e->use_graphs) return enqueue();
   fr_stream_s::Graph* g = nullptr;
   for (fr_stream_s::Graph& c : s->graphs)
-    if (c.idx == idx && c.scores == scores && c.B == B && c.mode == e->mlp_mode && c.prec == e->precision &&
-        c.variant == variant)
+    if (c.idx == idx && c.idx2 == idx2 && c.scores == scores && c.B == B && c.mode == e->mlp_mode &&
+        c.prec == e->precision && c.variant == variant)
       g = &c;
   if (g && g->exec) {
     FR_CUDA(e, cudaGraphLaunch(g->exec, s->stream));
@@ -552,8 +553,10 @@ static fr_status run_or_replay(fr_engine* e, fr_stream_s* s, const void* idx, co
     return FR_OK;
   }
   if (!g) {
-    if (s->graphs.size() >= 512 || !is_capturable_ptr(idx) || !is_capturable_ptr(scores)) return enqueue();
-    s->graphs.push_back({idx, scores, B, e->mlp_mode, e->precision, variant, 0, 0, nullptr});
+    if (s->graphs.size() >= 512 || !is_capturable_ptr(idx) || !is_capturable_ptr(scores) ||
+        (idx2 && !is_capturable_ptr(idx2)))
+      return enqueue();
+    s->graphs.push_back({idx, idx2, scores, B, e->mlp_mode, e->precision, variant, 0, 0, nullptr});
     g = &s->graphs.back();
   }
   if (g->seen < 1) {  // first sighting: plain launches (also warms attribute / tensor-map caches)
@@ -930,6 +933,72 @@ extern "C" fr_status fr_shard_infer(fr_engine* e, const int32_t* idx, int B_glob
   const int parity = (++s->shard_step) & 1;
   return run_or_replay(e, s, idx, scores_local, B_global, 1 + parity,
                        [&] { return shard_infer_enqueue(e, s, idx, B_global, scores_local, parity); });
+}
+
+
+// Which tables this rank needs indices for, ascending (= the column order of the sliced blocks): which = 0 the tables
+// it owns (indices of ALL items of the global batch), which = 1 the replicated tables (indices of ITS items only).
+extern "C" fr_status fr_shard_tables(fr_engine* e, int which, int32_t* ids, int* n) {
+  if (!e || !n || which < 0 || which > 1) return fr_fail(e, FR_ERR_INVALID, "fr_shard_tables: bad argument");
+  if (e->owner.empty() && e->world > 1) return fr_fail(e, FR_ERR_STATE, "fr_shard_init first");
+  fr_shard_table_lists(e);
+  const std::vector<int>& v = which == 0 ? e->owned_tables : e->repl_tables;
+  *n = (int)v.size();
+  if (ids)
+    for (size_t i = 0; i < v.size(); i++) ids[i] = v[i];
+  return FR_OK;
+}
+
+// fr_shard_infer fed the way the reference feeds its FPGAs (each receives only its own tables' indices,
+// embedding_47_krnl.cpp:899-914 per bank): idx_owned [B_global][n_owned] for the tables of fr_shard_tables(0),
+// idx_repl [B_global / world][n_repl] for the replicated tables of this rank's own items.  A rank then uploads
+// B_global * n_owned + B_local * n_repl indices per step instead of B_global * T.
+static fr_status shard_infer_sliced_enqueue(fr_engine* e, fr_stream_s* s, const int32_t* idx_owned, const int32_t* idx_repl,
+                                            int B_global, float* scores, int parity) {
+  const int Bl = B_global / e->world;
+  const size_t n_o = (size_t)B_global * e->owned_tables.size(), n_r = (size_t)Bl * e->repl_tables.size();
+  const int32_t* d_o = idx_owned;
+  const int32_t* d_r = idx_repl;
+  int32_t* stage_r = s->d_idx + (n_o + 3) / 4 * 4;   // both blocks fit: n_owned + n_repl <= T
+  if (n_o && n_r && idx_repl == idx_owned + (n_o + 3) / 4 * 4 && !is_device_ptr(idx_owned)) {
+    // one host buffer, the replicated block right behind the owned one (16-byte aligned): ONE copy -- every copy
+    // costs the engine ~5 us on top of its bytes
+    FR_CUDA(e, cudaMemcpyAsync(s->d_idx, idx_owned, ((n_o + 3) / 4 * 4 + n_r) * sizeof(int32_t), cudaMemcpyHostToDevice,
+                               s->stream));
+    d_o = s->d_idx;
+    d_r = stage_r;
+  } else if (n_o && !is_device_ptr(idx_owned)) {
+    FR_CUDA(e, cudaMemcpyAsync(s->d_idx, idx_owned, n_o * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+    d_o = s->d_idx;
+  }
+  if (n_r && d_r == idx_repl && !is_device_ptr(idx_repl)) {
+    FR_CUDA(e, cudaMemcpyAsync(stage_r, idx_repl, n_r * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+    d_r = stage_r;
+  }
+  fr_status st;
+  if ((st = frk_gather_push_sliced(e, d_o, d_r, B_global, s->slot, parity, s->stream)) != FR_OK) return st;
+  if ((st = frk_shard_signal_wait(e, s->slot, s->stream)) != FR_OK) return st;
+  float* d_scores = score_target(e, s, scores, Bl);
+  const float* x = e->d_xchg + fr_xchg_concat_off(e, s->slot, parity);
+  if ((st = run_mlp(e, s, x, Bl, d_scores)) != FR_OK) return st;
+  return emit_scores(e, s, scores, Bl, d_scores);
+}
+
+extern "C" fr_status fr_shard_infer_sliced(fr_engine* e, const int32_t* idx_owned, const int32_t* idx_repl, int B_global,
+                                           float* scores_local, fr_stream s) {
+  fr_status st = prep(e, &s, B_global, true, true);
+  if (st != FR_OK) return st;
+  if ((st = shard_check(e, s, B_global)) != FR_OK) return st;
+  if (B_global == 0) return FR_OK;
+  fr_shard_table_lists(e);
+  if (!scores_local || (!idx_owned && !e->owned_tables.empty()) || (!idx_repl && !e->repl_tables.empty()))
+    return fr_fail(e, FR_ERR_INVALID, "null idx/scores");
+  if (*e->h_shard_err) return fr_fail(e, FR_ERR_STATE, "a previous sharded step timed out waiting for a peer rank");
+  const int parity = (++s->shard_step) & 1;
+  const void* key = idx_owned ? (const void*)idx_owned : (const void*)idx_repl;
+  return run_or_replay(e, s, key, scores_local, B_global, 3 + parity,
+                       [&] { return shard_infer_sliced_enqueue(e, s, idx_owned, idx_repl, B_global, scores_local, parity); },
+                       idx_owned ? idx_repl : nullptr);
 }
 
 

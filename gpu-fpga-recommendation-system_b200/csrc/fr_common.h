@@ -49,9 +49,10 @@ struct fr_stream_s {
   // (idx, scores, B, mode) combination has been seen twice on this worker (launch-bound otherwise).
   struct Graph {
     const void* idx;
+    const void* idx2;       // second index block of the column-sliced sharded step (else null)
     const void* scores;
     int B, mode, prec;
-    int variant;            // 0: fr_infer; 1 / 2: fr_shard_infer with exchange-buffer parity 0 / 1
+    int variant;            // 0: fr_infer; 1 / 2: fr_shard_infer with exchange-buffer parity 0 / 1; 3 / 4: column-sliced
     int seen;               // direct (un-captured) runs so far
     int launches;           // kernels inside the graph
     cudaGraphExec_t exec;   // null until captured
@@ -112,6 +113,8 @@ struct fr_engine {
   float* d_bias[FR_MAX_LAYERS] = {nullptr, nullptr, nullptr, nullptr};
   bool layer_loaded[FR_MAX_LAYERS] = {false, false, false, false};
   void* tc_state = nullptr;  // tensor maps etc., owned by fr_mlp_tc.cu
+  int tc_last_ctas = 0;      // grid of the last tcgen05 GEMM launch, and of the last launch of every MLP step
+  int tc_layer_ctas[4] = {0, 0, 0, 0};
 
   fr_stream_s* default_stream = nullptr;
   std::vector<fr_stream_s*> streams;
@@ -131,6 +134,10 @@ struct fr_engine {
   int n_owned = 0;
   int* d_repl_ids = nullptr;     // pieces of replicated tables (local items only)
   int n_repl = 0;
+  // column-sliced index blocks (fr_shard_infer_sliced): the tables this rank owns / the replicated ones, ascending
+  // = the column order of the caller's blocks, and the piece descriptors with `table` renumbered to those columns
+  std::vector<int> owned_tables, repl_tables;
+  FrChunk* d_chunks_sliced = nullptr;
   bool shard_lists_built = false;
   int* h_shard_err = nullptr;    // pinned+mapped: set to 1 by the wait kernel on time-out
   int* h_watch = nullptr;        // pinned+mapped int[8]: which barrier wait a tcgen05 kernel gave up on before trapping
@@ -164,6 +171,10 @@ fr_status frk_gather(fr_engine* e, const int32_t* d_idx, int B, float* d_out, bo
 // copy `bytes` (a multiple of 16) of indices from a mapped page-locked host buffer into device memory with SM loads
 fr_status frk_stage_idx(fr_engine* e, const void* mapped_src, int32_t* d_dst, size_t bytes, cudaStream_t st);
 fr_status frk_gather_push(fr_engine* e, const int32_t* d_idx, int B_global, int slot, int parity, cudaStream_t st);
+// the same from column-sliced index blocks: d_idx_owned [B_global][owned_tables], d_idx_repl [B_global/world][repl_tables]
+fr_status frk_gather_push_sliced(fr_engine* e, const int32_t* d_idx_owned, const int32_t* d_idx_repl, int B_global, int slot,
+                                 int parity, cudaStream_t st);
+void fr_shard_table_lists(fr_engine* e);   // fills owned_tables / repl_tables from owner[] (idempotent)
 // publish "this rank finished pushing the next step of `slot`" to every peer, then wait for all peers' flags
 fr_status frk_shard_signal_wait(fr_engine* e, int slot, cudaStream_t st);
 // push + replicated lookup + flags in one launch (the exchange of fr_shard_infer)

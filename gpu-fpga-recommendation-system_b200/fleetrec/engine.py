@@ -240,6 +240,19 @@ class Engine:
         """One-call sharded step (device-side sync); scores: [B_global/world]."""
         self._chk(self._L.fr_shard_infer(self._h, _ptr(idx), B_global, _ptr(scores), worker._h if worker else None))
 
+    def shard_tables(self, which):
+        """Table ids this rank needs indices for, ascending: which=0 owned (all items), 1 replicated (its items)."""
+        n = C.c_int(0)
+        self._chk(self._L.fr_shard_tables(self._h, which, None, C.byref(n)))
+        ids = (C.c_int32 * max(n.value, 1))()
+        self._chk(self._L.fr_shard_tables(self._h, which, ids, C.byref(n)))
+        return [int(ids[i]) for i in range(n.value)]
+
+    def shard_infer_sliced(self, idx_owned, idx_repl, B_global, scores, worker=None):
+        """fr_shard_infer from column-sliced blocks: idx_owned [B_global][owned], idx_repl [B_global/world][replicated]."""
+        self._chk(self._L.fr_shard_infer_sliced(self._h, _ptr(idx_owned), _ptr(idx_repl), B_global, _ptr(scores),
+                                                worker._h if worker else None))
+
     def shard_read_concat(self, B_global, worker=None):
         out = np.empty((B_global // self.world, self.model.concat_floats), np.float32)
         self._chk(self._L.fr_shard_read_concat(self._h, B_global, out.ctypes.data, worker._h if worker else None))

@@ -52,6 +52,22 @@ def item_range(B_global, world, rank):
     return rank * per, (rank + 1) * per
 
 
+def rank_tables(owner, rank):
+    """(owned, replicated) table ids of `rank`, ascending -- the column order of its sliced index blocks
+    (what fr_shard_tables reports)."""
+    return ([t for t, o in enumerate(owner) if o == rank], [t for t, o in enumerate(owner) if o == -1])
+
+
+def slice_indices(idx, owner, world, rank):
+    """Column-slice a global index batch [B][T] for one rank, as the reference's index source does per FPGA
+    (each device is sent only its own tables' indices): returns (idx_owned [B][n_owned] over ALL items,
+    idx_repl [B/world][n_repl] over the rank's own items), both C-contiguous int32."""
+    owned, repl = rank_tables(owner, rank)
+    b0, b1 = item_range(idx.shape[0], world, rank)
+    return (np.ascontiguousarray(idx[:, owned], dtype=np.int32),
+            np.ascontiguousarray(idx[b0:b1, repl], dtype=np.int32))
+
+
 def exchange_handles(engine, dist, device=None):
     """All-gather every rank's 64-byte CUDA-IPC handle; returns world*64 bytes."""
     import torch

@@ -197,6 +197,18 @@ fr_status fr_shard_mlp(fr_engine* e, int B_global, float* scores_local, fr_strea
  * world <= 32.  A peer that never arrives makes the wait give up after ~2 s and the
  * next call return FR_ERR_STATE. */
 fr_status fr_shard_infer(fr_engine* e, const int32_t* idx, int B_global, float* scores_local, fr_stream s);
+
+/* The same step fed with column-sliced index blocks -- what every FPGA of the reference receives: only the indices
+ * of its own tables (load_access_idx is instantiated per bank, embedding_47_krnl.cpp:899-914).  fr_shard_tables
+ * returns, ascending (= the column order of the blocks), which = 0: the tables this rank owns, for which it needs
+ * the indices of ALL B_global items; which = 1: the replicated tables, for which it needs the indices of ITS
+ * B_global / world items only (ids may be null to query n).  A rank then uploads B_global * n_owned +
+ * B_local * n_repl indices per step instead of B_global * T.  When idx_repl starts right behind idx_owned in one
+ * host buffer (at the next multiple of 4 ints) both blocks travel in one copy. */
+fr_status fr_shard_tables(fr_engine* e, int which, int32_t* ids, int* n);
+fr_status fr_shard_infer_sliced(fr_engine* e, const int32_t* idx_owned /* [B_global][n_owned] */,
+                                const int32_t* idx_repl /* [B_global / world][n_repl] */, int B_global,
+                                float* scores_local, fr_stream s);
 /* Local concat buffer after the exchange (parity hook), [B_global/world][concat_floats]. */
 fr_status fr_shard_read_concat(fr_engine* e, int B_global, float* concat_local, fr_stream s);
 

@@ -31,6 +31,29 @@ def test_plan_owners_covers_every_float_once(model, world):
     assert shard.plan_owners(cat, world) == owner   # deterministic on every rank
 
 
+@pytest.mark.parametrize("model", ("small", "large"))
+@pytest.mark.parametrize("world", (2, 8))
+def test_column_sliced_index_blocks_cover_the_batch(model, world):
+    """fr_shard_infer_sliced's input: rank r is given [B][owned tables] over all items and [B/world][replicated
+    tables] over its own items.  Together the blocks of all ranks hold every index the un-sliced batch holds that
+    any rank reads, each owned column exactly once, and far fewer indices per rank than B * T."""
+    cat = catalogue.load(model)
+    owner = shard.plan_owners(cat, world)
+    B = 16 * world
+    idx = oracle.uniform_indices(cat.with_row_cap(1000), B, seed=3)
+    seen = np.zeros(cat.n_tables, np.int32)
+    for r in range(world):
+        owned, repl = shard.rank_tables(owner, r)
+        io, ir = shard.slice_indices(idx, owner, world, r)
+        assert io.shape == (B, len(owned)) and ir.shape == (B // world, len(repl))
+        assert io.flags.c_contiguous and ir.flags.c_contiguous and io.dtype == np.int32
+        b0, b1 = shard.item_range(B, world, r)
+        assert np.array_equal(io, idx[:, owned]) and np.array_equal(ir, idx[b0:b1, repl])
+        seen[owned] += 1
+        assert io.size + ir.size < idx.size
+    assert all(seen[t] == (0 if owner[t] == -1 else 1) for t in range(cat.n_tables))
+
+
 def _gloo_worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
@@ -238,4 +261,61 @@ def test_sharded_multi_worker_graph_replay(world):
     for r, e in enumerate(engs):
         for w in workers[r]:
             w.close()
+        e.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", (1, 2))
+def test_sharded_step_from_column_sliced_indices_matches_full_rows(world):
+    """fr_shard_infer_sliced (each rank uploads only [B][owned tables] + [B/world][replicated tables]) gives the
+    bits fr_shard_infer gives from the full [B][T] rows: same lookups, same exchange, same MLP; direct and
+    graph-replayed, from pinned host blocks whose CONTENTS change between steps."""
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch
+    cat = catalogue.load("small").with_row_cap(5000)
+    dims = cat.layer_dims
+    owner = shard.plan_owners(cat, world)
+    tables = oracle.make_tables(cat, "hash", seed=29)
+    W, b = oracle.make_weights(dims, seed=42)
+    B, per = 1024, 1024 // world
+    engs = []
+    for r in range(world):
+        e = fleetrec.Engine(cat, device=r, max_batch=B)
+        e.shard_init(r, world, owner)
+        for t in cat.tables:
+            e.load_table(t.id, tables[t.id])
+        e.load_mlp(W, b)
+        engs.append(e)
+    for e in engs:
+        e.shard_attach_local(engs)
+    for r, e in enumerate(engs):
+        assert (e.shard_tables(0), e.shard_tables(1)) == shard.rank_tables(owner, r)
+    full = torch.empty((B, cat.n_tables), dtype=torch.int32).pin_memory()
+    blocks = []
+    for r in range(world):
+        o, p = shard.slice_indices(np.zeros((B, cat.n_tables), np.int32), owner, world, r)
+        blocks.append((torch.from_numpy(o.copy()).pin_memory(), torch.from_numpy(p.copy()).pin_memory()))
+    out_full = [torch.empty(per, dtype=torch.float32).pin_memory() for _ in engs]
+    out_sl = [torch.empty(per, dtype=torch.float32).pin_memory() for _ in engs]
+    for step in range(5):
+        idx = oracle.zipf_indices(cat, B, seed=700 + step)
+        full.copy_(torch.from_numpy(idx))
+        for r in range(world):
+            o, p = shard.slice_indices(idx, owner, world, r)
+            blocks[r][0].copy_(torch.from_numpy(o))
+            blocks[r][1].copy_(torch.from_numpy(p))
+        for r, e in enumerate(engs):
+            e.shard_infer(full.numpy(), B, out_full[r].numpy())
+        for e in engs:
+            e.sync()
+        for r, e in enumerate(engs):
+            e.shard_infer_sliced(blocks[r][0].numpy(), blocks[r][1].numpy(), B, out_sl[r].numpy())
+        for e in engs:
+            e.sync()
+        exp = oracle.mlp(oracle.gather(cat, tables, idx), dims, W, b, mode=1)
+        got = np.concatenate([t.numpy() for t in out_sl])
+        assert np.array_equal(got.view(np.uint32), np.concatenate([t.numpy() for t in out_full]).view(np.uint32)), step
+        assert float(np.max(np.abs(got - exp) / np.maximum(np.abs(exp), 1e-6))) <= 1e-3, step
+    for e in engs:
         e.close()

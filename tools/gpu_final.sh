@@ -4,6 +4,7 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 R=${ROUND:-r01}
+export BENCH_HARD_LIMIT_S=500
 run() { name=$1; shift; echo "=== $name"; timeout "$@" > gpurun_out/$name.log 2>&1; echo "exit $? ($name)"; tail -n ${TAILN:-1} gpurun_out/$name.log | cut -c1-${CUT:-400}; }
 TAILN=3 run t_all 900 python -m pytest tests -q -m gpu
 run smoke 300 python -c "import __graft_entry__ as g; g.smoke()"
@@ -13,8 +14,10 @@ run host 300 gpu-fpga-recommendation-system_b200/host/fleetrec_host small 2048 2
 run stress_$R 600 python bench.py --workload stress
 run sweep_$R 600 python bench.py --workload sweep
 run cublas_$R 300 python tools/cublas_ref.py small
-FR_FUSE=1 run bench_fused_$R 300 python bench.py --cpu-seconds 0
+FR_CHAIN=1 run bench_chain_$R 300 python bench.py --cpu-seconds 0
 run bench_medium_$R 300 python bench.py --model medium --cpu-seconds 0 --steps 1000
+FR_CHAIN=1 FR_CHAIN_PROF=1 run chain_timeline_$R 120 python tools/chain_timeline.py small 2048
+run pcie_$R 200 python tools/pcie_probe.py
 # ncu: launch list of the bench command, then full captures
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 480 --csv \
   --log-file gpurun_out/launches_$R.csv python bench.py --steps 100 --warmup 5 --cpu-seconds 0 --kernel-reps 2 > gpurun_out/ncu_launch_$R.log 2>&1
