@@ -553,7 +553,7 @@ def run_stress(args):
                            "l2": "uniform indices over tables far larger than L2; a pool of 4 index batches rotates"},
                 "gpu_launches": int(2 * (args.steps + max(args.warmup, 3) + 1)),
                 "roofline": {"bound": "hbm", "achieved": u["achieved"], "peak": pk["hbm"], "unit": "GB/s", "frac": u["frac"],
-                             "traffic_ncu": ncu_traffic("gather_concat_kernel<0"),
+                             "traffic_ncu": ncu_traffic("gather_concat_kernel<0"),   # same launch shape, 1 M-row tables
                              "traffic": None, "kernel": "gather_concat", "ms_per_launch": u["ms_per_launch"],
                              "peak_source": pk["src"], "algorithmic_bytes_per_item": per_item},
                 "uniform": res["uniform"], "zipf": res["zipf"]}
