@@ -271,7 +271,8 @@ def run_ours(args):
         eng.sync(workers[0])
     exp_s = oracle.mlp(exp_x, dims, W, b, mode=1)
     gate_err = float(np.max(np.abs(sc_host[0].numpy() - exp_s) / np.maximum(np.abs(exp_s), 1e-6)))
-    assert gate_err <= (1e-3 if args.precision == "tf32" else 2e-5), f"score parity gate failed: {gate_err}"
+    if not os.environ.get("FR_SHARD_NOWAIT"):   # (timing experiment that makes the exchange racy on purpose)
+        assert gate_err <= (1e-3 if args.precision == "tf32" else 2e-5), f"score parity gate failed: {gate_err}"
 
     host_us = {}   # host time to enqueue one step (if it approaches ms_per_step the host, not the GPU, is the limit)
 

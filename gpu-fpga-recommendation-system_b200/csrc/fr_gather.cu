@@ -616,6 +616,8 @@ fr_status frk_shard_signal_wait(fr_engine* e, int slot, cudaStream_t st) {
   int* d_err = nullptr;
   FR_CUDA(e, cudaHostGetDevicePointer(&d_err, e->h_shard_err, 0));
   static const bool nowait = getenv("FR_SHARD_NOWAIT") != nullptr;   // timing experiments only: results are then racy
+  static const bool noflags = getenv("FR_SHARD_NOWAIT") && atoi(getenv("FR_SHARD_NOWAIT")) == 2;   // no flag kernel at all
+  if (noflags) return FR_OK;
   shard_signal_wait_kernel<<<1, 32, 0, st>>>(e->d_peer_ptrs, (long long)fr_xchg_flags_off(e, slot), e->rank, e->world,
                                              e->d_step + slot, d_err, nowait ? -1ll : 20000000000ll /* ~10 s at 1.9 GHz */);
   e->launches++;
