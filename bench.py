@@ -407,6 +407,44 @@ def run_ours(args):
                                              if dom["bound"] == "tensor" and args.precision == "tf32" else ""),
                     share_of_step=dom["ms"] / sum(k["ms"] for k in kernels),
                     sms_occupied=dom.get("sms_occupied"), frac_of_occupied_sms=dom.get("frac_of_occupied_sms"))
+    # every MLP kernel launched on ALL worker streams at once: what that kernel sustains at the occupancy it has
+    # inside the timed region (alone it holds `sms_occupied` SMs)
+    layer_of = {"mlp_layer1": 0, "mlp_layer2": 1, "mlp_layer3+out": 2}
+    if not sharded and any(k["name"] in layer_of for k in kernels):
+        raw.frdbg_enqueue_layer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+
+        def burst(kd, reps):
+            for _ in range(reps):
+                for w in workers:
+                    rc = raw.frdbg_enqueue_layer(eng._h, kd, B, w._h)
+                    assert rc == 0, eng._L.fr_last_error(eng._h)
+        reps_c = 20
+        for k in kernels:
+            if k["name"] not in layer_of:
+                continue
+            kd = layer_of[k["name"]]
+            burst(kd, 3)
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(int(5e6))   # ~2.5 ms gate: the launches below queue up behind it, so the host's launch
+            c0.record(main)               # rate (~4 us per un-graphed launch) is not what is measured
+            for st_ in wstreams:
+                st_.wait_event(c0)
+            burst(kd, reps_c)
+            for st_ in wstreams:
+                ev = torch.cuda.Event()
+                ev.record(st_)
+                main.wait_event(ev)
+            c1.record(main)
+            torch.cuda.synchronize()
+            ms_eff = c0.elapsed_time(c1) / (reps_c * len(workers))
+            a_c = flops_k[1 + kd] / (ms_eff * 1e-3) / 1e12
+            k["at_step_occupancy"] = dict(
+                achieved=a_c, peak=tensor_peak, unit="TFLOP/s", frac=a_c / tensor_peak, ms_per_launch_effective=ms_eff,
+                note="the same kernel on all %d worker streams at once, %d launches: FLOPs of all launches / elapsed" %
+                     (len(workers), reps_c * len(workers)))
+        if "at_step_occupancy" in dom:
+            roofline["at_step_occupancy"] = dom["at_step_occupancy"]
     # the step as a whole: its kernels overlap across the worker streams, so the dominant kernel timed
     # alone (above) understates what the device sustains -- all MLP FLOPs of a step over the step time
     step_tf = world * step_flops / (ms_dev / args.steps * 1e-3) / 1e12 / world

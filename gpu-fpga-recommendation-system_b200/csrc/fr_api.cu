@@ -654,6 +654,17 @@ extern "C" fr_status fr_layer_only(fr_engine* e, int k, const float* x, int B, f
   return FR_OK;
 }
 
+// Debug hook (bench.py binds it by name): enqueue MLP step k alone on a worker, on whatever its activation
+// buffers hold, with no copies and no synchronisation -- so a bench can run one kernel on all workers at once and
+// see what it sustains at the occupancy of the real step.
+extern "C" fr_status frdbg_enqueue_layer(fr_engine* e, int k, int B, fr_stream s) {
+  fr_status st = prep(e, &s, B, false, true);
+  if (st != FR_OK) return st;
+  if (k < 0 || k >= mlp_steps(e) || B <= 0) return fr_fail(e, FR_ERR_INVALID, "frdbg_enqueue_layer: bad argument");
+  const float* out = nullptr;
+  return run_mlp_step(e, s, k, k == 0 ? s->d_x : s->d_h[k - 1], B, s->d_scores, &out);
+}
+
 extern "C" fr_status fr_sync(fr_engine* e, fr_stream s) {
   if (!e) return fr_fail(nullptr, FR_ERR_INVALID, "null engine");
   if (!s) s = e->default_stream;
