@@ -500,8 +500,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int i = et; i < BLOCK_N; i += 128) s_w4[i] = p.w4[i];
   }
   tc_fence_before();
-  if (CTAS == 2) cluster_sync_all();   // peer barriers must exist before any remote complete_tx / commit
-  else __syncthreads();
+  __syncthreads();                     // CTA-level order of the barrier inits, the staged bias and tcgen05.alloc's write of
+  if (CTAS == 2) cluster_sync_all();   // tmem_ptr; peer barriers must exist before any remote complete_tx / commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   if (p.pdl) griddep_wait();           // activations of the previous kernel are complete and visible from here
@@ -827,6 +827,7 @@ tc_mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p)
     for (int i = et; i < 256; i += kChainEpiWarps * 32) s_w4[i] = p.w4[i];
   }
   tc_fence_before();
+  __syncthreads();
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
@@ -1120,6 +1121,7 @@ tc_gather_linear_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid
     for (int i = threadIdx.x - kEpiWarp0 * 32; i < p.N; i += 128) s_bias[i] = p.bias ? p.bias[i] : 0.f;
   }
   tc_fence_before();
+  __syncthreads();
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
