@@ -987,10 +987,14 @@ static fr_status shard_infer_sliced_enqueue(fr_engine* e, fr_stream_s* s, const 
     d_r = stage_r;
   }
   fr_status st;
-  if ((st = frk_gather_push_sliced(e, d_o, d_r, B_global, s->slot, parity, s->stream)) != FR_OK) return st;
+  // experiment (FR_SHARD_PRIVATE=1, only when this rank owns no table, i.e. nothing is pushed): concat vectors in the
+  // worker's private buffer instead of the peer-mapped exchange region
+  static const bool priv_env = getenv("FR_SHARD_PRIVATE") && atoi(getenv("FR_SHARD_PRIVATE")) != 0;
+  const bool priv = priv_env && e->owned_tables.empty();
+  if ((st = frk_gather_push_sliced(e, d_o, d_r, B_global, s->slot, parity, s->stream, priv ? s->d_x : nullptr)) != FR_OK) return st;
   if ((st = frk_shard_signal_wait(e, s->slot, s->stream)) != FR_OK) return st;
   float* d_scores = score_target(e, s, scores, Bl);
-  const float* x = e->d_xchg + fr_xchg_concat_off(e, s->slot, parity);
+  const float* x = priv ? s->d_x : e->d_xchg + fr_xchg_concat_off(e, s->slot, parity);
   if ((st = run_mlp(e, s, x, Bl, d_scores)) != FR_OK) return st;
   return emit_scores(e, s, scores, Bl, d_scores);
 }

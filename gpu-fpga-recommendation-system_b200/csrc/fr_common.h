@@ -173,7 +173,7 @@ fr_status frk_stage_idx(fr_engine* e, const void* mapped_src, int32_t* d_dst, si
 fr_status frk_gather_push(fr_engine* e, const int32_t* d_idx, int B_global, int slot, int parity, cudaStream_t st);
 // the same from column-sliced index blocks: d_idx_owned [B_global][owned_tables], d_idx_repl [B_global/world][repl_tables]
 fr_status frk_gather_push_sliced(fr_engine* e, const int32_t* d_idx_owned, const int32_t* d_idx_repl, int B_global, int slot,
-                                 int parity, cudaStream_t st);
+                                 int parity, cudaStream_t st, float* private_out = nullptr);
 void fr_shard_table_lists(fr_engine* e);   // fills owned_tables / repl_tables from owner[] (idempotent)
 // publish "this rank finished pushing the next step of `slot`" to every peer, then wait for all peers' flags
 fr_status frk_shard_signal_wait(fr_engine* e, int slot, cudaStream_t st);

@@ -430,7 +430,7 @@ fr_status frk_gather_push(fr_engine* e, const int32_t* d_idx, int B_global, int 
 // The same step fed by column-sliced index blocks (what each FPGA of the reference receives: only its own tables'
 // indices): the push reads [B_global][owned tables], the replicated lookup [B_global / world][replicated tables].
 fr_status frk_gather_push_sliced(fr_engine* e, const int32_t* d_idx_owned, const int32_t* d_idx_repl, int B_global, int slot,
-                                 int parity, cudaStream_t st) {
+                                 int parity, cudaStream_t st, float* private_out) {
   if (!e->shard_lists_built) {
     std::lock_guard<std::mutex> g(e->mu);
     if (!e->shard_lists_built) {
@@ -451,7 +451,8 @@ fr_status frk_gather_push_sliced(fr_engine* e, const int32_t* d_idx_owned, const
     e->launches++;
   }
   if (e->n_repl) {
-    float4* own = reinterpret_cast<float4*>(e->d_xchg) + off4 - (long long)e->rank * per * (e->D / 4);
+    float4* own = (private_out ? reinterpret_cast<float4*>(private_out) : reinterpret_cast<float4*>(e->d_xchg) + off4) -
+                  (long long)e->rank * per * (e->D / 4);
     const int b0 = e->rank * per, b1 = (e->rank + 1) * per;
     // the block holds this rank's items only: row 0 is global item b0
     const int32_t* base = d_idx_repl - (size_t)b0 * n_rt;
