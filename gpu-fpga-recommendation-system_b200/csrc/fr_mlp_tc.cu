@@ -402,8 +402,6 @@ struct SmemLayout {
 
 struct TcParams {
   const float* a;      // [M][K] activations (A_LSU kernels read them with cp.async; the others through tmap_a)
-  float* y;            // EPI_STORE: [M][N] output activations (written through tmap_out, or directly when lsu_store)
-  int lsu_store;       // EPI_STORE: write the output with st.global from the staging buffer instead of TMA stores
   const float* bias;   // [N] or null
   float* out;          // EPI_DOT: scores [M]  (EPI_STORE writes through tmap_out)
   const float* w4;     // EPI_DOT: output-layer weights [N]
@@ -655,24 +653,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int c = 0; c < BLOCK_N; c += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + c, r);
-        if (EPI == EPI_STORE && p.lsu_store) {
-          // Stores through the LSU: the TMA unit is the bottleneck of these kernels (it takes in ~33 B/clk and a
-          // layer-1 tile stores 128 KB for every 352 KB it loads), the LSU is idle.  The staging buffer transposes
-          // as before; then 8 lanes read one 128-byte row piece by piece and the warp writes 4 full lines per
-          // instruction.  Two buffers alternate, so one __syncwarp per chunk orders reuse.
-          const uint32_t buf = smem_u32(store_buf + (sc & 1) * kStoreBufBytes);
-          epi_chunk_to_smem(r, smem_u32(s_bias + n0 + c), buf, lane, p.relu);
-          __syncwarp();
-          const int piece = lane & 7, rq = lane >> 3;
-          float* dst = p.y + (size_t)(row0 + rq) * p.N + n0 + c + piece * 4;
-#pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const int rr = rq + 4 * i;
-            const float4 v = lds128(buf + rr * 128 + ((piece ^ (rr & 7)) << 4));
-            if (row0 + rr < p.M) *reinterpret_cast<float4*>(dst + (size_t)(4 * i) * p.N) = v;
-          }
-          sc++;
-        } else if (EPI == EPI_STORE) {
+        if (EPI == EPI_STORE) {
           uint8_t* buf = store_buf + (sc & 1) * kStoreBufBytes;
           if (lane == 0) bulk_wait_read<1>();   // the store issued two chunks ago no longer reads `buf`
           __syncwarp();
@@ -1306,10 +1287,6 @@ struct TcState {
   // FR_TC_MCAST=1: 4-CTA multicast clusters for throughput-sized batches.  Off by default: parity-green, but not
   // faster -- halving the bytes every SM ISSUES changed nothing (layer 2, batch 2048: 28.8 us either way; batch
   // 16384: 37.8 against 34.7 us), so the ~33 B/clk an SM takes in is an ingest limit, and 4-CTA clusters pack worse.
-  // FR_TC_LSU_STORE: 0 = TMA stores everywhere (default), 1 = st.global stores for tiles <= 256 wide, 2 = everywhere.
-  // Measured neutral (layer 1, batch 2048: 22.6 us either way; 219 / 222 / 217 M inferences/s for 1 / 0 / 2): the
-  // stores were not what the TMA unit was short of.
-  int lsu_store = 0;
   bool mcast = false;
   // FR_TC_ALSU=1: the A operand of throughput-sized batches through cp.async (LSU) instead of TMA.  Off by default:
   // parity-green (bit-identical) but slower -- 0.85 us per K slice whatever the stage count (layer 2, batch 2048:
@@ -1509,7 +1486,6 @@ fr_status frtc_prepare(fr_engine* e) {
     for (int k = 0; k < 3; k++)
       if ((s = encode_2d(e, st, &st->w_map64[k], e->d_Wt[k], e->dims[k + 1], e->dims[k], 64)) != FR_OK) return s;
     if (const char* env = getenv("FR_TC_MCAST")) st->mcast = atoi(env) != 0;
-    if (const char* env = getenv("FR_TC_LSU_STORE")) st->lsu_store = atoi(env);
     if (const char* env = getenv("FR_TC_ALSU")) st->a_lsu = atoi(env) != 0;
     for (int k = 0; k < 3; k++)
       if ((s = encode_2d(e, st, &st->w_map128[k], e->d_Wt[k], e->dims[k + 1], e->dims[k], 128)) != FR_OK) return s;
@@ -1697,7 +1673,6 @@ static fr_status frtc_layer_impl(fr_engine* e, fr_stream_s* s, int k, const floa
   if (k < 2 && (r = get_a_map(e, st, s->d_h[k], e->dims[k + 1], B, kStoreBoxRows, &o)) != FR_OK) return r;
   TcParams p;
   p.a = in;
-  p.y = k < 2 ? s->d_h[k] : nullptr;
   p.bias = act ? e->d_bias[k] : nullptr;
   p.M = B;
   p.N = e->dims[k + 1];
@@ -1711,7 +1686,6 @@ static fr_status frtc_layer_impl(fr_engine* e, fr_stream_s* s, int k, const floa
   p.out = d_scores;
   TcLayerCfg c = st->cfg[k];
   if (st->auto_tiles && k < 2) c.block_n = pick_block_n(e, k, B);   // same 128-row weight boxes for 256 and 512
-  p.lsu_store = (st->lsu_store == 2 || (st->lsu_store == 1 && c.block_n <= 256)) ? 1 : 0;
   const CUtensorMap& w = (st->auto_tiles && k < 2 && c.block_n == 128) ? st->w_map64[k] : st->w_map[k];
   p.latency = (st->auto_tiles && B <= kLatencyBatch) ? 1 : 0;
   cudaStream_t cs = s->stream;
