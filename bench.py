@@ -370,7 +370,8 @@ def run_ours(args):
     step_flops = sum(flops[1:4])
     names_k, flops_k = per_kernel(kms, flops)
     gather_bytes = B * cat.gather_bytes_per_item(materialised=True)
-    tensor_peak = pk["bf16"] / 2 if args.precision == "tf32" else 2 * 148 * 128 * 1.965e-3   # TF/s
+    f16_ops = os.environ.get("FR_TC_F16", "0") == "1" and args.precision == "tf32"   # experimental fp16-operand path
+    tensor_peak = pk["bf16"] if f16_ops else (pk["bf16"] / 2 if args.precision == "tf32" else 2 * 148 * 128 * 1.965e-3)   # TF/s
     # SMs every MLP launch occupies (one CTA per SM): a 2048-item batch is 8..32 tiles, so a kernel timed ALONE runs
     # on 8..32 of the 148 SMs -- `frac` (the contract's definition, against the whole device) is small by
     # construction; `frac_of_occupied_sms` relates it to the tensor peak of the SMs it actually held, and
@@ -403,7 +404,8 @@ def run_ours(args):
     roofline = dict(bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"], unit=dom["unit"], frac=dom["frac"],
                     traffic=tr["bytes_per_launch"] if tr else None, traffic_source=tr["source"] if tr else None,
                     kernel=dom["name"], ms_per_launch=dom["ms"],
-                    peak_source=pk["src"] + ("; tf32 tensor peak taken as half the measured dense bf16 rate"
+                    peak_source=pk["src"] + ("; fp16 operands: the dense bf16 / fp16 rate" if f16_ops and dom["bound"] == "tensor"
+                                             else "; tf32 tensor peak taken as half the measured dense bf16 rate"
                                              if dom["bound"] == "tensor" and args.precision == "tf32" else ""),
                     share_of_step=dom["ms"] / sum(k["ms"] for k in kernels),
                     sms_occupied=dom.get("sms_occupied"), frac_of_occupied_sms=dom.get("frac_of_occupied_sms"))
@@ -497,7 +499,8 @@ def run_ours(args):
     h2d_bytes, h2d_rank_max = sum(per_rank), max(per_rank)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32 (fp32 storage, fp32 accumulate)" if args.precision == "tf32" else "f32",
+            "dtype": ("f16 operands (experimental FR_TC_F16; fp32 accumulate)" if os.environ.get("FR_TC_F16", "0") == "1"
+                      else "tf32 (fp32 storage, fp32 accumulate)") if args.precision == "tf32" else "f32",
             "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": B * 4 * world,
                     "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_rank_max": h2d_rank_max},

@@ -116,6 +116,7 @@ static void free_stream(fr_stream_s* s) {
     if (g.exec) cudaGraphExecDestroy(g.exec);
   cudaFree(s->d_idx);
   cudaFree(s->d_x);
+  cudaFree(s->d_x32);
   for (int k = 0; k < 3; k++) cudaFree(s->d_h[k]);
   cudaFree(s->d_scores);
   if (s->ev[0]) cudaEventDestroy(s->ev[0]);
@@ -164,6 +165,7 @@ extern "C" fr_status fr_create(const fr_model_desc* desc, int n_gpus, const int*
   if (const char* env = getenv("FR_GRAPHS")) e->use_graphs = atoi(env) != 0;
   if (const char* env = getenv("FR_PDL")) e->pdl_mask = atoi(env) & 7;
   if (const char* env = getenv("FR_FUSE")) e->fuse_lookup = atoi(env) != 0;
+  if (const char* env = getenv("FR_TC_F16")) e->tc_f16 = atoi(env) != 0 && e->precision == FR_PREC_TF32;
   if (const char* env = getenv("FR_ZEROCOPY")) {
     const int v = atoi(env);
     e->zero_copy_pct = v == 1 ? 100 : (v < 0 ? 0 : (v > 100 ? 100 : v));
@@ -195,6 +197,7 @@ extern "C" void fr_destroy(fr_engine* e) {
   for (int k = 0; k < FR_MAX_LAYERS; k++) {
     cudaFree(e->d_W[k]);
     cudaFree(e->d_Wt[k]);
+    cudaFree(e->d_Wt16[k]);
     cudaFree(e->d_bias[k]);
   }
   cudaFree(e->d_chunks);
@@ -339,6 +342,10 @@ extern "C" fr_status fr_load_mlp(fr_engine* e, int layer, const float* W, const 
   else FR_CUDA(e, cudaMemsetAsync(e->d_bias[layer], 0, (size_t)out * sizeof(float), e->default_stream->stream));
   fr_status st = frk_transpose_round_tf32(e, e->d_W[layer], in, out, e->d_Wt[layer], e->default_stream->stream);
   if (st != FR_OK) return st;
+  if (e->tc_f16 && layer < 3) {   // the tf32-rounded value has an 11-bit significand: exact in fp16 when in range
+    if (!e->d_Wt16[layer]) FR_CUDA(e, cudaMalloc(&e->d_Wt16[layer], nw * 2));
+    if ((st = frk_to_f16(e, e->d_Wt[layer], e->d_Wt16[layer], (int64_t)nw, e->default_stream->stream)) != FR_OK) return st;
+  }
   FR_CUDA(e, cudaStreamSynchronize(e->default_stream->stream));
   e->layer_loaded[layer] = true;
   return FR_OK;
@@ -520,7 +527,7 @@ static fr_status infer_enqueue(fr_engine* e, fr_stream_s* s, const int32_t* idx,
     }
     return emit_scores(e, s, scores, B, d_scores);
   }
-  if ((st = frk_gather(e, d_idx, B, s->d_x, e->precision == FR_PREC_TF32, s->stream)) != FR_OK) return st;
+  if ((st = frk_gather(e, d_idx, B, s->d_x, e->precision == FR_PREC_TF32, s->stream, fr_tc_f16(e))) != FR_OK) return st;
   if ((st = run_mlp(e, s, s->d_x, B, d_scores)) != FR_OK) return st;
   return emit_scores(e, s, scores, B, d_scores);
 }
@@ -627,7 +634,15 @@ extern "C" fr_status fr_mlp_only(fr_engine* e, const float* x, int B, float* sco
   if (B == 0) return FR_OK;
   if (!x || !scores) return fr_fail(e, FR_ERR_INVALID, "null x/scores");
   const float* d_x = x;
-  if (!is_device_ptr(x)) {
+  if (fr_tc_f16(e)) {   // the tcgen05 path wants fp16 rows: land fp32 input next to the worker's buffers, convert
+    if (!is_device_ptr(x)) {
+      if (!s->d_x32) FR_CUDA(e, cudaMalloc(&s->d_x32, (size_t)e->max_batch * e->D * sizeof(float)));
+      FR_CUDA(e, cudaMemcpyAsync(s->d_x32, x, (size_t)B * e->D * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+      d_x = s->d_x32;
+    }
+    if ((st = frk_to_f16(e, d_x, s->d_x, (int64_t)B * e->D, s->stream)) != FR_OK) return st;
+    d_x = s->d_x;
+  } else if (!is_device_ptr(x)) {
     FR_CUDA(e, cudaMemcpyAsync(s->d_x, x, (size_t)B * e->D * sizeof(float), cudaMemcpyHostToDevice, s->stream));
     d_x = s->d_x;
   }
@@ -640,6 +655,7 @@ extern "C" fr_status fr_layer_only(fr_engine* e, int k, const float* x, int B, f
   fr_status st = prep(e, &s, B, false, true);
   if (st != FR_OK) return st;
   if (k < 0 || k >= mlp_steps(e)) return fr_fail(e, FR_ERR_INVALID, "fr_layer_only: step %d of %d", k, mlp_steps(e));
+  if (fr_tc_f16(e)) return fr_fail(e, FR_ERR_UNSUPPORTED, "fr_layer_only takes fp32 activations; the engine runs FR_TC_F16");
   if (B == 0) return FR_OK;
   if (!x || !y) return fr_fail(e, FR_ERR_INVALID, "null x/y");
   const bool last = (k == mlp_steps(e) - 1);
@@ -730,7 +746,7 @@ extern "C" fr_status fr_time_kernels(fr_engine* e, const int32_t* idx, int B, in
     } else if (e->world == 1) {
       FR_CUDA(e, cudaEventRecord(e0, s->stream));
       for (int r = 0; r < reps; r++)
-        if ((st = frk_gather(e, d_idx, B, s->d_x, round, s->stream)) != FR_OK) return st;
+        if ((st = frk_gather(e, d_idx, B, s->d_x, round, s->stream, fr_tc_f16(e))) != FR_OK) return st;
       FR_CUDA(e, cudaEventRecord(e1, s->stream));
       FR_CUDA(e, cudaEventSynchronize(e1));
       FR_CUDA(e, cudaEventElapsedTime(&ms5[0], e0, e1));

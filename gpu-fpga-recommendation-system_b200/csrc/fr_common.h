@@ -42,6 +42,7 @@ struct fr_stream_s {
   cudaStream_t stream = nullptr;
   int32_t* d_idx = nullptr;   // [max_batch][T]
   float* d_x = nullptr;       // [max_batch][D]      concat activations
+  float* d_x32 = nullptr;     // tc_f16: landing zone of fr_mlp_only's fp32 input before the conversion
   float* d_h[3] = {nullptr, nullptr, nullptr};  // [max_batch][hidden k]
   float* d_scores = nullptr;  // [max_batch]
   cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -110,6 +111,11 @@ struct fr_engine {
 
   float* d_W[FR_MAX_LAYERS] = {nullptr, nullptr, nullptr, nullptr};    // [in][out] fp32 (reference layout)
   float* d_Wt[FR_MAX_LAYERS] = {nullptr, nullptr, nullptr, nullptr};   // [out][in] tf32-rounded (tcgen05 B operand)
+  void* d_Wt16[FR_MAX_LAYERS] = {nullptr, nullptr, nullptr, nullptr};  // the same as fp16 (tc_f16)
+  // FR_TC_F16=1 (experimental): the tcgen05 path computes on fp16 operands / activations (kind::f16, FP32
+  // accumulate): the 11-bit significand TF32 keeps, in half the bytes, within fp16's range.  Single-GPU fr_infer
+  // and fr_mlp_only only; the chain / fused / multicast / cp.async variants and fr_layer_only stay TF32-only.
+  bool tc_f16 = false;
   float* d_bias[FR_MAX_LAYERS] = {nullptr, nullptr, nullptr, nullptr};
   bool layer_loaded[FR_MAX_LAYERS] = {false, false, false, false};
   void* tc_state = nullptr;  // tensor maps etc., owned by fr_mlp_tc.cu
@@ -147,6 +153,8 @@ struct fr_engine {
 };
 
 fr_status fr_fail(const fr_engine* e, fr_status code, const char* fmt, ...);
+// the tcgen05 path runs on fp16 operands (FR_TC_F16=1 and the engine's precision is the tensor-core one)
+inline bool fr_tc_f16(const fr_engine* e) { return e->tc_f16 && e->precision == FR_PREC_TF32 && e->world == 1; }
 #define FR_CUDA(e, call)                                                                          \
   do {                                                                                            \
     cudaError_t err__ = (call);                                                                   \
@@ -167,7 +175,10 @@ inline cudaError_t fr_h2d(fr_engine* e, void* dst, const void* src, size_t bytes
 
 // ---- kernels (each returns after enqueueing; bumps e->launches) -----------
 fr_status frk_upload_chunks(fr_engine* e);
-fr_status frk_gather(fr_engine* e, const int32_t* d_idx, int B, float* d_out, bool round_tf32, cudaStream_t st);
+fr_status frk_gather(fr_engine* e, const int32_t* d_idx, int B, float* d_out, bool round_tf32, cudaStream_t st,
+                     bool out_f16 = false);
+// fp32 -> fp16 (round to nearest even), n elements (n % 4 == 0)
+fr_status frk_to_f16(fr_engine* e, const float* src, void* dst, int64_t n, cudaStream_t st);
 // copy `bytes` (a multiple of 16) of indices from a mapped page-locked host buffer into device memory with SM loads
 fr_status frk_stage_idx(fr_engine* e, const void* mapped_src, int32_t* d_dst, size_t bytes, cudaStream_t st);
 fr_status frk_gather_push(fr_engine* e, const int32_t* d_idx, int B_global, int slot, int parity, cudaStream_t st);

@@ -62,7 +62,7 @@ __device__ __forceinline__ float4 ld_row8(const float4* base, int64_t piece) {
 // PUSH = false: out4 is the local [B][C] buffer.
 // PUSH = true : peer_out[r] is rank r's exchange buffer; item b lands on rank
 //               b / items_per_rank at local row b % items_per_rank (NVLink peer stores).
-template <bool ROUND, bool PUSH, int DT>
+template <bool ROUND, bool PUSH, int DT, bool OUT16 = false>
 __global__ void __launch_bounds__(256) gather_concat_kernel(const FrChunk* __restrict__ chunks,
                                                             const int* __restrict__ chunk_ids, int n_chunks,
                                                             const int32_t* __restrict__ idx, int T, int b_begin,
@@ -106,6 +106,12 @@ __global__ void __launch_bounds__(256) gather_concat_kernel(const FrChunk* __res
     if (PUSH) {
       const int r = b / items_per_rank;
       peer_out[r][peer_off4 + (size_t)(b - r * items_per_rank) * C + c] = o;
+    } else if (OUT16) {   // fp16 concat vectors (tc_f16): the piece is 4 halves
+      const __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
+      uint2 w;
+      w.x = *reinterpret_cast<const uint32_t*>(&lo);
+      w.y = *reinterpret_cast<const uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(out4)[(size_t)b * C + c] = w;
     } else {
       out4[(size_t)b * C + c] = o;
     }
@@ -198,7 +204,7 @@ int grid_for(int64_t n, int block, int sm_count) {
 template <bool ROUND, bool PUSH>
 void launch_gather(const fr_engine* e, const int* d_ids, int n_chunks, const int32_t* d_idx, int b_begin, int b_end,
                    float4* out4, float4* const* peers, int items_per_rank, cudaStream_t st, long long peer_off4 = 0,
-                   const FrChunk* chunks = nullptr, int idx_cols = 0) {
+                   const FrChunk* chunks = nullptr, int idx_cols = 0, bool out_f16 = false) {
   if (!chunks) {   // full index rows [B][T]; else a column-sliced block with its own descriptors
     chunks = e->d_chunks;
     idx_cols = (int)e->tables.size();
@@ -222,6 +228,10 @@ void launch_gather(const fr_engine* e, const int* d_ids, int n_chunks, const int
   auto kern = e->table_dtype == FR_TABLE_F32 ? gather_concat_kernel<ROUND, PUSH, FR_TABLE_F32>
               : e->table_dtype == FR_TABLE_F16 ? gather_concat_kernel<ROUND, PUSH, FR_TABLE_F16>
                                                : gather_concat_kernel<ROUND, PUSH, FR_TABLE_BF16>;
+  if (out_f16 && !PUSH)
+    kern = e->table_dtype == FR_TABLE_F32 ? gather_concat_kernel<false, false, FR_TABLE_F32, true>
+           : e->table_dtype == FR_TABLE_F16 ? gather_concat_kernel<false, false, FR_TABLE_F16, true>
+                                            : gather_concat_kernel<false, false, FR_TABLE_BF16, true>;
   cudaLaunchKernelEx(&cfg, kern, chunks, d_ids, n_chunks, d_idx, idx_cols, b_begin, b_end, out4, peers, C, items_per_rank,
                      peer_off4);
 }
@@ -256,9 +266,12 @@ fr_status frk_upload_chunks(fr_engine* e) {
   return FR_OK;
 }
 
-fr_status frk_gather(fr_engine* e, const int32_t* d_idx, int B, float* d_out, bool round_tf32, cudaStream_t st) {
+fr_status frk_gather(fr_engine* e, const int32_t* d_idx, int B, float* d_out, bool round_tf32, cudaStream_t st, bool out_f16) {
   if (B == 0) return FR_OK;
-  if (round_tf32)
+  if (out_f16)
+    launch_gather<false, false>(e, nullptr, e->D / 4, d_idx, 0, B, reinterpret_cast<float4*>(d_out), nullptr, 1, st, 0, nullptr, 0,
+                                true);
+  else if (round_tf32)
     launch_gather<true, false>(e, nullptr, e->D / 4, d_idx, 0, B, reinterpret_cast<float4*>(d_out), nullptr, 1, st);
   else
     launch_gather<false, false>(e, nullptr, e->D / 4, d_idx, 0, B, reinterpret_cast<float4*>(d_out), nullptr, 1, st);
@@ -275,6 +288,25 @@ fr_status frk_gather(fr_engine* e, const int32_t* d_idx, int B, float* d_out, bo
 // ld.cv: the same host buffer carries new indices on every replay -- never serve it from a cache.
 __global__ void stage_idx_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n16) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = __ldcv(src + i);
+}
+
+__global__ void to_f16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = src[i];
+    const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+    uint2 w;
+    w.x = *reinterpret_cast<const uint32_t*>(&lo);
+    w.y = *reinterpret_cast<const uint32_t*>(&hi);
+    dst[i] = w;
+  }
+}
+
+fr_status frk_to_f16(fr_engine* e, const float* src, void* dst, int64_t n, cudaStream_t st) {
+  const int64_t n4 = n / 4;
+  to_f16_kernel<<<grid_for(n4, 256, e->sm_count), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst), n4);
+  e->launches++;
+  FR_CUDA(e, cudaGetLastError());
+  return FR_OK;
 }
 
 fr_status frk_stage_idx(fr_engine* e, const void* mapped_src, int32_t* d_dst, size_t bytes, cudaStream_t st) {

@@ -217,6 +217,38 @@ __device__ __forceinline__ void epi_chunk_to_smem(const uint32_t (&r)[32], uint3
   }
 }
 
+// The same for fp16 activations (ELT = 2 kernels): 64 accumulator columns (two TMEM loads) + bias -> ReLU -> fp16
+// (round to nearest even) -> one 128-byte row of the staging buffer, 8 pieces of 8 halves.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void epi_chunk64_to_smem_f16(const uint32_t (&r0)[32], const uint32_t (&r1)[32], uint32_t bias_addr,
+                                                        uint32_t buf_addr, int lane, int relu) {
+  const uint32_t row = buf_addr + lane * 128;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {   // piece j = columns 8j .. 8j+7
+    const float4 b0 = lds128(bias_addr + j * 32), b1 = lds128(bias_addr + j * 32 + 16);
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int cidx = 8 * j + q;
+      v[q] = __uint_as_float(cidx < 32 ? r0[cidx] : r1[cidx - 32]);
+    }
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    if (relu) {
+#pragma unroll
+      for (int q = 0; q < 8; q++) v[q] = fmaxf(v[q], 0.f);
+    }
+    uint4 o;
+    o.x = pack_f16x2(v[0], v[1]); o.y = pack_f16x2(v[2], v[3]); o.z = pack_f16x2(v[4], v[5]); o.w = pack_f16x2(v[6], v[7]);
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row + ((j ^ (lane & 7)) << 4)), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w)
+                 : "memory");
+  }
+}
+
 // One epilogue chunk of layer 3: dot += sum_j act(acc[j] + bias[j]) * w4[j] over 32 columns, in column order.
 __device__ __forceinline__ float epi_chunk_dot(const uint32_t (&r)[32], uint32_t bias_addr, uint32_t w4_addr, int relu,
                                                float dot) {
@@ -308,6 +340,18 @@ __device__ __forceinline__ void umma_tf32_pair(uint32_t d_tmem, uint64_t a_desc,
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// The same MMA on fp16 operands (kind::f16, K = 16 per instruction = the same 32 bytes of a swizzled row).
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
@@ -418,6 +462,11 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32_m(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// kind::f16 instruction descriptor: D = f32, A = B = f16 (format 0), both K-major.
+__host__ __device__ constexpr uint32_t make_idesc_f16_m(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
 // Persistent: cluster c (one CTA or a CTA pair) walks tiles c, c + n_clusters, ... of the
 // (M / (128*CTAS)) x (N / BLOCK_N) tile grid, n fastest.  Three pipelines run concurrently:
 //   smem ring   full/empty        TMA producer  <-> MMA issuer
@@ -443,11 +492,18 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32_m(int m, int n) {
 // The leader's MMA issuer waits for its own CTA's a_full; the peer CTA's otherwise idle warp 1 waits for the
 // peer's and relays it as one remote arrival on the leader's full barrier.  TMA then carries the weights
 // only: 32 KB per K slice of a 512-wide tile (0.49 us at the measured rate, the MMAs take 0.5).
-template <int BLOCK_N, int STAGES, int EPI, int CTAS, int PAIRS, bool A_LSU>
+//
+// ELT = 2 (experimental, FR_TC_F16=1): fp16 operands and activations, kind::f16.  The shared-memory picture is the
+// same in BYTES (128-byte swizzled rows, 32 bytes of K per MMA), a K slice is 64 elements instead of 32; fp16
+// carries the same 11-bit significand TF32 keeps, in half the bytes, at twice the MMA rate -- at the price of
+// fp16's range.
+template <int BLOCK_N, int STAGES, int EPI, int CTAS, int PAIRS, bool A_LSU, int ELT>
 __global__ void __launch_bounds__(kThreads + (A_LSU ? kLoaderWarps * 32 : 0), 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const TcParams p) {
   static_assert(!A_LSU || (CTAS == 2 && PAIRS == 1), "the cp.async A loader is built for plain CTA pairs");
+  static_assert(ELT == 4 || (ELT == 2 && CTAS == 2 && PAIRS == 1 && !A_LSU), "fp16 operands: plain CTA pairs only");
+  constexpr int BK = 128 / ELT;   // elements of K per slice (one 128-byte swizzle row)
   using L = SmemLayout<BLOCK_N, STAGES, CTAS>;
   extern __shared__ uint8_t smem_raw[];
   // the dynamic-smem base offset is identical in both CTAs of a pair, so is the aligned layout
@@ -467,7 +523,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t crank = (CTAS == 2) ? cluster_ctarank() : 0u;   // rank in the cluster
   const uint32_t rank = crank & 1u, pair = crank >> 1;            // rank in the MMA pair, pair in the cluster
   const bool leader = (rank == 0);
-  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int num_kb = (p.K + BK - 1) / BK;
   const int n_tiles_n = p.N / BLOCK_N;
   const int n_tiles = ((p.M + BLOCK_M * CS - 1) / (BLOCK_M * CS)) * n_tiles_n;   // a tile = (BLOCK_M * CS) rows x BLOCK_N
   const int cluster_id = blockIdx.x / CS, n_clusters = gridDim.x / CS;
@@ -524,22 +580,22 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int r0 = (int)pair * kPartRows;
             const uint32_t bar = smem_u32(&full_bar[s]) & kPeerBitMask;   // "my pair leader's", in every destination
             if (leader) mbar_expect_tx(&full_bar[s], 2 * L::kStageBytes);
-            tma_load_2d_pair(&tmap_a, bar, a_dst, kb * BLOCK_K, m0);
-            tma_load_2d_pair_mcast(&tmap_b, bar, b_dst + r0 * (BLOCK_K * 4), kb * BLOCK_K,
+            tma_load_2d_pair(&tmap_a, bar, a_dst, kb * BK, m0);
+            tma_load_2d_pair_mcast(&tmap_b, bar, b_dst + r0 * (BLOCK_K * 4), kb * BK,
                                    nb0 + (r0 / L::kSubRows) * L::kMmaN + r0 % L::kSubRows, (uint16_t)(0x5u << rank));
           } else if (CTAS == 2) {
             const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);   // leader's barrier
             if (leader) mbar_expect_tx(&full_bar[s], 2 * (L::kStageBytes - (A_LSU ? L::kABytes : 0)));
-            if (!A_LSU) tma_load_2d_pair(&tmap_a, bar, a_dst, kb * BLOCK_K, m0);
+            if (!A_LSU) tma_load_2d_pair(&tmap_a, bar, a_dst, kb * BK, m0);
 #pragma unroll
             for (int h = 0; h < L::kNSub; h++)   // this CTA's rows of Wt for MMA h of the K step
-              tma_load_2d_pair(&tmap_b, bar, b_dst + h * L::kSubBytes, kb * BLOCK_K, nb0 + h * L::kMmaN);
+              tma_load_2d_pair(&tmap_b, bar, b_dst + h * L::kSubBytes, kb * BK, nb0 + h * L::kMmaN);
           } else {
             mbar_expect_tx(&full_bar[s], L::kStageBytes);
-            tma_load_2d(&tmap_a, &full_bar[s], a_dst, kb * BLOCK_K, m0);
+            tma_load_2d(&tmap_a, &full_bar[s], a_dst, kb * BK, m0);
 #pragma unroll
             for (int h = 0; h < L::kNSub; h++)
-              tma_load_2d(&tmap_b, &full_bar[s], b_dst + h * L::kSubBytes, kb * BLOCK_K, nb0 + h * L::kMmaN);
+              tma_load_2d(&tmap_b, &full_bar[s], b_dst + h * L::kSubBytes, kb * BK, nb0 + h * L::kMmaN);
           }
         }
       }
@@ -561,7 +617,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
     }
     if (leader) {
-      constexpr uint32_t idesc = make_idesc_tf32_m(BLOCK_M * CTAS, L::kMmaN);
+      constexpr uint32_t idesc = ELT == 2 ? make_idesc_f16_m(BLOCK_M * CTAS, L::kMmaN) : make_idesc_tf32_m(BLOCK_M * CTAS, L::kMmaN);
       uint32_t kc = 0, it = 0;
       for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
         const uint32_t as = it % L::kAcc;
@@ -591,7 +647,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 // advance 32 bytes of K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field;
                 // MMA h of the step reads Wt sub-tile h and accumulates into TMEM columns h * 256
                 const uint64_t bd = b_desc + (uint64_t)(k * 2) + (uint64_t)(h * (L::kSubBytes >> 4));
-                if (CTAS == 2) umma_tf32_pair(d_tmem + h * L::kMmaN, a_desc + (uint64_t)(k * 2), bd, idesc, (kb | k) != 0);
+                if (ELT == 2) umma_f16_pair(d_tmem + h * L::kMmaN, a_desc + (uint64_t)(k * 2), bd, idesc, (kb | k) != 0);
+                else if (CTAS == 2) umma_tf32_pair(d_tmem + h * L::kMmaN, a_desc + (uint64_t)(k * 2), bd, idesc, (kb | k) != 0);
                 else umma_tf32(d_tmem + h * L::kMmaN, a_desc + (uint64_t)(k * 2), bd, idesc, (kb | k) != 0);
               }
             }
@@ -622,7 +679,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int s = kc % STAGES;
         mbar_wait(&empty_bar[s], ((kc / STAGES) & 1) ^ 1, 5, kc, tile);
         const uint32_t slot = smem_u32(smem + s * L::kStageBytes);
-        const int col = kb * BLOCK_K + j * 4;
+        const int col = kb * BK + j * 4;
         const bool col_ok = col < p.K;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -649,6 +706,26 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
       float dot = 0.f;
+      if (EPI == EPI_STORE && ELT == 2) {
+        // fp16 activations: 64 accumulator columns fill one 128-byte row of the 32-row store box
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 64) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(taddr + c, r0);
+          tmem_ld32(taddr + c + 32, r1);
+          uint8_t* buf = store_buf + (sc & 1) * kStoreBufBytes;
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          epi_chunk64_to_smem_f16(r0, r1, smem_u32(s_bias + n0 + c), smem_u32(buf), lane, p.relu);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M) {
+            tma_store_2d(&tmap_out, buf, n0 + c, row0);
+            bulk_commit();
+          }
+          sc++;
+        }
+      } else
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N; c += 32) {
         uint32_t r[32];
@@ -1305,23 +1382,26 @@ struct TcState {
   // 32-row boxes are the epilogue's store boxes
   struct AMap {
     const void* ptr;
-    int K, rows, box_rows;
+    int K, rows, box_rows, elt;
     CUtensorMap map;
   };
+  CUtensorMap w_map16[3];   // tc_f16: fp16 weights in 128-row x 64-element boxes
   std::vector<AMap> a_maps;
   std::mutex mu;
 };
 
-fr_status encode_2d(fr_engine* e, TcState* st, CUtensorMap* map, const void* base, int rows, int K, int box_rows) {
+fr_status encode_2d(fr_engine* e, TcState* st, CUtensorMap* map, const void* base, int rows, int K, int box_rows,
+                    int elt = 4) {
   const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * elt};
+  const cuuint32_t box[2] = {(cuuint32_t)(128 / elt), (cuuint32_t)box_rows};   // one 128-byte swizzle row of K
   const cuuint32_t estr[2] = {1, 1};
   static const int promo = getenv("FR_TMA_L2PROMO") ? atoi(getenv("FR_TMA_L2PROMO")) : 3;   // experiment knob
   const CUtensorMapL2promotion l2p = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
                                      : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                      : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-  CUresult r = st->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = st->encode(map, elt == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                          const_cast<void*>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -1338,7 +1418,7 @@ int g_max_clusters = 0;   // FR_TC_MAX_CLUSTERS: cap the persistent grid (tests 
 // inferences/s (a longer gang leaves too few clusters per launch to keep 148 SMs busy).
 int g_min_kb = 32;
 
-template <int BLOCK_N, int STAGES, int EPI, int CTAS, int PAIRS = 1, bool A_LSU = false>
+template <int BLOCK_N, int STAGES, int EPI, int CTAS, int PAIRS = 1, bool A_LSU = false, int ELT = 4>
 fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const TcParams& p,
                  bool pdl_attr, cudaStream_t st) {
   using L = SmemLayout<BLOCK_N, STAGES, CTAS>;
@@ -1346,7 +1426,7 @@ fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const
   static_assert(L::kDyn <= 227 * 1024, "tile configuration exceeds the 227 KB shared memory of an SM");
   static_assert(L::kTmemCols == 256 || L::kTmemCols == 512, "TMEM allocation must be a power of two");
   static_assert(L::kNSub == 1 || CTAS == 2, "512-wide tiles are pair tiles");
-  auto kern = tc_linear_kernel<BLOCK_N, STAGES, EPI, CTAS, PAIRS, A_LSU>;
+  auto kern = tc_linear_kernel<BLOCK_N, STAGES, EPI, CTAS, PAIRS, A_LSU, ELT>;
   static std::atomic<uint64_t> attr_done{0};  // bit d: opt-in smem size set on device d for this instantiation
   const uint64_t bit = 1ull << (e->device & 63);
   if (!(attr_done.load() & bit)) {
@@ -1357,9 +1437,11 @@ fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const
   const int n_tiles = (p.M + BLOCK_M * CS - 1) / (BLOCK_M * CS) * (p.N / BLOCK_N);
   int max_clusters = e->sm_count / CS;
   if (g_max_clusters > 0 && g_max_clusters < max_clusters) max_clusters = g_max_clusters;   // test knob
-  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int num_kb = (p.K + 128 / ELT - 1) / (128 / ELT);
   // (ganging only pays when the epilogue of one tile runs under the next tile's MMAs: two accumulator stages)
-  const int gang = (num_kb >= g_min_kb || L::kAcc == 1 || p.latency) ? 1 : (g_min_kb + num_kb - 1) / num_kb;   // tiles per cluster wanted
+  // an fp16 K slice carries twice the K of a TF32 one in the same bytes: half as many slices make the same gang
+  const int min_kb = ELT == 2 ? (g_min_kb + 1) / 2 : g_min_kb;
+  const int gang = (num_kb >= min_kb || L::kAcc == 1 || p.latency) ? 1 : (min_kb + num_kb - 1) / num_kb;   // tiles per cluster wanted
   int n_clusters = (n_tiles + gang - 1) / gang;
   if (n_clusters > max_clusters) n_clusters = max_clusters;
   cudaLaunchConfig_t cfg = {};
@@ -1382,10 +1464,11 @@ fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const
   return FR_OK;
 }
 
-fr_status get_a_map(fr_engine* e, TcState* st, const void* ptr, int K, int rows, int box_rows, CUtensorMap* out) {
+fr_status get_a_map(fr_engine* e, TcState* st, const void* ptr, int K, int rows, int box_rows, CUtensorMap* out,
+                    int elt = 4) {
   std::lock_guard<std::mutex> g(st->mu);
   for (const TcState::AMap& m : st->a_maps)
-    if (m.ptr == ptr && m.K == K && m.rows == rows && m.box_rows == box_rows) {
+    if (m.ptr == ptr && m.K == K && m.rows == rows && m.box_rows == box_rows && m.elt == elt) {
       *out = m.map;
       return FR_OK;
     }
@@ -1394,7 +1477,8 @@ fr_status get_a_map(fr_engine* e, TcState* st, const void* ptr, int K, int rows,
   m.K = K;
   m.rows = rows;
   m.box_rows = box_rows;
-  fr_status s = encode_2d(e, st, &m.map, ptr, rows, K, box_rows);
+  m.elt = elt;
+  fr_status s = encode_2d(e, st, &m.map, ptr, rows, K, box_rows, elt);
   if (s != FR_OK) return s;
   if (st->a_maps.size() < 1024) st->a_maps.push_back(m);
   *out = m.map;
@@ -1489,6 +1573,9 @@ fr_status frtc_prepare(fr_engine* e) {
     if (const char* env = getenv("FR_TC_ALSU")) st->a_lsu = atoi(env) != 0;
     for (int k = 0; k < 3; k++)
       if ((s = encode_2d(e, st, &st->w_map128[k], e->d_Wt[k], e->dims[k + 1], e->dims[k], 128)) != FR_OK) return s;
+    if (e->tc_f16)
+      for (int k = 0; k < 3; k++)
+        if ((s = encode_2d(e, st, &st->w_map16[k], e->d_Wt16[k], e->dims[k + 1], e->dims[k], 128, 2)) != FR_OK) return s;
     if (const char* env = getenv("FR_CHAIN")) st->chain = atoi(env) != 0;
     if (getenv("FR_CHAIN_PROF") && atoi(getenv("FR_CHAIN_PROF")) != 0 && !st->d_prof) {
       FR_CUDA(e, cudaMalloc(&st->d_prof, kProfIters * kProfPhases * kProfSlots * sizeof(long long)));
@@ -1525,7 +1612,7 @@ bool frtc_can_fuse(const fr_engine* e) {
   // row pitch and in-row offset of a piece must fit the packed descriptor (dims up to 1020 floats)
   bool dims_ok = true;
   for (const FrTable& t : e->tables) dims_ok = dims_ok && t.dim / 4 < 256;
-  return e->fuse_lookup && st && st->ready && e->world == 1 && e->precision == FR_PREC_TF32 &&
+  return e->fuse_lookup && !fr_tc_f16(e) && st && st->ready && e->world == 1 && e->precision == FR_PREC_TF32 &&
          e->table_dtype == FR_TABLE_F32 && e->dims[1] % kFuseN == 0 &&
          e->dims[1] <= kMaxN && e->D / 4 <= kFuseMaxChunks && dims_ok;
 }
@@ -1583,7 +1670,7 @@ fr_status frtc_fused_layer1(fr_engine* e, fr_stream_s* s, const int32_t* d_idx, 
 // which spread one small batch over more SMs.
 bool frtc_can_chain(const fr_engine* e, int B) {
   const TcState* st = static_cast<const TcState*>(e->tc_state);
-  if (!st || !st->ready || !st->chain || !st->auto_tiles || e->precision != FR_PREC_TF32) return false;
+  if (!st || !st->ready || !st->chain || !st->auto_tiles || e->precision != FR_PREC_TF32 || fr_tc_f16(e)) return false;
   if (B <= kLatencyBatch || e->dims[3] != 256) return false;
   for (int k = 1; k <= 2; k++)
     if (e->dims[k] % kChainW || e->dims[k] / kChainW > kChainMaxChunks) return false;
@@ -1661,7 +1748,38 @@ fr_status frtc_layer(fr_engine* e, fr_stream_s* s, int k, const float* in, int B
   return r;
 }
 
+// fp16 operands (tc_f16): `in` and s->d_h[k] hold fp16 [B][dim]; CTA pairs, 512-wide tiles where K is long
+static fr_status frtc_layer_f16(fr_engine* e, fr_stream_s* s, int k, const float* in, int B, float* d_scores) {
+  TcState* st = static_cast<TcState*>(e->tc_state);
+  const bool act = (e->mlp_mode == FR_MLP_BIAS_RELU_SIGMOID);
+  CUtensorMap a, o;
+  fr_status r = get_a_map(e, st, in, e->dims[k], B, BLOCK_M, &a, 2);
+  if (r != FR_OK) return r;
+  o = a;
+  if (k < 2 && (r = get_a_map(e, st, s->d_h[k], e->dims[k + 1], B, kStoreBoxRows, &o, 2)) != FR_OK) return r;
+  TcParams p;
+  p.a = in;
+  p.bias = act ? e->d_bias[k] : nullptr;
+  p.M = B;
+  p.N = e->dims[k + 1];
+  p.K = e->dims[k];
+  p.relu = act ? 1 : 0;
+  p.sigmoid = act ? 1 : 0;
+  p.w4 = e->d_W[3];
+  p.b4 = act ? e->d_bias[3] : nullptr;
+  p.pdl = 0;
+  p.out = d_scores;
+  p.latency = 0;
+  const int N = p.N, num_kb = (p.K + 63) / 64;
+  const int tiles256 = (B + 2 * BLOCK_M - 1) / (2 * BLOCK_M) * (N / 256);
+  if (k == 2) return launch<256, 5, EPI_DOT, 2, 1, false, 2>(e, a, st->w_map16[k], o, p, false, s->stream);
+  if (N % 512 == 0 && num_kb >= kWideMinKb && tiles256 < e->sm_count / 2)
+    return launch<512, 3, EPI_STORE, 2, 1, false, 2>(e, a, st->w_map16[k], o, p, false, s->stream);
+  return launch<256, 5, EPI_STORE, 2, 1, false, 2>(e, a, st->w_map16[k], o, p, false, s->stream);
+}
+
 static fr_status frtc_layer_impl(fr_engine* e, fr_stream_s* s, int k, const float* in, int B, float* d_scores) {
+  if (fr_tc_f16(e)) return frtc_layer_f16(e, s, k, in, B, d_scores);
   TcState* st = static_cast<TcState*>(e->tc_state);
   const bool act = (e->mlp_mode == FR_MLP_BIAS_RELU_SIGMOID);
   CUtensorMap a, o;
