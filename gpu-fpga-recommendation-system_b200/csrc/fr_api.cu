@@ -113,7 +113,8 @@ static void free_stream(fr_stream_s* s) {
   if (!s) return;
   if (s->stream) cudaStreamSynchronize(s->stream);
   for (fr_stream_s::Graph& g : s->graphs)
-    if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (int f = 0; f < 2; f++)
+      if (g.exec[f]) cudaGraphExecDestroy(g.exec[f]);
   cudaFree(s->d_idx);
   cudaFree(s->d_x);
   cudaFree(s->d_x32);
@@ -165,7 +166,6 @@ extern "C" fr_status fr_create(const fr_model_desc* desc, int n_gpus, const int*
   if (const char* env = getenv("FR_GRAPHS")) e->use_graphs = atoi(env) != 0;
   if (const char* env = getenv("FR_PDL")) e->pdl_mask = atoi(env) & 7;
   if (const char* env = getenv("FR_FUSE")) e->fuse_lookup = atoi(env) != 0;
-  if (const char* env = getenv("FR_TC_F16")) e->tc_f16 = atoi(env) != 0 && e->precision == FR_PREC_TF32;
   if (const char* env = getenv("FR_ZEROCOPY")) {
     const int v = atoi(env);
     e->zero_copy_pct = v == 1 ? 100 : (v < 0 ? 0 : (v > 100 ? 100 : v));
@@ -212,6 +212,7 @@ extern "C" void fr_destroy(fr_engine* e) {
   cudaFree(e->d_step);
   cudaFree(e->d_done);
   if (e->h_shard_err) cudaFreeHost(e->h_shard_err);
+  if (e->h_idx_err) cudaFreeHost(e->h_idx_err);
   if (e->h_watch) cudaFreeHost(e->h_watch);
   delete e;
 }
@@ -275,6 +276,8 @@ extern "C" fr_status fr_load_table(fr_engine* e, int table_id, const float* host
     cudaFree(stage);
   }
   tb.loaded = true;
+  tb.range_valid = false;
+  e->f16_dirty = true;
   return FR_OK;
 }
 
@@ -287,6 +290,8 @@ extern "C" fr_status fr_fill_table_reference(fr_engine* e, int table_id, int64_t
   if ((st = frk_fill_reference(e, tb.d, tb.rows, tb.dim, debug_rows, e->default_stream->stream)) != FR_OK) return st;
   FR_CUDA(e, cudaStreamSynchronize(e->default_stream->stream));
   tb.loaded = true;
+  tb.range_valid = false;
+  e->f16_dirty = true;
   return FR_OK;
 }
 
@@ -299,6 +304,8 @@ extern "C" fr_status fr_fill_table_hash(fr_engine* e, int table_id, uint32_t see
   if ((st = frk_fill_hash(e, tb.d, seed, table_id, tb.rows, tb.dim, e->default_stream->stream)) != FR_OK) return st;
   FR_CUDA(e, cudaStreamSynchronize(e->default_stream->stream));
   tb.loaded = true;
+  tb.range_valid = false;
+  e->f16_dirty = true;
   return FR_OK;
 }
 
@@ -342,12 +349,9 @@ extern "C" fr_status fr_load_mlp(fr_engine* e, int layer, const float* W, const 
   else FR_CUDA(e, cudaMemsetAsync(e->d_bias[layer], 0, (size_t)out * sizeof(float), e->default_stream->stream));
   fr_status st = frk_transpose_round_tf32(e, e->d_W[layer], in, out, e->d_Wt[layer], e->default_stream->stream);
   if (st != FR_OK) return st;
-  if (e->tc_f16 && layer < 3) {   // the tf32-rounded value has an 11-bit significand: exact in fp16 when in range
-    if (!e->d_Wt16[layer]) FR_CUDA(e, cudaMalloc(&e->d_Wt16[layer], nw * 2));
-    if ((st = frk_to_f16(e, e->d_Wt[layer], e->d_Wt16[layer], (int64_t)nw, e->default_stream->stream)) != FR_OK) return st;
-  }
   FR_CUDA(e, cudaStreamSynchronize(e->default_stream->stream));
   e->layer_loaded[layer] = true;
+  e->f16_dirty = true;
   return FR_OK;
 }
 
@@ -362,6 +366,7 @@ extern "C" fr_status fr_set_precision(fr_engine* e, int p) {
   if (!e) return fr_fail(nullptr, FR_ERR_INVALID, "null engine");
   if (p != FR_PREC_TF32 && p != FR_PREC_FP32) return fr_fail(e, FR_ERR_INVALID, "bad precision %d", p);
   e->precision = p;
+  e->f16_dirty = true;
   return FR_OK;
 }
 
@@ -436,6 +441,13 @@ static fr_status prep(fr_engine* e, fr_stream* s, int B, bool need_tables, bool 
       fr_status st = frtc_prepare(e);
       if (st != FR_OK) return st;
     }
+    if (need_tables && e->f16_dirty && e->f16_mode != FR_F16_OFF) {   // tables and weights are all loaded here
+      std::lock_guard<std::mutex> g(e->mu);
+      if (e->f16_dirty) {
+        fr_status st = fr_f16_analyse(e);
+        if (st != FR_OK) return st;
+      }
+    }
   }
   return FR_OK;
 }
@@ -476,11 +488,11 @@ static float* score_target(const fr_engine* e, fr_stream_s* s, float* scores, in
 static int mlp_steps(const fr_engine* e) { return e->precision == FR_PREC_TF32 ? 3 : 4; }
 
 static fr_status run_mlp_step(fr_engine* e, fr_stream_s* s, int step, const float* in, int B, float* d_scores,
-                              const float** out) {
+                              const float** out, const FrPeerWait* wait = nullptr) {
   const bool act = (e->mlp_mode == FR_MLP_BIAS_RELU_SIGMOID);
   if (e->precision == FR_PREC_TF32) {
     *out = step < 2 ? s->d_h[step] : d_scores;
-    return frtc_layer(e, s, step, in, B, d_scores);
+    return frtc_layer(e, s, step, in, B, d_scores, wait);
   }
   if (step < 3) {
     *out = s->d_h[step];
@@ -491,13 +503,29 @@ static fr_status run_mlp_step(fr_engine* e, fr_stream_s* s, int step, const floa
   return frk_final_dot(e, in, e->d_W[3], act ? e->d_bias[3] : nullptr, d_scores, B, e->dims[3], act, s->stream);
 }
 
-static fr_status run_mlp(fr_engine* e, fr_stream_s* s, const float* d_x, int B, float* d_scores) {
-  if (B == 0) return FR_OK;
+// wait_slot >= 0: the MLP of a table-sharded step -- d_x is the slot's concat buffer, complete once every rank has
+// published the slot's current step.  The tcgen05 path polls the flags inside its first kernel; the others wait first.
+static fr_status run_mlp(fr_engine* e, fr_stream_s* s, const float* d_x, int B, float* d_scores, int wait_slot = -1) {
+  if (B == 0) return wait_slot >= 0 ? frk_shard_wait(e, wait_slot, s->stream) : FR_OK;
+  FrPeerWait pw = {nullptr, nullptr, 0, nullptr};
+  const FrPeerWait* wait = nullptr;
+  if (wait_slot >= 0) {
+    if (e->precision == FR_PREC_TF32 && !frtc_can_chain(e, B)) {
+      pw.flags = reinterpret_cast<const int*>(e->d_xchg + fr_xchg_flags_off(e, wait_slot));
+      pw.step = e->d_step + wait_slot;
+      pw.world = e->world;
+      FR_CUDA(e, cudaHostGetDevicePointer(&pw.err, e->h_shard_err, 0));
+      wait = &pw;
+    } else {
+      fr_status st = frk_shard_wait(e, wait_slot, s->stream);
+      if (st != FR_OK) return st;
+    }
+  }
   if (frtc_can_chain(e, B)) return frtc_chain(e, s, d_x, B, d_scores);   // all layers in one persistent launch
   const float* in = d_x;
   for (int k = 0; k < mlp_steps(e); k++) {
     const float* out = nullptr;
-    fr_status st = run_mlp_step(e, s, k, in, B, d_scores, &out);
+    fr_status st = run_mlp_step(e, s, k, in, B, d_scores, &out, k == 0 ? wait : nullptr);
     if (st != FR_OK) return st;
     in = out;
   }
@@ -512,6 +540,7 @@ static fr_status emit_scores(fr_engine* e, fr_stream_s* s, float* scores, int B,
 
 // Enqueue one batch on the worker's stream: [H2D idx] -> gather -> MLP launches -> [D2H scores].
 static fr_status infer_enqueue(fr_engine* e, fr_stream_s* s, const int32_t* idx, int B, float* scores) {
+  s->f16 = fr_tc_f16(e);
   const int32_t* d_idx = nullptr;
   fr_status st = stage_idx(e, s, idx, B, &d_idx);
   if (st != FR_OK) return st;
@@ -542,74 +571,158 @@ static bool is_capturable_ptr(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged || a.type == cudaMemoryTypeHost;
 }
 
-// The batch is 4-6 tiny launches; issued one by one the host (~5 us per launch) is the bottleneck,
-// so a (idx, scores, B, variant) combination seen before on this worker is replayed as ONE CUDA
-// graph.  `enqueue` issues the step's work on s->stream (it is called directly, or under capture).
+// The batch is 4-6 tiny launches; issued one by one the host (~4 us per launch) is the bottleneck, so a
+// (buffers, B, entry point) combination is captured into a CUDA graph the first time a worker sees it and
+// replayed as ONE cudaGraphLaunch from then on.  `enqueue(f)` issues the step's work on s->stream (called
+// directly, or under capture) for flavour f: the table-sharded steps alternate between two exchange
+// buffers, so their graphs come in pairs that are captured TOGETHER -- which graph a call replays is then
+// independent of how many steps the worker has issued before (no per-parity warm-up).  The very first call
+// of an (entry point, B) pair on an engine runs un-captured: it sets function attributes and fills the
+// tensor-map cache.  The cache holds kMaxGraphs combinations per worker, least recently used evicted.
+enum { FR_GV_INFER = 0, FR_GV_SHARD = 1, FR_GV_SHARD_SLICED = 2, FR_GV_MANY = 3 };   // | sub-batches << 4
+constexpr size_t kMaxGraphs = 64;
+
+static bool engine_warm(fr_engine* e, int variant, int B) {
+  std::lock_guard<std::mutex> g(e->mu);
+  for (const std::pair<int, int>& w : e->warmed)
+    if (w.first == variant && w.second == B) return true;
+  e->warmed.push_back({variant, B});
+  return false;
+}
+
+static void drop_graph(fr_stream_s::Graph& g) {
+  for (int f = 0; f < 2; f++)
+    if (g.exec[f]) cudaGraphExecDestroy(g.exec[f]);
+  g.exec[0] = g.exec[1] = nullptr;
+}
+
 template <class F>
 static fr_status run_or_replay(fr_engine* e, fr_stream_s* s, const void* idx, const void* scores, int B, int variant,
-                               F&& enqueue, const void* idx2 = nullptr) {
-  if (!e->use_graphs) return enqueue();
+                               int flavours, int flavour, F&& enqueue, const void* idx2 = nullptr, bool bypass = false) {
+  if (!e->use_graphs || bypass) {
+    e->graph_direct++;
+    return enqueue(flavour);
+  }
   fr_stream_s::Graph* g = nullptr;
+  const int prec_key = e->precision | (fr_tc_f16(e) ? 16 : 0);
   for (fr_stream_s::Graph& c : s->graphs)
     if (c.idx == idx && c.idx2 == idx2 && c.scores == scores && c.B == B && c.mode == e->mlp_mode &&
-        c.prec == e->precision && c.variant == variant)
+        c.prec == prec_key && c.variant == variant) {
       g = &c;
-  if (g && g->exec) {
-    FR_CUDA(e, cudaGraphLaunch(g->exec, s->stream));
+      break;
+    }
+  if (g && g->exec[flavour]) {
+    FR_CUDA(e, cudaGraphLaunch(g->exec[flavour], s->stream));
+    g->last_use = ++s->graph_clock;
     e->launches += g->launches;
+    e->graph_hits++;
     return FR_OK;
   }
+  if ((g && g->failed) || !is_capturable_ptr(idx) || !is_capturable_ptr(scores) || (idx2 && !is_capturable_ptr(idx2)) ||
+      !engine_warm(e, variant, B)) {
+    e->graph_direct++;
+    return enqueue(flavour);
+  }
   if (!g) {
-    if (s->graphs.size() >= 512 || !is_capturable_ptr(idx) || !is_capturable_ptr(scores) ||
-        (idx2 && !is_capturable_ptr(idx2)))
-      return enqueue();
-    s->graphs.push_back({idx, idx2, scores, B, e->mlp_mode, e->precision, variant, 0, 0, nullptr});
+    if (s->graphs.size() >= kMaxGraphs) {   // evict the least recently used combination
+      size_t lru = 0;
+      for (size_t i = 1; i < s->graphs.size(); i++)
+        if (s->graphs[i].last_use < s->graphs[lru].last_use) lru = i;
+      drop_graph(s->graphs[lru]);
+      s->graphs.erase(s->graphs.begin() + lru);
+    }
+    s->graphs.push_back({idx, idx2, scores, B, e->mlp_mode, prec_key, variant, flavours, false, 0, 0, {nullptr, nullptr}});
     g = &s->graphs.back();
   }
-  if (g->seen < 1) {  // first sighting: plain launches (also warms attribute / tensor-map caches)
-    g->seen++;
-    return enqueue();
-  }
-  if (g->seen == INT_MAX) return enqueue();  // capture failed before
-  const int64_t l0 = e->launches.load();
-  cudaError_t ce = cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal);
-  if (ce != cudaSuccess) {
-    cudaGetLastError();
-    g->seen = INT_MAX;
-    return enqueue();
-  }
-  fr_status st = enqueue();
-  cudaGraph_t graph = nullptr;
-  ce = cudaStreamEndCapture(s->stream, &graph);
-  const int captured = (int)(e->launches.load() - l0);
-  e->launches -= captured;  // nothing ran yet
-  if (st != FR_OK || ce != cudaSuccess || !graph) {
-    cudaGetLastError();
+  g->last_use = ++s->graph_clock;
+  for (int f = 0; f < flavours && !g->failed; f++) {
+    const int64_t l0 = e->launches.load();
+    cudaError_t ce = cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal);
+    if (ce != cudaSuccess) {
+      cudaGetLastError();
+      g->failed = true;
+      break;
+    }
+    const fr_status st = enqueue(f);
+    cudaGraph_t graph = nullptr;
+    ce = cudaStreamEndCapture(s->stream, &graph);
+    g->launches = (int)(e->launches.load() - l0);
+    e->launches -= g->launches;  // nothing ran yet
+    if (st == FR_OK && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&g->exec[f], graph, 0);
     if (graph) cudaGraphDestroy(graph);
-    g->seen = INT_MAX;
-    return enqueue();
+    if (st != FR_OK || ce != cudaSuccess || !g->exec[f]) {
+      cudaGetLastError();
+      g->failed = true;
+    }
   }
-  ce = cudaGraphInstantiate(&g->exec, graph, 0);
-  cudaGraphDestroy(graph);
-  if (ce != cudaSuccess) {
-    cudaGetLastError();
-    g->exec = nullptr;
-    g->seen = INT_MAX;
-    return enqueue();
+  if (g->failed) {
+    drop_graph(*g);
+    e->graph_direct++;
+    return enqueue(flavour);
   }
-  g->launches = captured;
-  FR_CUDA(e, cudaGraphLaunch(g->exec, s->stream));
+  FR_CUDA(e, cudaGraphLaunch(g->exec[flavour], s->stream));
   e->launches += g->launches;
+  e->graph_captures++;
   return FR_OK;
 }
 
-extern "C" fr_status fr_infer(fr_engine* e, const int32_t* idx, int B, float* scores, fr_stream s) {
+// Drop every cached graph of a worker (its buffers are about to be freed or re-used for something else).
+extern "C" fr_status fr_graph_flush(fr_engine* e, fr_stream s) {
+  if (!e) return fr_fail(nullptr, FR_ERR_INVALID, "null engine");
+  if (!s) s = e->default_stream;
+  FR_CUDA(e, cudaSetDevice(e->device));
+  FR_CUDA(e, cudaStreamSynchronize(s->stream));
+  for (fr_stream_s::Graph& g : s->graphs) drop_graph(g);
+  s->graphs.clear();
+  return FR_OK;
+}
+
+extern "C" fr_status fr_graph_stats(const fr_engine* e, int64_t* replayed, int64_t* captured, int64_t* direct) {
+  if (!e) return fr_fail(nullptr, FR_ERR_INVALID, "null engine");
+  if (replayed) *replayed = e->graph_hits.load();
+  if (captured) *captured = e->graph_captures.load();
+  if (direct) *direct = e->graph_direct.load();
+  return FR_OK;
+}
+
+fr_status fr_infer_opts(fr_engine* e, const int32_t* idx, int B, float* scores, fr_stream s, bool no_graph) {
   fr_status st = prep(e, &s, B, true, true);
   if (st != FR_OK) return st;
   if (B == 0) return FR_OK;
   if (!idx || !scores) return fr_fail(e, FR_ERR_INVALID, "null idx/scores");
   if (e->world > 1) return fr_fail(e, FR_ERR_STATE, "engine is table-sharded over %d ranks: use fr_shard_infer", e->world);
-  return run_or_replay(e, s, idx, scores, B, 0, [&] { return infer_enqueue(e, s, idx, B, scores); });
+  return run_or_replay(e, s, idx, scores, B, FR_GV_INFER, 1, 0, [&](int) { return infer_enqueue(e, s, idx, B, scores); },
+                       nullptr, no_graph);
+}
+
+extern "C" fr_status fr_infer(fr_engine* e, const int32_t* idx, int B, float* scores, fr_stream s) {
+  return fr_infer_opts(e, idx, B, scores, s, false);
+}
+
+// n batches of B items in ONE call on one worker: idx [n][B][T] and scores [n][B] contiguous.  Host buffers
+// travel in one copy each way (a copy costs the engine ~4 us on top of its bytes, whatever its size), the
+// batches then run back to back on the worker's stream, each through the same kernels as fr_infer.
+extern "C" fr_status fr_infer_many(fr_engine* e, const int32_t* idx, int n, int B, float* scores, fr_stream s) {
+  if (n < 0 || B < 0 || (int64_t)n * B > INT_MAX) return fr_fail(e, FR_ERR_INVALID, "fr_infer_many: n=%d B=%d", n, B);
+  fr_status st = prep(e, &s, n * B, true, true);   // the worker's index / score buffers hold max_batch items
+  if (st != FR_OK) return st;
+  if (n == 0 || B == 0) return FR_OK;
+  if (!idx || !scores) return fr_fail(e, FR_ERR_INVALID, "null idx/scores");
+  if (e->world > 1) return fr_fail(e, FR_ERR_STATE, "engine is table-sharded over %d ranks: use fr_shard_infer", e->world);
+  if (n > 4095) return fr_fail(e, FR_ERR_INVALID, "fr_infer_many: at most 4095 batches per call");
+  return run_or_replay(e, s, idx, scores, B, FR_GV_MANY | (n << 4), 1, 0, [&](int) {
+    s->f16 = fr_tc_f16(e);
+    const int32_t* d_idx = nullptr;
+    fr_status r = stage_idx(e, s, idx, n * B, &d_idx);
+    if (r != FR_OK) return r;
+    float* d_scores = score_target(e, s, scores, n * B);
+    for (int i = 0; i < n; i++) {
+      const int32_t* bi = d_idx + (size_t)i * B * e->tables.size();
+      if ((r = frk_gather(e, bi, B, s->d_x, e->precision == FR_PREC_TF32, s->stream, fr_tc_f16(e))) != FR_OK) return r;
+      if ((r = run_mlp(e, s, s->d_x, B, d_scores + (size_t)i * B)) != FR_OK) return r;
+    }
+    return emit_scores(e, s, scores, n * B, d_scores);
+  });
 }
 
 extern "C" fr_status fr_gather_only(fr_engine* e, const int32_t* idx, int B, float* concat, fr_stream s) {
@@ -633,17 +746,17 @@ extern "C" fr_status fr_mlp_only(fr_engine* e, const float* x, int B, float* sco
   if (st != FR_OK) return st;
   if (B == 0) return FR_OK;
   if (!x || !scores) return fr_fail(e, FR_ERR_INVALID, "null x/scores");
+  // (caller data: the fp16 range analysis cannot bound it, so this entry point always runs TF32 / FP32)
+  s->f16 = false;
   const float* d_x = x;
-  if (fr_tc_f16(e)) {   // the tcgen05 path wants fp16 rows: land fp32 input next to the worker's buffers, convert
-    if (!is_device_ptr(x)) {
-      if (!s->d_x32) FR_CUDA(e, cudaMalloc(&s->d_x32, (size_t)e->max_batch * e->D * sizeof(float)));
-      FR_CUDA(e, cudaMemcpyAsync(s->d_x32, x, (size_t)B * e->D * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-      d_x = s->d_x32;
-    }
-    if ((st = frk_to_f16(e, d_x, s->d_x, (int64_t)B * e->D, s->stream)) != FR_OK) return st;
-    d_x = s->d_x;
-  } else if (!is_device_ptr(x)) {
+  if (!is_device_ptr(x)) {
     FR_CUDA(e, cudaMemcpyAsync(s->d_x, x, (size_t)B * e->D * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    d_x = s->d_x;
+  }
+  // kind::tf32 TRUNCATES fp32 operands; the header promises round-to-nearest (what the lookup does on the
+  // fr_infer path), so the same input gives the same scores through either entry point
+  if (e->precision == FR_PREC_TF32) {
+    if ((st = frk_round_tf32(e, d_x, s->d_x, (int64_t)B * e->D, s->stream)) != FR_OK) return st;
     d_x = s->d_x;
   }
   float* d_scores = score_target(e, s, scores, B);
@@ -655,7 +768,7 @@ extern "C" fr_status fr_layer_only(fr_engine* e, int k, const float* x, int B, f
   fr_status st = prep(e, &s, B, false, true);
   if (st != FR_OK) return st;
   if (k < 0 || k >= mlp_steps(e)) return fr_fail(e, FR_ERR_INVALID, "fr_layer_only: step %d of %d", k, mlp_steps(e));
-  if (fr_tc_f16(e)) return fr_fail(e, FR_ERR_UNSUPPORTED, "fr_layer_only takes fp32 activations; the engine runs FR_TC_F16");
+  s->f16 = false;
   if (B == 0) return FR_OK;
   if (!x || !y) return fr_fail(e, FR_ERR_INVALID, "null x/y");
   const bool last = (k == mlp_steps(e) - 1);
@@ -689,10 +802,78 @@ extern "C" fr_status fr_sync(fr_engine* e, fr_stream s) {
     const int* w = e->h_watch;
     if (w && w[0])
       return fr_fail(e, FR_ERR_CUDA, "cudaStreamSynchronize: %s; tcgen05 kernel watchdog: wait %d (1 smem slot free, 2 TMEM stage "
-                     "free, 3 smem slot full, 4 TMEM stage full) gave up in CTA %d of %d, warp %d, parity %d, counters %d/%d",
-                     cudaGetErrorString(ce), w[1], w[2], w[5], w[3], w[4], w[6], w[7]);
+                     "free, 3 smem slot full, 4 TMEM stage full, 8 peer ranks' rows) gave up in CTA %d of %d, warp %d, parity %d, "
+                     "counters %d/%d", cudaGetErrorString(ce), w[1], w[2], w[5], w[3], w[4], w[6], w[7]);
     return fr_fail(e, FR_ERR_CUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(ce));
   }
+  // a sharded step that gave up waiting for a peer rank ran its MLP on an incomplete concat buffer
+  if (e->h_shard_err && *reinterpret_cast<volatile int*>(e->h_shard_err))
+    return fr_fail(e, FR_ERR_STATE, "a sharded step timed out waiting for a peer rank's rows (~10 s); its scores are invalid");
+  if (e->h_idx_err) {
+    volatile int* ie = e->h_idx_err;
+    if (ie[0]) {
+      const int n = ie[0], col = ie[1], val = ie[2], item = ie[3];
+      ie[0] = 0;
+      return fr_fail(e, FR_ERR_INVALID, "%d out-of-range indices since the last fr_sync (e.g. item %d, index column %d: %d); "
+                     "row 0 was read instead", n, item, col, val);
+    }
+  }
+  return FR_OK;
+}
+
+static void drop_all_graphs(fr_engine* e) {
+  std::lock_guard<std::mutex> g(e->mu);
+  std::vector<fr_stream_s*> all = e->streams;
+  all.push_back(e->default_stream);
+  for (fr_stream_s* s : all) {
+    for (fr_stream_s::Graph& gr : s->graphs) drop_graph(gr);
+    s->graphs.clear();
+  }
+}
+
+// Engine options (include/fleetrec.h FR_OPT_*).  Changing one synchronises the device and drops the cached CUDA
+// graphs, which were captured under the old setting.
+extern "C" fr_status fr_set_option(fr_engine* e, int option, int value) {
+  if (!e) return fr_fail(nullptr, FR_ERR_INVALID, "null engine");
+  FR_CUDA(e, cudaSetDevice(e->device));
+  switch (option) {
+    case FR_OPT_CUDA_GRAPHS: case FR_OPT_CHECK_INDICES: case FR_OPT_FUSE_LOOKUP:
+      if (value != 0 && value != 1) return fr_fail(e, FR_ERR_INVALID, "fr_set_option(%d): value must be 0 or 1", option);
+      break;
+    case FR_OPT_TILE_HINT:
+      if (value < FR_HINT_AUTO || value > FR_HINT_THROUGHPUT) return fr_fail(e, FR_ERR_INVALID, "FR_OPT_TILE_HINT: FR_HINT_*");
+      break;
+    case FR_OPT_F16_OPERANDS:
+      if (value < FR_F16_OFF || value > FR_F16_GUARDED) return fr_fail(e, FR_ERR_INVALID, "FR_OPT_F16_OPERANDS: FR_F16_*");
+      if (value != FR_F16_OFF && e->world > 1)
+        return fr_fail(e, FR_ERR_UNSUPPORTED, "fp16 operands are not available on a table-sharded engine");
+      break;
+    default:
+      return fr_fail(e, FR_ERR_INVALID, "fr_set_option: unknown option %d", option);
+  }
+  if (option == FR_OPT_CHECK_INDICES && value && !e->h_idx_err) {
+    FR_CUDA(e, cudaHostAlloc(&e->h_idx_err, 4 * sizeof(int), cudaHostAllocMapped));
+    memset(e->h_idx_err, 0, 4 * sizeof(int));
+  }
+  FR_CUDA(e, cudaDeviceSynchronize());
+  drop_all_graphs(e);
+  switch (option) {
+    case FR_OPT_CUDA_GRAPHS: e->use_graphs = value != 0; break;
+    case FR_OPT_CHECK_INDICES: e->check_indices = value != 0; break;
+    case FR_OPT_FUSE_LOOKUP: e->fuse_lookup = value != 0; break;
+    case FR_OPT_TILE_HINT: e->tile_hint = value; break;
+    case FR_OPT_F16_OPERANDS: e->f16_mode = value; e->f16_dirty = true; break;
+  }
+  return FR_OK;
+}
+
+extern "C" fr_status fr_f16_report(fr_engine* e, int* active, float* bounds5) {
+  fr_stream s = nullptr;
+  fr_status st = prep(e, &s, 0, true, true);   // runs the analysis if it is due (tables and weights must be loaded)
+  if (st != FR_OK) return st;
+  if (active) *active = fr_tc_f16(e) ? 1 : 0;
+  if (bounds5)
+    for (int i = 0; i < 5; i++) bounds5[i] = e->f16_bounds[i];
   return FR_OK;
 }
 
@@ -730,6 +911,7 @@ extern "C" fr_status fr_time_kernels(fr_engine* e, const int32_t* idx, int B, in
   for (int i = 0; i < 5; i++) ms5[i] = 0.f;
   cudaEvent_t e0 = s->ev[0], e1 = s->ev[1];
   const bool round = e->precision == FR_PREC_TF32;
+  s->f16 = fr_tc_f16(e);
   // every kernel is timed alone, back to back `reps` times, events on its own stream
   for (int pass = 0; pass < 2; pass++) {  // pass 0 = warm-up
     const float* in = s->d_x;
@@ -804,8 +986,7 @@ extern "C" fr_status fr_shard_init(fr_engine* e, int rank, int world, const int*
   }
   if (world > 32) return fr_fail(e, FR_ERR_UNSUPPORTED, "world %d > 32 (one warp publishes and polls the flags)", world);
   FR_CUDA(e, cudaSetDevice(e->device));
-  e->n_slots = 17;   // the default worker + 16 created workers
-  if (const char* env = getenv("FR_SHARD_SLOTS")) e->n_slots = atoi(env) > 0 ? atoi(env) : 1;
+  e->n_slots = 33;   // the default worker + 32 created workers
   const size_t bytes = (size_t)e->n_slots * fr_xchg_slot_floats(e) * sizeof(float);
   FR_CUDA(e, cudaMalloc(&e->d_xchg, bytes));
   FR_CUDA(e, cudaMemsetAsync(e->d_xchg, 0, bytes, e->default_stream->stream));
@@ -884,7 +1065,7 @@ extern "C" fr_status fr_shard_attach_local(fr_engine* e, fr_engine* const* peers
 static fr_status shard_check(fr_engine* e, const fr_stream_s* s, int B_global) {
   if (!e->d_xchg) return fr_fail(e, FR_ERR_STATE, "fr_shard_init first");
   if (s->slot >= e->n_slots)
-    return fr_fail(e, FR_ERR_UNSUPPORTED, "worker %d has no exchange slot (%d slots; FR_SHARD_SLOTS)", s->slot, e->n_slots);
+    return fr_fail(e, FR_ERR_UNSUPPORTED, "worker %d has no exchange slot (%d slots per engine)", s->slot, e->n_slots);
   if (!e->d_peer_ptrs) return fr_fail(e, FR_ERR_STATE, "exchange buffers not attached (fr_shard_import)");
   if (B_global % e->world) return fr_fail(e, FR_ERR_INVALID, "B_global %d not divisible by world %d", B_global, e->world);
   return FR_OK;
@@ -898,7 +1079,9 @@ extern "C" fr_status fr_shard_gather_push(fr_engine* e, const int32_t* idx, int 
   const int32_t* d_idx = nullptr;
   if ((st = stage_idx(e, s, idx, B_global, &d_idx)) != FR_OK) return st;
   if (B_global == 0) return FR_OK;
-  return frk_gather_push(e, d_idx, B_global, s->slot, 0, s->stream);
+  const int T = (int)e->tables.size();
+  return frk_shard_exchange(e, e->d_chunks, d_idx, T, d_idx + (size_t)e->rank * (B_global / e->world) * T, T, B_global,
+                            s->slot, 0, s->stream);
 }
 
 extern "C" fr_status fr_shard_mlp(fr_engine* e, int B_global, float* scores_local, fr_stream s) {
@@ -908,6 +1091,7 @@ extern "C" fr_status fr_shard_mlp(fr_engine* e, int B_global, float* scores_loca
   const int Bl = B_global / e->world;
   if (Bl == 0) return FR_OK;
   if (!scores_local) return fr_fail(e, FR_ERR_INVALID, "null scores");
+  s->f16 = false;
   float* d_scores = is_device_ptr(scores_local) ? scores_local : s->d_scores;
   if ((st = run_mlp(e, s, e->d_xchg + fr_xchg_concat_off(e, s->slot, 0), Bl, d_scores)) != FR_OK) return st;
   return emit_scores(e, s, scores_local, Bl, d_scores);
@@ -919,6 +1103,8 @@ extern "C" fr_status fr_shard_read_concat(fr_engine* e, int B_global, float* con
   if (!s) s = e->default_stream;
   FR_CUDA(e, cudaSetDevice(e->device));
   if (s->slot >= e->n_slots) return fr_fail(e, FR_ERR_UNSUPPORTED, "worker has no exchange slot");
+  if (*reinterpret_cast<volatile int*>(e->h_shard_err))
+    return fr_fail(e, FR_ERR_STATE, "a sharded step timed out waiting for a peer rank's rows; the concat buffer is incomplete");
   const int Bl = B_global / e->world;
   const float* src = e->d_xchg + fr_xchg_concat_off(e, s->slot, s->shard_step & 1);  // last step's parity
   FR_CUDA(e, cudaMemcpyAsync(concat_local, src, (size_t)Bl * e->D * sizeof(float), cudaMemcpyDefault, s->stream));
@@ -933,20 +1119,17 @@ extern "C" fr_status fr_shard_read_concat(fr_engine* e, int B_global, float* con
 // device, so the step is replayed as a CUDA graph (one per buffer parity).
 static fr_status shard_infer_enqueue(fr_engine* e, fr_stream_s* s, const int32_t* idx, int B_global, float* scores,
                                      int parity) {
+  s->f16 = false;
   const int32_t* d_idx = nullptr;
   fr_status st = stage_idx(e, s, idx, B_global, &d_idx);
   if (st != FR_OK) return st;
-  static const bool one_launch = getenv("FR_SHARD_ONE_LAUNCH") && atoi(getenv("FR_SHARD_ONE_LAUNCH")) != 0;
-  if (one_launch) {
-    if ((st = frk_shard_push_sync(e, d_idx, B_global, s->slot, parity, s->stream)) != FR_OK) return st;
-  } else {
-    if ((st = frk_gather_push(e, d_idx, B_global, s->slot, parity, s->stream)) != FR_OK) return st;
-    if ((st = frk_shard_signal_wait(e, s->slot, s->stream)) != FR_OK) return st;
-  }
+  const int T = (int)e->tables.size();
   const int Bl = B_global / e->world;
+  if ((st = frk_shard_exchange(e, e->d_chunks, d_idx, T, d_idx + (size_t)e->rank * Bl * T, T, B_global, s->slot, parity,
+                               s->stream)) != FR_OK) return st;
   float* d_scores = score_target(e, s, scores, Bl);
   const float* x = e->d_xchg + fr_xchg_concat_off(e, s->slot, parity);
-  if ((st = run_mlp(e, s, x, Bl, d_scores)) != FR_OK) return st;
+  if ((st = run_mlp(e, s, x, Bl, d_scores, s->slot)) != FR_OK) return st;
   return emit_scores(e, s, scores, Bl, d_scores);
 }
 
@@ -958,8 +1141,8 @@ extern "C" fr_status fr_shard_infer(fr_engine* e, const int32_t* idx, int B_glob
   if (!idx || !scores_local) return fr_fail(e, FR_ERR_INVALID, "null idx/scores");
   if (*e->h_shard_err) return fr_fail(e, FR_ERR_STATE, "a previous sharded step timed out waiting for a peer rank");
   const int parity = (++s->shard_step) & 1;
-  return run_or_replay(e, s, idx, scores_local, B_global, 1 + parity,
-                       [&] { return shard_infer_enqueue(e, s, idx, B_global, scores_local, parity); });
+  return run_or_replay(e, s, idx, scores_local, B_global, FR_GV_SHARD, 2, parity,
+                       [&](int par) { return shard_infer_enqueue(e, s, idx, B_global, scores_local, par); });
 }
 
 
@@ -982,6 +1165,7 @@ extern "C" fr_status fr_shard_tables(fr_engine* e, int which, int32_t* ids, int*
 // B_global * n_owned + B_local * n_repl indices per step instead of B_global * T.
 static fr_status shard_infer_sliced_enqueue(fr_engine* e, fr_stream_s* s, const int32_t* idx_owned, const int32_t* idx_repl,
                                             int B_global, float* scores, int parity) {
+  s->f16 = false;
   const int Bl = B_global / e->world;
   const size_t n_o = (size_t)B_global * e->owned_tables.size(), n_r = (size_t)Bl * e->repl_tables.size();
   const int32_t* d_o = idx_owned;
@@ -1002,16 +1186,14 @@ static fr_status shard_infer_sliced_enqueue(fr_engine* e, fr_stream_s* s, const 
     FR_CUDA(e, cudaMemcpyAsync(stage_r, idx_repl, n_r * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
     d_r = stage_r;
   }
-  fr_status st;
-  // experiment (FR_SHARD_PRIVATE=1, only when this rank owns no table, i.e. nothing is pushed): concat vectors in the
-  // worker's private buffer instead of the peer-mapped exchange region
-  static const bool priv_env = getenv("FR_SHARD_PRIVATE") && atoi(getenv("FR_SHARD_PRIVATE")) != 0;
-  const bool priv = priv_env && e->owned_tables.empty();
-  if ((st = frk_gather_push_sliced(e, d_o, d_r, B_global, s->slot, parity, s->stream, priv ? s->d_x : nullptr)) != FR_OK) return st;
-  if ((st = frk_shard_signal_wait(e, s->slot, s->stream)) != FR_OK) return st;
+  const FrChunk* chunks = frk_sliced_chunks(e);
+  if (!chunks) return FR_ERR_CUDA;   // (message left by the failing upload)
+  fr_status st = frk_shard_exchange(e, chunks, d_o, (int)e->owned_tables.size(), d_r, (int)e->repl_tables.size(), B_global,
+                                    s->slot, parity, s->stream);
+  if (st != FR_OK) return st;
   float* d_scores = score_target(e, s, scores, Bl);
-  const float* x = priv ? s->d_x : e->d_xchg + fr_xchg_concat_off(e, s->slot, parity);
-  if ((st = run_mlp(e, s, x, Bl, d_scores)) != FR_OK) return st;
+  const float* x = e->d_xchg + fr_xchg_concat_off(e, s->slot, parity);
+  if ((st = run_mlp(e, s, x, Bl, d_scores, s->slot)) != FR_OK) return st;
   return emit_scores(e, s, scores, Bl, d_scores);
 }
 
@@ -1027,8 +1209,8 @@ extern "C" fr_status fr_shard_infer_sliced(fr_engine* e, const int32_t* idx_owne
   if (*e->h_shard_err) return fr_fail(e, FR_ERR_STATE, "a previous sharded step timed out waiting for a peer rank");
   const int parity = (++s->shard_step) & 1;
   const void* key = idx_owned ? (const void*)idx_owned : (const void*)idx_repl;
-  return run_or_replay(e, s, key, scores_local, B_global, 3 + parity,
-                       [&] { return shard_infer_sliced_enqueue(e, s, idx_owned, idx_repl, B_global, scores_local, parity); },
+  return run_or_replay(e, s, key, scores_local, B_global, FR_GV_SHARD_SLICED, 2, parity,
+                       [&](int par) { return shard_infer_sliced_enqueue(e, s, idx_owned, idx_repl, B_global, scores_local, par); },
                        idx_owned ? idx_repl : nullptr);
 }
 
@@ -1050,5 +1232,7 @@ extern "C" fr_status fr_merge_tables(fr_engine* e, int a, int b, int dst) {
   if ((st = frk_merge(e, A.d, A.rows, A.dim, B.d, B.rows, B.dim, M.d, e->default_stream->stream)) != FR_OK) return st;
   FR_CUDA(e, cudaStreamSynchronize(e->default_stream->stream));
   M.loaded = true;
+  M.range_valid = false;
+  e->f16_dirty = true;
   return FR_OK;
 }

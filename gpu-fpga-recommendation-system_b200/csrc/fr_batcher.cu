@@ -18,6 +18,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <map>
 #include <thread>
 
 #include "fr_common.h"
@@ -60,9 +61,17 @@ struct fr_batcher {
   fr_status worker_error = FR_OK;
   std::string worker_error_msg;
 
+  // One ticket per submit.  A request larger than the room left in the open batch is split over several batches,
+  // which run concurrently on different workers and may finish in any order: the ticket completes when its LAST
+  // OUTSTANDING part retires (not when its last-submitted part does).
+  struct Pending {
+    int outstanding = 0;   // parts handed to batches and not yet scored
+    bool sealed = false;   // submit has handed out every part
+  };
   uint64_t next_ticket = 1;
   uint64_t completed_below = 1;       // every ticket < this is complete
   std::vector<uint64_t> done_out_of_order;
+  std::map<uint64_t, Pending> pending;
 
   std::vector<std::thread> workers;
   std::vector<fr_stream> streams;
@@ -104,6 +113,17 @@ void complete_ticket_locked(fr_batcher* b, uint64_t t) {
   }
 }
 
+// a part of ticket t has been scored (or, with part_done = false, submit has just sealed the ticket)
+void retire_part_locked(fr_batcher* b, uint64_t t, bool part_done) {
+  auto it = b->pending.find(t);
+  if (it == b->pending.end()) return;
+  if (part_done) it->second.outstanding--;
+  if (it->second.sealed && it->second.outstanding == 0) {
+    b->pending.erase(it);
+    complete_ticket_locked(b, t);
+  }
+}
+
 bool ticket_done_locked(const fr_batcher* b, uint64_t t) {
   if (t < b->completed_below) return true;
   for (uint64_t d : b->done_out_of_order)
@@ -122,7 +142,9 @@ void worker_main(fr_batcher* b, int w) {
       bt = b->closed.front();
       b->closed.pop_front();
     }
-    fr_status st = fr_infer(b->eng, bt->idx, bt->count, bt->scores, b->streams[w]);
+    // full batches replay a CUDA graph per (staging buffer, worker); a deadline-closed batch has a one-off size, which
+    // would only fill the graph cache with entries never used again
+    fr_status st = fr_infer_opts(b->eng, bt->idx, bt->count, bt->scores, b->streams[w], bt->count != b->max_batch);
     if (st == FR_OK) st = fr_sync(b->eng, b->streams[w]);
     const Clock::time_point now = Clock::now();
     if (st == FR_OK)
@@ -140,7 +162,7 @@ void worker_main(fr_batcher* b, int w) {
         const float us = std::chrono::duration<float, std::micro>(now - r.t_submit).count();
         if (b->latency_us.size() < 65536) b->latency_us.push_back(us);
         else b->latency_us[b->lat_pos++ % 65536] = us;
-        complete_ticket_locked(b, r.ticket);
+        retire_part_locked(b, r.ticket, true);
       }
       bt->count = 0;
       bt->reqs.clear();
@@ -214,16 +236,28 @@ extern "C" fr_status fr_batcher_submit(fr_batcher* b, const int32_t* idx, int n,
   if (!b) return fr_fail(nullptr, FR_ERR_INVALID, "fr_batcher_submit: null batcher");
   if (!idx || !scores_out || !ticket || n <= 0) return fr_fail(b->eng, FR_ERR_INVALID, "fr_batcher_submit: bad argument");
   int done = 0;
-  uint64_t last_ticket = 0;
   std::unique_lock<std::mutex> lk(b->mu);
   if (b->worker_error != FR_OK) return fr_fail(b->eng, b->worker_error, "batcher worker failed: %s", b->worker_error_msg.c_str());
-  // a request larger than the room left is split over consecutive batches; the returned ticket is
-  // that of its last part, and parts complete in order
+  const uint64_t my_ticket = b->next_ticket++;
+  b->pending[my_ticket] = fr_batcher::Pending();
+  // seal the ticket on every way out: a ticket whose submit failed half-way still completes once the parts already
+  // handed out have been scored, so nobody waits on it for ever
+  auto seal = [&] {
+    b->pending[my_ticket].sealed = true;
+    retire_part_locked(b, my_ticket, false);
+    b->cv_done.notify_all();
+  };
   while (done < n) {
-    if (b->stop) return fr_fail(b->eng, FR_ERR_STATE, "batcher is shutting down");
+    if (b->stop) {
+      seal();
+      return fr_fail(b->eng, FR_ERR_STATE, "batcher is shutting down");
+    }
     if (!b->open) {
-      b->cv_free.wait(lk, [&] { return b->stop || !b->pool.empty(); });
-      if (b->stop) return fr_fail(b->eng, FR_ERR_STATE, "batcher is shutting down");
+      b->cv_free.wait(lk, [&] { return b->stop || !b->pool.empty() || b->open; });
+      if (b->stop) {
+        seal();
+        return fr_fail(b->eng, FR_ERR_STATE, "batcher is shutting down");
+      }
       if (b->open) continue;   // another producer opened one while this thread waited
       b->open = b->pool.back();
       b->pool.pop_back();
@@ -234,14 +268,15 @@ extern "C" fr_status fr_batcher_submit(fr_batcher* b, const int32_t* idx, int n,
     Batch* bt = b->open;
     const int take = std::min(n - done, b->max_batch - bt->count);
     memcpy(bt->idx + (size_t)bt->count * b->T, idx + (size_t)done * b->T, (size_t)take * b->T * sizeof(int32_t));
-    last_ticket = b->next_ticket++;
-    bt->reqs.push_back({last_ticket, bt->count, take, scores_out + done, Clock::now()});
+    bt->reqs.push_back({my_ticket, bt->count, take, scores_out + done, Clock::now()});
+    b->pending[my_ticket].outstanding++;
     bt->count += take;
     done += take;
     b->n_requests++;
     if (bt->count == b->max_batch) close_open_locked(b, false);
   }
-  *ticket = last_ticket;
+  seal();
+  *ticket = my_ticket;
   return FR_OK;
 }
 

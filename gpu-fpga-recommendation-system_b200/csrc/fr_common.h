@@ -7,6 +7,7 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/fleetrec.h"
@@ -19,7 +20,7 @@ struct FrChunk {
   int table;           // column of idx[][] to read
   int stride4;         // row pitch in float4 (= dim/4)
   int col4;            // float4 offset inside the row
-  int pad_;
+  int rows;            // rows of the table (clamped to INT_MAX): bound of the optional index check
 };
 
 // The same piece, compact (16 bytes), for the lookup fused into layer 1 (staged in shared memory).
@@ -36,6 +37,9 @@ struct FrTable {
   int tier = 0;
   bool resident = true;  // false: owned by another rank
   bool loaded = false;
+  // max |x| and min non-zero |x| of the image (fr_precision.cu), valid until the table is written again
+  float maxabs = 0.f, minabs = 0.f;
+  bool range_valid = false;
 };
 
 struct fr_stream_s {
@@ -53,16 +57,20 @@ struct fr_stream_s {
     const void* idx2;       // second index block of the column-sliced sharded step (else null)
     const void* scores;
     int B, mode, prec;
-    int variant;            // 0: fr_infer; 1 / 2: fr_shard_infer with exchange-buffer parity 0 / 1; 3 / 4: column-sliced
-    int seen;               // direct (un-captured) runs so far
-    int launches;           // kernels inside the graph
-    cudaGraphExec_t exec;   // null until captured
+    int variant;            // FR_GV_*: which entry point (and how many sub-batches) the graph replays
+    int flavours;           // 1, or 2 for the sharded steps (one graph per exchange-buffer parity, captured together)
+    bool failed;            // capture / instantiation failed once: this combination runs un-graphed
+    int launches;           // kernels inside one graph
+    uint64_t last_use;      // LRU stamp
+    cudaGraphExec_t exec[2];
   };
   std::vector<Graph> graphs;
+  uint64_t graph_clock = 0;
   // table-sharded steps: which exchange slot this worker owns (creation order, identical on every
   // rank) and how many sharded steps it has issued (parity of the concat buffer = step & 1)
   int slot = 0;
   int shard_step = 0;
+  bool f16 = false;   // the step being enqueued runs the tcgen05 MLP on fp16 operands (set by the entry point)
 };
 
 struct FrPeer {
@@ -115,7 +123,10 @@ struct fr_engine {
   // FR_TC_F16=1 (experimental): the tcgen05 path computes on fp16 operands / activations (kind::f16, FP32
   // accumulate): the 11-bit significand TF32 keeps, in half the bytes, within fp16's range.  Single-GPU fr_infer
   // and fr_mlp_only only; the chain / fused / multicast / cp.async variants and fr_layer_only stay TF32-only.
-  bool tc_f16 = false;
+  bool tc_f16 = false;            // the decision: fr_infer computes on fp16 operands
+  int f16_mode = FR_F16_OFF;      // FR_OPT_F16_OPERANDS
+  bool f16_dirty = true;          // tables / weights / the option changed since the range analysis last ran
+  float f16_bounds[5] = {0, 0, 0, 0, 0};
   float* d_bias[FR_MAX_LAYERS] = {nullptr, nullptr, nullptr, nullptr};
   bool layer_loaded[FR_MAX_LAYERS] = {false, false, false, false};
   void* tc_state = nullptr;  // tensor maps etc., owned by fr_mlp_tc.cu
@@ -130,7 +141,7 @@ struct fr_engine {
   int rank = 0, world = 1;
   std::vector<int> owner;        // [T], -1 replicated
   float* d_xchg = nullptr;       // exchange region: n_slots x { concat[2][max_batch/world][D], flags[world] }
-  int n_slots = 0;               // in-flight sharded steps (one per worker stream), FR_SHARD_SLOTS
+  int n_slots = 0;               // in-flight sharded steps (one per worker stream)
   int next_slot = 0;             // slot handed to the next stream created
   int* d_step = nullptr;         // [n_slots] device-side step counters (the flag kernel increments its slot's)
   int* d_done = nullptr;         // [n_slots] blocks of the running exchange kernel that have finished their stores
@@ -149,10 +160,21 @@ struct fr_engine {
   int* h_watch = nullptr;        // pinned+mapped int[8]: which barrier wait a tcgen05 kernel gave up on before trapping
 
   std::atomic<int64_t> launches{0};
+  // CUDA-graph cache introspection (fr_graph_stats): steps replayed from a graph, steps that had to be captured
+  // first, steps issued as plain launches (graphs off, cache bypass, un-capturable buffers)
+  std::atomic<int64_t> graph_hits{0}, graph_captures{0}, graph_direct{0};
+  std::vector<std::pair<int, int>> warmed;   // (entry point, B) pairs that have run un-captured once (guarded by mu)
+  // fr_set_check_indices: the lookup kernels compare every index with its table's row count, count the offenders in
+  // h_idx_err (pinned + mapped: {count, table column, value, item}) and read row 0 instead; fr_sync reports them
+  int tile_hint = 0;              // FR_HINT_*: latency- or throughput-oriented tcgen05 tiles (fr_set_option)
+  bool check_indices = false;
+  int* h_idx_err = nullptr;
   mutable std::string err;
 };
 
 fr_status fr_fail(const fr_engine* e, fr_status code, const char* fmt, ...);
+// fr_infer with the CUDA-graph cache bypassed on request (one-shot buffer / batch-size combinations)
+fr_status fr_infer_opts(fr_engine* e, const int32_t* idx, int B, float* scores, fr_stream s, bool no_graph);
 // the tcgen05 path runs on fp16 operands (FR_TC_F16=1 and the engine's precision is the tensor-core one)
 inline bool fr_tc_f16(const fr_engine* e) { return e->tc_f16 && e->precision == FR_PREC_TF32 && e->world == 1; }
 #define FR_CUDA(e, call)                                                                          \
@@ -179,17 +201,30 @@ fr_status frk_gather(fr_engine* e, const int32_t* d_idx, int B, float* d_out, bo
                      bool out_f16 = false);
 // fp32 -> fp16 (round to nearest even), n elements (n % 4 == 0)
 fr_status frk_to_f16(fr_engine* e, const float* src, void* dst, int64_t n, cudaStream_t st);
+// fp32 -> tf32 (round to nearest, ties away: cvt.rna), n elements (n % 4 == 0); dst may alias src
+fr_status frk_round_tf32(fr_engine* e, const float* src, float* dst, int64_t n, cudaStream_t st);
 // copy `bytes` (a multiple of 16) of indices from a mapped page-locked host buffer into device memory with SM loads
 fr_status frk_stage_idx(fr_engine* e, const void* mapped_src, int32_t* d_dst, size_t bytes, cudaStream_t st);
-fr_status frk_gather_push(fr_engine* e, const int32_t* d_idx, int B_global, int slot, int parity, cudaStream_t st);
-// the same from column-sliced index blocks: d_idx_owned [B_global][owned_tables], d_idx_repl [B_global/world][repl_tables]
-fr_status frk_gather_push_sliced(fr_engine* e, const int32_t* d_idx_owned, const int32_t* d_idx_repl, int B_global, int slot,
-                                 int parity, cudaStream_t st, float* private_out = nullptr);
+// The exchange of a table-sharded step in one launch: this rank's owned pieces of every item of the global batch are
+// stored into the concat buffer (slot, parity) of the rank that owns the item, the replicated pieces of its own items
+// into its own, and the last block publishes the step to every peer.  idx_owned [B_global][T_owned], idx_repl
+// [B_global / world][T_repl] (row 0 = this rank's first item); chunks[].table names the column in those blocks.
+fr_status frk_shard_exchange(fr_engine* e, const FrChunk* chunks, const int32_t* d_idx_owned, int T_owned,
+                             const int32_t* d_idx_repl, int T_repl, int B_global, int slot, int parity, cudaStream_t st);
+const FrChunk* frk_sliced_chunks(fr_engine* e);   // descriptors whose `table` is the column of a column-sliced block
 void fr_shard_table_lists(fr_engine* e);   // fills owned_tables / repl_tables from owner[] (idempotent)
-// publish "this rank finished pushing the next step of `slot`" to every peer, then wait for all peers' flags
-fr_status frk_shard_signal_wait(fr_engine* e, int slot, cudaStream_t st);
-// push + replicated lookup + flags in one launch (the exchange of fr_shard_infer)
-fr_status frk_shard_push_sync(fr_engine* e, const int32_t* d_idx, int B_global, int slot, int parity, cudaStream_t st);
+// wait (on the device) until every rank has published the slot's current step; the tcgen05 path does this inside
+// its first kernel instead (FrPeerWait)
+fr_status frk_shard_wait(fr_engine* e, int slot, cudaStream_t st);
+// a peer that has not published after this many SM cycles (~2 s) is given up on: h_shard_err is set, fr_sync reports it
+constexpr long long kShardTimeoutCycles = 4000000000ll;
+// what the first MLP kernel of a sharded step polls before it touches the concat buffer
+struct FrPeerWait {
+  const int* flags;   // this rank's flag block of the slot: flags[r] = last step rank r has pushed
+  const int* step;    // the slot's step counter (already bumped by this rank's exchange kernel)
+  int world;
+  int* err;           // device alias of h_shard_err
+};
 
 // exchange-region geometry (floats): one slot = two concat buffers + a flag block
 inline size_t fr_xchg_buf_floats(const fr_engine* e) { return (size_t)(e->max_batch / e->world) * e->D; }
@@ -220,8 +255,12 @@ fr_status frk_final_dot(fr_engine* e, const float* H, const float* w, const floa
 
 // TF32 tcgen05 path (fr_mlp_tc.cu)
 fr_status frtc_prepare(fr_engine* e);                // builds tensor maps for weights; idempotent
+fr_status frtc_prepare_f16(fr_engine* e);            // tensor maps of the fp16 weight copies (after frtc_prepare)
+// FR_F16_GUARDED: bound every operand of the MLP from the loaded tables and weights, decide e->tc_f16 (fr_precision.cu)
+fr_status fr_f16_analyse(fr_engine* e);
 void frtc_destroy(fr_engine* e);
-fr_status frtc_layer(fr_engine* e, fr_stream_s* s, int k, const float* in, int B, float* d_scores);
+fr_status frtc_layer(fr_engine* e, fr_stream_s* s, int k, const float* in, int B, float* d_scores,
+                     const FrPeerWait* wait = nullptr);   // wait: poll the peers' step flags before the first load of `in`
 // the whole MLP (3 GEMMs + output layer) as ONE persistent launch: in [B][dims[0]] -> d_scores [B]; uses s->d_h[0..1]
 bool frtc_can_chain(const fr_engine* e, int B);
 fr_status frtc_chain(fr_engine* e, fr_stream_s* s, const float* in, int B, float* d_scores);

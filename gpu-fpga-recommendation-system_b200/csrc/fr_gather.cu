@@ -59,6 +59,18 @@ __device__ __forceinline__ float4 ld_row8(const float4* base, int64_t piece) {
   return v;
 }
 
+// Optional bounds check of one index: an offender is counted in err[0] (the first one also leaves its index column,
+// value and item in err[1..3]) and row 0 is read in its place.
+__device__ __forceinline__ int64_t checked_row(int64_t row, const FrChunk& ch, int item, int* err) {
+  if ((uint64_t)row < (uint64_t)ch.rows) return row;
+  if (ch.col4 == 0 && atomicAdd(err, 1) == 0) {   // one report per (item, table), by the piece at the row's head
+    err[1] = ch.table;
+    err[2] = (int)row;
+    err[3] = item;
+  }
+  return 0;
+}
+
 // PUSH = false: out4 is the local [B][C] buffer.
 // PUSH = true : peer_out[r] is rank r's exchange buffer; item b lands on rank
 //               b / items_per_rank at local row b % items_per_rank (NVLink peer stores).
@@ -68,7 +80,8 @@ __global__ void __launch_bounds__(256) gather_concat_kernel(const FrChunk* __res
                                                             const int32_t* __restrict__ idx, int T, int b_begin,
                                                             int b_end, float4* __restrict__ out4,
                                                             float4* const* __restrict__ peer_out, int C,
-                                                            int items_per_rank, long long peer_off4) {
+                                                            int items_per_rank, long long peer_off4,
+                                                            int* __restrict__ idx_err) {
   // one thread = one piece x kItems consecutive items; block = (pieces rounded to 32, <= 128) x item groups.
   // (A flattened (piece, item group) space, which keeps every lane busy when a rank's piece subset is not a
   // multiple of 32, was measured SLOWER for the sharded push: 13.4 against 12.0 us per step at two ranks.)
@@ -83,6 +96,10 @@ __global__ void __launch_bounds__(256) gather_concat_kernel(const FrChunk* __res
   for (int i = 0; i < kItems; i++) {
     const int b = b0 + i;
     row[i] = (b < b_end) ? (int64_t)__ldg(idx + (size_t)b * T + ch.table) : 0;
+  }
+  if (idx_err) {   // fr_set_check_indices: the reference never checks (embedding_47_krnl.cpp:925-934)
+#pragma unroll
+    for (int i = 0; i < kItems; i++) row[i] = checked_row(row[i], ch, b0 + i, idx_err);
   }
   float4 v[kItems];
 #pragma unroll
@@ -232,8 +249,10 @@ void launch_gather(const fr_engine* e, const int* d_ids, int n_chunks, const int
     kern = e->table_dtype == FR_TABLE_F32 ? gather_concat_kernel<false, false, FR_TABLE_F32, true>
            : e->table_dtype == FR_TABLE_F16 ? gather_concat_kernel<false, false, FR_TABLE_F16, true>
                                             : gather_concat_kernel<false, false, FR_TABLE_BF16, true>;
+  int* d_err = nullptr;
+  if (e->check_indices && e->h_idx_err) cudaHostGetDevicePointer(&d_err, e->h_idx_err, 0);
   cudaLaunchKernelEx(&cfg, kern, chunks, d_ids, n_chunks, d_idx, idx_cols, b_begin, b_end, out4, peers, C, items_per_rank,
-                     peer_off4);
+                     peer_off4, d_err);
 }
 
 }  // namespace
@@ -251,7 +270,7 @@ fr_status frk_upload_chunks(fr_engine* e) {
       c.table = s.table;
       c.stride4 = t.dim / 4;
       c.col4 = s.col / 4 + k;
-      c.pad_ = 0;
+      c.rows = t.rows > 0x7FFFFFFF ? 0x7FFFFFFF : (int)t.rows;
       hf[s.dst / 4 + k] = {c.base, c.table, (c.stride4 << 8) | c.col4};
       covered[s.dst / 4 + k] = 1;
     }
@@ -304,6 +323,22 @@ __global__ void to_f16_kernel(const float4* __restrict__ src, uint2* __restrict_
 fr_status frk_to_f16(fr_engine* e, const float* src, void* dst, int64_t n, cudaStream_t st) {
   const int64_t n4 = n / 4;
   to_f16_kernel<<<grid_for(n4, 256, e->sm_count), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst), n4);
+  e->launches++;
+  FR_CUDA(e, cudaGetLastError());
+  return FR_OK;
+}
+
+__global__ void round_tf32_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = src[i];
+    v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+    dst[i] = v;
+  }
+}
+
+fr_status frk_round_tf32(fr_engine* e, const float* src, float* dst, int64_t n, cudaStream_t st) {
+  const int64_t n4 = n / 4;
+  round_tf32_kernel<<<grid_for(n4, 256, e->sm_count), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), n4);
   e->launches++;
   FR_CUDA(e, cudaGetLastError());
   return FR_OK;
@@ -429,138 +464,50 @@ void fr_shard_table_lists(fr_engine* e) {
   }
 }
 
-fr_status frk_gather_push(fr_engine* e, const int32_t* d_idx, int B_global, int slot, int parity, cudaStream_t st) {
-  if (!e->shard_lists_built) {
-    std::lock_guard<std::mutex> g(e->mu);
-    if (!e->shard_lists_built) {
-      fr_status s = build_shard_lists(e);
-      if (s != FR_OK) return s;
-    }
-  }
-  const int per = B_global / e->world;
-  const bool round = (e->precision == FR_PREC_TF32);
-  // concat buffer `parity` of slot `slot` in every rank's exchange region (same layout on all ranks)
-  const long long off4 = (long long)(fr_xchg_concat_off(e, slot, parity) / 4);
-  float4* const* peers = reinterpret_cast<float4* const*>(e->d_peer_ptrs);
-  if (e->n_owned) {
-    if (round) launch_gather<true, true>(e, e->d_owned_ids, e->n_owned, d_idx, 0, B_global, nullptr, peers, per, st, off4);
-    else launch_gather<false, true>(e, e->d_owned_ids, e->n_owned, d_idx, 0, B_global, nullptr, peers, per, st, off4);
-    e->launches++;
-  }
-  if (e->n_repl) {
-    // local items only, written into this rank's own buffer (row b - rank*per)
-    float4* own = reinterpret_cast<float4*>(e->d_xchg) + off4 - (long long)e->rank * per * (e->D / 4);
-    const int b0 = e->rank * per, b1 = (e->rank + 1) * per;
-    if (round) launch_gather<true, false>(e, e->d_repl_ids, e->n_repl, d_idx, b0, b1, own, nullptr, 1, st);
-    else launch_gather<false, false>(e, e->d_repl_ids, e->n_repl, d_idx, b0, b1, own, nullptr, 1, st);
-    e->launches++;
-  }
-  FR_CUDA(e, cudaGetLastError());
-  return FR_OK;
-}
-
-// The same step fed by column-sliced index blocks (what each FPGA of the reference receives: only its own tables'
-// indices): the push reads [B_global][owned tables], the replicated lookup [B_global / world][replicated tables].
-fr_status frk_gather_push_sliced(fr_engine* e, const int32_t* d_idx_owned, const int32_t* d_idx_repl, int B_global, int slot,
-                                 int parity, cudaStream_t st, float* private_out) {
-  if (!e->shard_lists_built) {
-    std::lock_guard<std::mutex> g(e->mu);
-    if (!e->shard_lists_built) {
-      fr_status s = build_shard_lists(e);
-      if (s != FR_OK) return s;
-    }
-  }
-  const int per = B_global / e->world;
-  const bool round = (e->precision == FR_PREC_TF32);
-  const long long off4 = (long long)(fr_xchg_concat_off(e, slot, parity) / 4);
-  float4* const* peers = reinterpret_cast<float4* const*>(e->d_peer_ptrs);
-  const int n_ot = (int)e->owned_tables.size(), n_rt = (int)e->repl_tables.size();
-  if (e->n_owned) {
-    if (round) launch_gather<true, true>(e, e->d_owned_ids, e->n_owned, d_idx_owned, 0, B_global, nullptr, peers, per, st, off4,
-                                         e->d_chunks_sliced, n_ot);
-    else launch_gather<false, true>(e, e->d_owned_ids, e->n_owned, d_idx_owned, 0, B_global, nullptr, peers, per, st, off4,
-                                    e->d_chunks_sliced, n_ot);
-    e->launches++;
-  }
-  if (e->n_repl) {
-    float4* own = (private_out ? reinterpret_cast<float4*>(private_out) : reinterpret_cast<float4*>(e->d_xchg) + off4) -
-                  (long long)e->rank * per * (e->D / 4);
-    const int b0 = e->rank * per, b1 = (e->rank + 1) * per;
-    // the block holds this rank's items only: row 0 is global item b0
-    const int32_t* base = d_idx_repl - (size_t)b0 * n_rt;
-    if (round) launch_gather<true, false>(e, e->d_repl_ids, e->n_repl, base, b0, b1, own, nullptr, 1, st, 0, e->d_chunks_sliced, n_rt);
-    else launch_gather<false, false>(e, e->d_repl_ids, e->n_repl, base, b0, b1, own, nullptr, 1, st, 0, e->d_chunks_sliced, n_rt);
-    e->launches++;
-  }
-  FR_CUDA(e, cudaGetLastError());
-  return FR_OK;
-}
-
-// Device-side step barrier of the sharded path.  Every slot of a rank's exchange region ends in a
-// flag block: flags[r] = last step of this slot rank r finished pushing.  The step number lives in
-// device memory (one counter per slot, bumped here), so the launch has no per-step argument and the
-// whole sharded step can be replayed as a CUDA graph.
-namespace {
-__global__ void shard_signal_wait_kernel(float* const* __restrict__ peer_base, long long flags_off_floats, int rank,
-                                         int world, int* step_counter, int* err, long long timeout_cycles) {
-  const int t = threadIdx.x;
-  const int step = *step_counter + 1;   // kernels of one slot are stream-ordered: no race on the counter
-  __syncwarp();
-  // all stores of the preceding push kernel(s) are complete (stream order); make them visible
-  // system-wide before the flag that announces them
-  __threadfence_system();
-  if (t < world) {
-    int* f = reinterpret_cast<int*>(peer_base[t] + flags_off_floats) + rank;
-    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f), "r"(step) : "memory");
-  }
-  if (t == 0) *step_counter = step;
-  if (t < world) {
-    const int* mine = reinterpret_cast<const int*>(peer_base[rank] + flags_off_floats) + t;
-    const long long t0 = clock64();
-    int v;
-    do {
-      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-      if (timeout_cycles < 0) break;
-      if (v < step && clock64() - t0 > timeout_cycles) {
-        *reinterpret_cast<volatile int*>(err) = 1;   // surfaced by the next fr_shard_infer / fr_sync
-        break;
-      }
-    } while (v < step);
-  }
-}
-}  // namespace
-
-// ---- the whole exchange of a sharded step in ONE launch ---------------------------------------
+// ---- the exchange of a table-sharded step in ONE launch ------------------------------------------
 // Blocks [0, g1): this rank's OWNED pieces for every item of the global batch, stored straight into
-// the concat buffer of the rank that owns the item (NVLink peer stores).  Blocks [g1, g1 + g2): the
-// REPLICATED (on-chip class) pieces for this rank's own items.  The block that finishes last (a
-// device-wide counter, the classic threadfence reduction) publishes "rank r pushed step n of this
-// slot" into every peer's flag block and waits until all peers have published n: the kernel does not
-// complete before every rank's rows have landed here, so the MLP simply follows it in the stream.
-// Against push + replicated lookup + flag kernel this is 4 launches per step instead of 6.
+// the concat buffer of the rank that owns the item (128-bit NVLink peer stores: lookup and all-to-all
+// are one kernel).  Blocks [g1, g1 + g2): the REPLICATED (on-chip class) pieces for this rank's own
+// items.  The block that finishes last (a device-wide counter, the threadfence-reduction pattern)
+// bumps the slot's step counter and publishes "rank r has pushed step n of this slot" into every
+// peer's flag block (st.release.sys).  Nobody waits here: the first MLP kernel of the step polls the
+// flags right before its first load of the concat buffer (tc_linear_kernel, TcParams::wait_*), so its
+// set-up and the other workers' kernels run while the peers' rows are still in flight; the FP32 path
+// waits in shard_wait_kernel.  The step number lives in device memory, so the launch has no per-step
+// argument and the whole step replays as a CUDA graph.
+//
+// Index blocks: idx_owned [B_global][T_owned] over all items, idx_repl [per][T_repl] over this rank's
+// items (for full rows both point into the same [B_global][T] block); `chunks[].table` is the column.
 namespace {
 template <bool ROUND, int DT>
 __global__ void __launch_bounds__(256)
-shard_push_sync_kernel(const FrChunk* __restrict__ chunks, const int* __restrict__ owned_ids, int n_owned,
-                       const int* __restrict__ repl_ids, int n_repl, const int32_t* __restrict__ idx, int T,
-                       int B_global, int per, int rank, int world, float4* const* __restrict__ peer_out, int C,
-                       long long peer_off4, int g1, int gx1, int gx2, float* const* __restrict__ peer_base,
-                       long long flags_off_floats, int* step_counter, int* done_counter, int* err,
-                       long long timeout_cycles) {
+shard_exchange_kernel(const FrChunk* __restrict__ chunks, const int* __restrict__ owned_ids, int n_owned,
+                      const int* __restrict__ repl_ids, int n_repl, const int32_t* __restrict__ idx_owned, int T_owned,
+                      const int32_t* __restrict__ idx_repl, int T_repl, int B_global, int per, int rank, int world,
+                      float4* const* __restrict__ peer_out, int C, long long peer_off4, int g1, int gx1, int gx2,
+                      float* const* __restrict__ peer_base, long long flags_off_floats, int* step_counter,
+                      int* done_counter, int* __restrict__ idx_err) {
   const int part = (int)blockIdx.x < g1 ? 0 : 1;
   const int lb = part ? (int)blockIdx.x - g1 : (int)blockIdx.x;
   const int gx = part ? gx2 : gx1;
   const int n_chunks = part ? n_repl : n_owned;
   const int* ids = part ? repl_ids : owned_ids;
-  const int b_end = part ? (rank + 1) * per : B_global;
+  const int32_t* idx = part ? idx_repl : idx_owned;
+  const int T = part ? T_repl : T_owned;
+  const int n_items = part ? per : B_global;          // rows of `idx`
+  const int item0 = part ? rank * per : 0;            // global item of idx row 0
   const int ci = (lb % gx) * 32 + threadIdx.x;
-  const int b0 = (part ? rank * per : 0) + ((lb / gx) * 8 + threadIdx.y) * kItems;
-  if (ci < n_chunks) {
+  const int i0 = ((lb / gx) * 8 + threadIdx.y) * kItems;
+  if (ci < n_chunks && i0 < n_items) {
     const int c = ids[ci];
     const FrChunk ch = chunks[c];
     int64_t row[kItems];
 #pragma unroll
-    for (int i = 0; i < kItems; i++) row[i] = (b0 + i < b_end) ? (int64_t)__ldg(idx + (size_t)(b0 + i) * T + ch.table) : 0;
+    for (int i = 0; i < kItems; i++) row[i] = (i0 + i < n_items) ? (int64_t)__ldg(idx + (size_t)(i0 + i) * T + ch.table) : 0;
+    if (idx_err) {
+#pragma unroll
+      for (int i = 0; i < kItems; i++) row[i] = checked_row(row[i], ch, item0 + i0 + i, idx_err);
+    }
     float4 v[kItems];
 #pragma unroll
     for (int i = 0; i < kItems; i++)
@@ -568,8 +515,8 @@ shard_push_sync_kernel(const FrChunk* __restrict__ chunks, const int* __restrict
                                 : ld_row8<DT == FR_TABLE_F32 ? FR_TABLE_F16 : DT>(ch.base, row[i] * ch.stride4 + ch.col4);
 #pragma unroll
     for (int i = 0; i < kItems; i++) {
-      const int b = b0 + i;
-      if (b >= b_end) break;
+      if (i0 + i >= n_items) break;
+      const int b = item0 + i0 + i;
       float4 o = v[i];
       if (ROUND) {
         o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
@@ -578,7 +525,7 @@ shard_push_sync_kernel(const FrChunk* __restrict__ chunks, const int* __restrict
       peer_out[r][peer_off4 + (size_t)(b - r * per) * C + c] = o;
     }
   }
-  // ---- last block out publishes and waits ----
+  // ---- last block out publishes ----
   __shared__ int s_last;
   __syncthreads();                             // the block's stores are ordered before thread 0's fence (CTA barrier),
   if (threadIdx.x == 0 && threadIdx.y == 0) {  // and the fence is cumulative: one system fence per block, not 256
@@ -589,7 +536,7 @@ shard_push_sync_kernel(const FrChunk* __restrict__ chunks, const int* __restrict
   if (!s_last || threadIdx.y != 0) return;
   __threadfence_system();                      // every other block's stores, ordered before their atomicAdd
   const int t = threadIdx.x;
-  const int step = *step_counter + 1;          // launches of one slot are stream-ordered: no race
+  const int step = *reinterpret_cast<volatile int*>(step_counter) + 1;   // launches of one slot are stream-ordered
   __syncwarp();
   if (t == 0) {
     *done_counter = 0;
@@ -598,61 +545,72 @@ shard_push_sync_kernel(const FrChunk* __restrict__ chunks, const int* __restrict
   if (t < world) {
     int* f = reinterpret_cast<int*>(peer_base[t] + flags_off_floats) + rank;
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f), "r"(step) : "memory");
-    const int* mine = reinterpret_cast<const int*>(peer_base[rank] + flags_off_floats) + t;
-    const long long t0 = clock64();
-    int v;
-    do {
-      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-      if (v < step && clock64() - t0 > timeout_cycles) {
-        *reinterpret_cast<volatile int*>(err) = 1;   // surfaced by the next fr_shard_infer / fr_sync
-        break;
-      }
-    } while (v < step);
   }
+}
+
+// Wait until every rank has published the slot's current step (FP32 path and the two-phase API; the tcgen05 path
+// waits inside its first kernel).  One warp, lane t watches rank t.
+__global__ void shard_wait_kernel(const int* __restrict__ flags, int world, const int* step_counter, int* err,
+                                  long long timeout_cycles) {
+  const int t = threadIdx.x;
+  const int step = *reinterpret_cast<const volatile int*>(step_counter);
+  if (t >= world) return;
+  const long long t0 = clock64();
+  int v;
+  do {
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + t) : "memory");
+    if (v < step && clock64() - t0 > timeout_cycles) {
+      *reinterpret_cast<volatile int*>(err) = 1;   // reported by fr_sync and by the next sharded call
+      break;
+    }
+  } while (v < step);
 }
 }  // namespace
 
-fr_status frk_shard_push_sync(fr_engine* e, const int32_t* d_idx, int B_global, int slot, int parity, cudaStream_t st) {
-  if (!e->shard_lists_built) {
-    std::lock_guard<std::mutex> g(e->mu);
-    if (!e->shard_lists_built) {
-      fr_status s = build_shard_lists(e);
-      if (s != FR_OK) return s;
-    }
-  }
+static fr_status ensure_shard_lists(fr_engine* e) {
+  if (e->shard_lists_built) return FR_OK;
+  std::lock_guard<std::mutex> g(e->mu);
+  if (e->shard_lists_built) return FR_OK;
+  return build_shard_lists(e);
+}
+
+fr_status frk_shard_exchange(fr_engine* e, const FrChunk* chunks, const int32_t* d_idx_owned, int T_owned,
+                             const int32_t* d_idx_repl, int T_repl, int B_global, int slot, int parity, cudaStream_t st) {
+  fr_status s = ensure_shard_lists(e);
+  if (s != FR_OK) return s;
   const int per = B_global / e->world;
   const int gx1 = (e->n_owned + 31) / 32, gy1 = e->n_owned ? (B_global + 8 * kItems - 1) / (8 * kItems) : 0;
   const int gx2 = (e->n_repl + 31) / 32, gy2 = e->n_repl ? (per + 8 * kItems - 1) / (8 * kItems) : 0;
   const int g1 = gx1 * gy1, g2 = gx2 * gy2;
-  if (g1 + g2 == 0) return fr_fail(e, FR_ERR_STATE, "this rank holds no table at all");
-  int* d_err = nullptr;
-  FR_CUDA(e, cudaHostGetDevicePointer(&d_err, e->h_shard_err, 0));
+  int* d_idx_err = nullptr;
+  if (e->check_indices && e->h_idx_err) FR_CUDA(e, cudaHostGetDevicePointer(&d_idx_err, e->h_idx_err, 0));
   const bool round = (e->precision == FR_PREC_TF32);
-  auto kern = round ? (e->table_dtype == FR_TABLE_F32   ? shard_push_sync_kernel<true, FR_TABLE_F32>
-                       : e->table_dtype == FR_TABLE_F16 ? shard_push_sync_kernel<true, FR_TABLE_F16>
-                                                        : shard_push_sync_kernel<true, FR_TABLE_BF16>)
-                    : (e->table_dtype == FR_TABLE_F32   ? shard_push_sync_kernel<false, FR_TABLE_F32>
-                       : e->table_dtype == FR_TABLE_F16 ? shard_push_sync_kernel<false, FR_TABLE_F16>
-                                                        : shard_push_sync_kernel<false, FR_TABLE_BF16>);
-  kern<<<g1 + g2, dim3(32, 8), 0, st>>>(e->d_chunks, e->d_owned_ids, e->n_owned, e->d_repl_ids, e->n_repl, d_idx,
-                                        (int)e->tables.size(), B_global, per, e->rank, e->world,
-                                        reinterpret_cast<float4* const*>(e->d_peer_ptrs), e->D / 4,
-                                        (long long)(fr_xchg_concat_off(e, slot, parity) / 4), g1, gx1 ? gx1 : 1,
-                                        gx2 ? gx2 : 1, e->d_peer_ptrs, (long long)fr_xchg_flags_off(e, slot),
-                                        e->d_step + slot, e->d_done + slot, d_err, 20000000000ll /* ~10 s at 1.9 GHz */);
+  auto kern = round ? (e->table_dtype == FR_TABLE_F32   ? shard_exchange_kernel<true, FR_TABLE_F32>
+                       : e->table_dtype == FR_TABLE_F16 ? shard_exchange_kernel<true, FR_TABLE_F16>
+                                                        : shard_exchange_kernel<true, FR_TABLE_BF16>)
+                    : (e->table_dtype == FR_TABLE_F32   ? shard_exchange_kernel<false, FR_TABLE_F32>
+                       : e->table_dtype == FR_TABLE_F16 ? shard_exchange_kernel<false, FR_TABLE_F16>
+                                                        : shard_exchange_kernel<false, FR_TABLE_BF16>);
+  // a rank that holds no table at all still publishes its (empty) step: one idle block
+  kern<<<g1 + g2 > 0 ? g1 + g2 : 1, dim3(32, 8), 0, st>>>(
+      chunks, e->d_owned_ids, e->n_owned, e->d_repl_ids, e->n_repl, d_idx_owned, T_owned, d_idx_repl, T_repl, B_global, per,
+      e->rank, e->world, reinterpret_cast<float4* const*>(e->d_peer_ptrs), e->D / 4,
+      (long long)(fr_xchg_concat_off(e, slot, parity) / 4), g1, gx1 ? gx1 : 1, gx2 ? gx2 : 1, e->d_peer_ptrs,
+      (long long)fr_xchg_flags_off(e, slot), e->d_step + slot, e->d_done + slot, d_idx_err);
   e->launches++;
   FR_CUDA(e, cudaGetLastError());
   return FR_OK;
 }
 
-fr_status frk_shard_signal_wait(fr_engine* e, int slot, cudaStream_t st) {
+const FrChunk* frk_sliced_chunks(fr_engine* e) {
+  return ensure_shard_lists(e) == FR_OK ? e->d_chunks_sliced : nullptr;
+}
+
+fr_status frk_shard_wait(fr_engine* e, int slot, cudaStream_t st) {
   int* d_err = nullptr;
   FR_CUDA(e, cudaHostGetDevicePointer(&d_err, e->h_shard_err, 0));
-  static const bool nowait = getenv("FR_SHARD_NOWAIT") != nullptr;   // timing experiments only: results are then racy
-  static const bool noflags = getenv("FR_SHARD_NOWAIT") && atoi(getenv("FR_SHARD_NOWAIT")) == 2;   // no flag kernel at all
-  if (noflags) return FR_OK;
-  shard_signal_wait_kernel<<<1, 32, 0, st>>>(e->d_peer_ptrs, (long long)fr_xchg_flags_off(e, slot), e->rank, e->world,
-                                             e->d_step + slot, d_err, nowait ? -1ll : 20000000000ll /* ~10 s at 1.9 GHz */);
+  shard_wait_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const int*>(e->d_xchg + fr_xchg_flags_off(e, slot)), e->world,
+                                      e->d_step + slot, d_err, kShardTimeoutCycles);
   e->launches++;
   FR_CUDA(e, cudaGetLastError());
   return FR_OK;

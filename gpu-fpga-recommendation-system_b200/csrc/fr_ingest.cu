@@ -46,6 +46,7 @@ struct fr_ingest {
   fr_engine* eng = nullptr;
   fr_ingest_config cfg;
   size_t block_bytes = 0;
+  std::vector<int64_t> rows;        // rows of every table: bound of the FR_INGEST_INDICES validation
   std::vector<Conn> conns;
   std::mutex mu;
   int64_t global_batch_count = 0;   // cuda_server.c:23
@@ -110,6 +111,23 @@ void conn_main(fr_ingest* g, int ci) {
                                                    std::to_string(g->block_bytes) + " bytes)");
       break;
     }
+    if (g->cfg.payload == FR_INGEST_INDICES) {
+      // the block came off a socket: an index outside its table would be an out-of-bounds device read
+      const int32_t* ix = reinterpret_cast<const int32_t*>(c.in[slot]);
+      const size_t T = g->rows.size();
+      size_t bad = (size_t)-1;
+      for (size_t i = 0, n = (size_t)g->cfg.batch * T; i < n; i++)
+        if ((uint64_t)(int64_t)ix[i] >= (uint64_t)g->rows[i % T]) {
+          bad = i;
+          break;
+        }
+      if (bad != (size_t)-1) {
+        conn_fail(c, FR_ERR_INVALID, "block " + std::to_string(batch_no) + ": index " + std::to_string(ix[bad]) + " of table " +
+                                         std::to_string(bad % T) + " (item " + std::to_string(bad / T) + ") is outside its " +
+                                         std::to_string(g->rows[bad % T]) + " rows");
+        break;   // the blocks already in flight are still retired below
+      }
+    }
     fr_status st = g->cfg.payload == FR_INGEST_CONCAT
                        ? fr_mlp_only(g->eng, reinterpret_cast<const float*>(c.in[slot]), g->cfg.batch, c.out[slot], c.stream)
                        : fr_infer(g->eng, reinterpret_cast<const int32_t*>(c.in[slot]), g->cfg.batch, c.out[slot], c.stream);
@@ -148,6 +166,7 @@ extern "C" fr_status fr_ingest_start(fr_engine* e, const fr_ingest_config* cfg, 
   g->cfg = *cfg;
   g->block_bytes = (size_t)cfg->batch * (cfg->payload == FR_INGEST_CONCAT ? (size_t)e->D * sizeof(float)
                                                                           : e->tables.size() * sizeof(int32_t));
+  for (const FrTable& t : e->tables) g->rows.push_back(t.rows);
   g->conns.resize(cfg->n_conn);
   auto fail = [&](fr_status st, const std::string& msg) {
     fr_ingest_destroy(g);

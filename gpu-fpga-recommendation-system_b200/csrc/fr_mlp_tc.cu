@@ -455,7 +455,34 @@ struct TcParams {
   int pdl;             // issue griddepcontrol.wait / launch_dependents (no-ops unless a launch in the chain
                        // carries the programmatic-serialization attribute)
   int latency;         // host-side hint: small batch, one tile per cluster (no ganging)
+  // table-sharded step (layer 1 only): the A operand is this rank's exchange buffer, which the peer ranks fill over
+  // NVLink.  The TMA producer polls wait_flags[0..wait_n) until every rank has published step *wait_step, right
+  // before its first A load -- TMEM allocation, barrier set-up and bias staging of this launch, and every other
+  // worker's kernels, run while the peers' rows are still in flight.  wait_flags == nullptr: no wait.
+  const int* wait_flags;
+  const int* wait_step;
+  int wait_n;
+  int* wait_err;
 };
+
+// Poll the peers' step flags (system-scope acquire: the rows were written by other GPUs); a peer that has not
+// published after ~2 s is given up on -- *err is set (fr_sync reports it) and the kernel runs on what is there.
+__device__ __forceinline__ void wait_for_peers(const TcParams& p) {
+  const int want = *reinterpret_cast<const volatile int*>(p.wait_step);
+  const long long t0 = clock64();
+  for (int r = 0; r < p.wait_n; r++) {
+    int v;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p.wait_flags + r) : "memory");
+      if (v >= want) break;
+      if (clock64() - t0 > 4000000000ll) {
+        *reinterpret_cast<volatile int*>(p.wait_err) = 1;
+        break;
+      }
+    }
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");   // the TMA loads that follow read through the async proxy
+}
 
 // kind::tf32 instruction descriptor: D=f32, A=B=tf32, both K-major, M = 128*CTAS, N = n.
 __host__ __device__ constexpr uint32_t make_idesc_tf32_m(int m, int n) {
@@ -563,6 +590,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 0) {
     // ===== TMA producer (both CTAs of a pair) =====
     if (lane == 0) {
+      if (p.wait_flags) wait_for_peers(p);
       uint32_t kc = 0;   // k-slices issued so far (ring position runs on across tiles)
       for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
         const int m0 = (((tile / n_tiles_n) * PAIRS + (int)pair) * CTAS + (int)rank) * BLOCK_M;
@@ -1441,7 +1469,10 @@ fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const
   // (ganging only pays when the epilogue of one tile runs under the next tile's MMAs: two accumulator stages)
   // an fp16 K slice carries twice the K of a TF32 one in the same bytes: half as many slices make the same gang
   const int min_kb = ELT == 2 ? (g_min_kb + 1) / 2 : g_min_kb;
-  const int gang = (num_kb >= min_kb || L::kAcc == 1 || p.latency) ? 1 : (min_kb + num_kb - 1) / num_kb;   // tiles per cluster wanted
+  // ... and only for launches that could not fill half the machine anyway: a launch with that many tiles is spread
+  // over all the SMs it can use (layer 3 at batch 16384 is 64 tiles: ganged in twos it ran on 64 of the 148 SMs)
+  const int gang = (num_kb >= min_kb || L::kAcc == 1 || p.latency || 2 * n_tiles >= max_clusters)
+                       ? 1 : (min_kb + num_kb - 1) / num_kb;   // tiles per cluster wanted
   int n_clusters = (n_tiles + gang - 1) / gang;
   if (n_clusters > max_clusters) n_clusters = max_clusters;
   cudaLaunchConfig_t cfg = {};
@@ -1507,10 +1538,23 @@ bool parse_tiles(TcLayerCfg cfg[3]) {
 // (medium model, batch 1: 77 -> ~45 us per fr_infer).
 constexpr int kLatencyBatch = 512;
 constexpr int kWideMinKb = 16;   // K slices from which a 512-wide single-stage tile beats two 256-wide ones
+// Is this launch a latency case -- nothing else in flight to fill the machine?  FR_OPT_TILE_HINT says so explicitly;
+// by default an engine with at most two worker streams (the reference's THREAD_NUM, cuda_server.c:554-556) is
+// taken to serve one batch at a time, and batches of <= 512 items always are.
+bool latency_mode(const fr_engine* e, int B) {
+  if (e->tile_hint == FR_HINT_LATENCY) return true;
+  if (e->tile_hint == FR_HINT_THROUGHPUT) return B <= kLatencyBatch;
+  return B <= kLatencyBatch || e->streams.size() <= 2;
+}
 int pick_block_n(const fr_engine* e, int k, int B) {
   const int N = e->dims[k + 1], K = e->dims[k];
-  if (B <= kLatencyBatch) return 128;
-  const int tiles256 = (B + 2 * BLOCK_M - 1) / (2 * BLOCK_M) * (N / 256);
+  const int m_tiles = (B + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int tiles256 = m_tiles * (N / 256);
+  if (latency_mode(e, B)) {
+    // the narrowest tiles that still run as ONE wave of clusters: most SMs busy, least work per SM
+    if (B <= kLatencyBatch || m_tiles * (N / 128) <= e->sm_count / 2) return 128;
+    if (tiles256 <= e->sm_count / 2) return 256;
+  }
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
   if (N % 512 == 0 && num_kb >= kWideMinKb && tiles256 < e->sm_count / 2) return 512;
   return 256;
@@ -1573,9 +1617,6 @@ fr_status frtc_prepare(fr_engine* e) {
     if (const char* env = getenv("FR_TC_ALSU")) st->a_lsu = atoi(env) != 0;
     for (int k = 0; k < 3; k++)
       if ((s = encode_2d(e, st, &st->w_map128[k], e->d_Wt[k], e->dims[k + 1], e->dims[k], 128)) != FR_OK) return s;
-    if (e->tc_f16)
-      for (int k = 0; k < 3; k++)
-        if ((s = encode_2d(e, st, &st->w_map16[k], e->d_Wt16[k], e->dims[k + 1], e->dims[k], 128, 2)) != FR_OK) return s;
     if (const char* env = getenv("FR_CHAIN")) st->chain = atoi(env) != 0;
     if (getenv("FR_CHAIN_PROF") && atoi(getenv("FR_CHAIN_PROF")) != 0 && !st->d_prof) {
       FR_CUDA(e, cudaMalloc(&st->d_prof, kProfIters * kProfPhases * kProfSlots * sizeof(long long)));
@@ -1583,6 +1624,18 @@ fr_status frtc_prepare(fr_engine* e) {
     }
   }
   st->ready = true;
+  return FR_OK;
+}
+
+// Tensor maps of the fp16 weight copies (128-row x 64-element boxes); called by the range analysis once it has
+// decided for fp16 operands and (re)built d_Wt16 -- the device addresses do not change afterwards.
+fr_status frtc_prepare_f16(fr_engine* e) {
+  TcState* st = static_cast<TcState*>(e->tc_state);
+  if (!st || !st->ready) return fr_fail(e, FR_ERR_STATE, "frtc_prepare_f16 before frtc_prepare");
+  for (int k = 0; k < 3; k++) {
+    fr_status s = encode_2d(e, st, &st->w_map16[k], e->d_Wt16[k], e->dims[k + 1], e->dims[k], 128, 2);
+    if (s != FR_OK) return s;
+  }
   return FR_OK;
 }
 
@@ -1741,9 +1794,10 @@ fr_status frtc_chain(fr_engine* e, fr_stream_s* s, const float* in, int B, float
 
 // One launch: layer k (0,1: store tf32-rounded activations into s->d_h[k]; 2: layer 3 with the
 // output layer + sigmoid folded in, writes d_scores).
-static fr_status frtc_layer_impl(fr_engine* e, fr_stream_s* s, int k, const float* in, int B, float* d_scores);
-fr_status frtc_layer(fr_engine* e, fr_stream_s* s, int k, const float* in, int B, float* d_scores) {
-  const fr_status r = frtc_layer_impl(e, s, k, in, B, d_scores);
+static fr_status frtc_layer_impl(fr_engine* e, fr_stream_s* s, int k, const float* in, int B, float* d_scores,
+                                 const FrPeerWait* wait);
+fr_status frtc_layer(fr_engine* e, fr_stream_s* s, int k, const float* in, int B, float* d_scores, const FrPeerWait* wait) {
+  const fr_status r = frtc_layer_impl(e, s, k, in, B, d_scores, wait);
   if (r == FR_OK) e->tc_layer_ctas[k] = e->tc_last_ctas;
   return r;
 }
@@ -1770,6 +1824,9 @@ static fr_status frtc_layer_f16(fr_engine* e, fr_stream_s* s, int k, const float
   p.pdl = 0;
   p.out = d_scores;
   p.latency = 0;
+  p.wait_flags = p.wait_step = nullptr;
+  p.wait_n = 0;
+  p.wait_err = nullptr;
   const int N = p.N, num_kb = (p.K + 63) / 64;
   const int tiles256 = (B + 2 * BLOCK_M - 1) / (2 * BLOCK_M) * (N / 256);
   if (k == 2) return launch<256, 5, EPI_DOT, 2, 1, false, 2>(e, a, st->w_map16[k], o, p, false, s->stream);
@@ -1778,8 +1835,9 @@ static fr_status frtc_layer_f16(fr_engine* e, fr_stream_s* s, int k, const float
   return launch<256, 5, EPI_STORE, 2, 1, false, 2>(e, a, st->w_map16[k], o, p, false, s->stream);
 }
 
-static fr_status frtc_layer_impl(fr_engine* e, fr_stream_s* s, int k, const float* in, int B, float* d_scores) {
-  if (fr_tc_f16(e)) return frtc_layer_f16(e, s, k, in, B, d_scores);
+static fr_status frtc_layer_impl(fr_engine* e, fr_stream_s* s, int k, const float* in, int B, float* d_scores,
+                                 const FrPeerWait* wait) {
+  if (s->f16) return frtc_layer_f16(e, s, k, in, B, d_scores);   // (single-GPU engines only: never with a wait)
   TcState* st = static_cast<TcState*>(e->tc_state);
   const bool act = (e->mlp_mode == FR_MLP_BIAS_RELU_SIGMOID);
   CUtensorMap a, o;
@@ -1802,20 +1860,24 @@ static fr_status frtc_layer_impl(fr_engine* e, fr_stream_s* s, int k, const floa
   p.pdl = e->pdl_mask ? 1 : 0;
   const bool pa = (e->pdl_mask & (k == 0 ? 2 : 1)) != 0;   // may this layer start under the tail of its predecessor
   p.out = d_scores;
+  p.wait_flags = wait ? wait->flags : nullptr;
+  p.wait_step = wait ? wait->step : nullptr;
+  p.wait_n = wait ? wait->world : 0;
+  p.wait_err = wait ? wait->err : nullptr;
   TcLayerCfg c = st->cfg[k];
   if (st->auto_tiles && k < 2) c.block_n = pick_block_n(e, k, B);   // same 128-row weight boxes for 256 and 512
   const CUtensorMap& w = (st->auto_tiles && k < 2 && c.block_n == 128) ? st->w_map64[k] : st->w_map[k];
-  p.latency = (st->auto_tiles && B <= kLatencyBatch) ? 1 : 0;
+  p.latency = (st->auto_tiles && latency_mode(e, B)) ? 1 : 0;
   cudaStream_t cs = s->stream;
   // throughput-sized batches: two pairs per cluster share every weight slice by TMA multicast (each CTA loads
   // half of its share: 128-row boxes for 512-wide tiles, 64-row boxes for 256-wide ones)
-  if (st->mcast && st->auto_tiles && B > kLatencyBatch && c.ctas == 2 && c.block_n >= 256) {
+  if (!wait && st->mcast && st->auto_tiles && B > kLatencyBatch && c.ctas == 2 && c.block_n >= 256) {
     if (k < 2 && c.block_n == 512) return launch<512, 3, EPI_STORE, 2, 2>(e, a, st->w_map128[k], o, p, pa, cs);
     if (k < 2) return launch<256, 5, EPI_STORE, 2, 2>(e, a, st->w_map64[k], o, p, pa, cs);
     return launch<256, 5, EPI_DOT, 2, 2>(e, a, st->w_map64[k], o, p, pa, cs);
   }
   // throughput-sized batches on plain pairs: the A operand goes through the LSU (cp.async), TMA carries the weights
-  if (st->a_lsu && st->auto_tiles && B > kLatencyBatch && c.ctas == 2 && c.block_n >= 256) {
+  if (!wait && st->a_lsu && st->auto_tiles && B > kLatencyBatch && c.ctas == 2 && c.block_n >= 256) {
     if (k < 2 && c.block_n == 512) return launch<512, 3, EPI_STORE, 2, 1, true>(e, a, w, o, p, pa, cs);
     if (k < 2) return launch<256, 5, EPI_STORE, 2, 1, true>(e, a, w, o, p, pa, cs);
     return launch<256, 5, EPI_DOT, 2, 1, true>(e, a, w, o, p, pa, cs);

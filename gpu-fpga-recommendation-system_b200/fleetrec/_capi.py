@@ -15,6 +15,9 @@ FR_OK, FR_ERR_INVALID, FR_ERR_CUDA, FR_ERR_OOM, FR_ERR_STATE, FR_ERR_UNSUPPORTED
 FR_MLP_LINEAR, FR_MLP_BIAS_RELU_SIGMOID = 0, 1
 FR_PREC_TF32, FR_PREC_FP32 = 0, 1
 FR_TABLE_F32, FR_TABLE_F16, FR_TABLE_BF16 = 0, 1, 2
+FR_OPT_CUDA_GRAPHS, FR_OPT_CHECK_INDICES, FR_OPT_FUSE_LOOKUP, FR_OPT_TILE_HINT, FR_OPT_F16_OPERANDS = range(5)
+FR_HINT_AUTO, FR_HINT_LATENCY, FR_HINT_THROUGHPUT = 0, 1, 2
+FR_F16_OFF, FR_F16_GUARDED = 0, 1
 
 
 class TableDesc(C.Structure):
@@ -68,16 +71,21 @@ SIGNATURES = {
     "fr_load_mlp": (_I, [_P, _I, _P, _P]),
     "fr_set_mlp_mode": (_I, [_P, _I]),
     "fr_set_precision": (_I, [_P, _I]),
+    "fr_set_option": (_I, [_P, _I, _I]),
+    "fr_f16_report": (_I, [_P, C.POINTER(C.c_int), C.POINTER(C.c_float)]),
     "fr_stream_create": (_I, [_P, C.POINTER(_P)]),
     "fr_stream_destroy": (None, [_P, _P]),
     "fr_stream_cuda": (_P, [_P]),
     "fr_infer": (_I, [_P, _P, _I, _P, _P]),
+    "fr_infer_many": (_I, [_P, _P, _I, _I, _P, _P]),
     "fr_gather_only": (_I, [_P, _P, _I, _P, _P]),
     "fr_mlp_only": (_I, [_P, _P, _I, _P, _P]),
     "fr_layer_only": (_I, [_P, _I, _P, _I, _P, _P]),
     "fr_sync": (_I, [_P, _P]),
     "fr_launch_count": (_I64, [_P]),
     "fr_table_bytes": (_I64, [_P]),
+    "fr_graph_stats": (_I, [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
+    "fr_graph_flush": (_I, [_P, _P]),
     "fr_mark": (_I, [_P, _P, _I]),
     "fr_elapsed_ms": (_I, [_P, _P, C.POINTER(C.c_float)]),
     "fr_time_kernels": (_I, [_P, _P, _I, _I, _P, C.POINTER(C.c_float)]),

@@ -143,6 +143,18 @@ class Engine:
     def set_precision(self, p):
         self._chk(self._L.fr_set_precision(self._h, p))
 
+    def set_option(self, option, value):
+        """fr_set_option: FR_OPT_CUDA_GRAPHS / CHECK_INDICES / FUSE_LOOKUP / TILE_HINT / F16_OPERANDS."""
+        self._chk(self._L.fr_set_option(self._h, option, int(value)))
+
+    def f16_report(self):
+        """(active, bounds): does fr_infer compute on fp16 operands, and the range bounds that decided it
+        ([max |x|, max |h1|, max |h2|, min non-zero |table element|, inexact weight-mass share])."""
+        active = C.c_int(0)
+        b = (C.c_float * 5)()
+        self._chk(self._L.fr_f16_report(self._h, C.byref(active), b))
+        return bool(active.value), [float(v) for v in b]
+
     # -- hot path ---------------------------------------------------------
     def infer_async(self, idx, scores, B=None, worker=None):
         B = idx.shape[0] if B is None else B
@@ -154,6 +166,10 @@ class Engine:
         self.infer_async(idx, scores, worker=worker)
         self.sync(worker)
         return scores
+
+    def infer_many_async(self, idx, scores, n, B, worker=None):
+        """fr_infer_many: n batches of B items, idx [n][B][T], scores [n][B]; one copy each way for host buffers."""
+        self._chk(self._L.fr_infer_many(self._h, _ptr(idx), n, B, _ptr(scores), worker._h if worker else None))
 
     def gather_only(self, idx, worker=None):
         idx = np.ascontiguousarray(idx, np.int32)
@@ -195,6 +211,15 @@ class Engine:
 
     def table_bytes(self):
         return self._L.fr_table_bytes(self._h)
+
+    def graph_stats(self):
+        """{replayed, captured, direct}: hot-path steps served from a cached CUDA graph / captured first / plain launches."""
+        r, c, d = C.c_int64(), C.c_int64(), C.c_int64()
+        self._chk(self._L.fr_graph_stats(self._h, C.byref(r), C.byref(c), C.byref(d)))
+        return {"replayed": r.value, "captured": c.value, "direct": d.value}
+
+    def graph_flush(self, worker=None):
+        self._chk(self._L.fr_graph_flush(self._h, worker._h if worker else None))
 
     def mark(self, which, worker=None):
         self._chk(self._L.fr_mark(self._h, worker._h if worker else None, which))

@@ -12,25 +12,57 @@ CUDA-IPC handles and the end-of-run barrier.
 import numpy as np
 
 
-def plan_owners(model, world, replicate_tiers=("PLRAM",), replicate_max_bytes=16 << 20, replicate_below_bytes=0):
+def plan_owners(model, world, replicate_tiers=("PLRAM",), replicate_max_bytes=16 << 20, replicate_below_bytes=0,
+                policy="balanced"):
     """owner[t] for every table: -1 = replicated on every rank, else the owning rank.
 
     On-chip-class tables (the reference's PLRAM tier: <= 10 000 rows, L2-resident
-    here) are replicated, which removes their floats from the exchange.  The rest
-    go to ranks greedily by descending bytes-per-item traffic then bytes, to the
-    currently lightest rank (ties: lowest rank) -- deterministic, so every rank
-    computes the same plan without communicating.  `replicate_below_bytes` > 0 additionally
-    replicates ANY table smaller than that, whatever its tier: a table that fits L2 many times over
-    costs next to nothing to replicate, and every replicated table leaves the exchange."""
+    here) are replicated, which removes their floats from the exchange.
+    `replicate_below_bytes` > 0 additionally replicates ANY table smaller than that, whatever its
+    tier: a table that fits L2 many times over costs next to nothing to replicate, and every
+    replicated table leaves the exchange.  The rest are owned by one rank each:
+
+    policy "balanced"    greedily by descending bytes-per-item traffic then bytes, to the currently lightest
+                         rank (ties: lowest rank): traffic within one widest row, capacity spread.
+    policy "contiguous"  in concat (wire) order, cut into `world` runs of about equal floats: every rank pushes ONE
+                         contiguous run of every item's vector (long NVLink stores, every lane of the push kernel
+                         busy) -- traffic stays balanced, resident bytes are whatever the runs hold.
+
+    Deterministic, so every rank computes the same plan without communicating."""
     owner = [None] * model.n_tables
     if world == 1:
         return [0] * model.n_tables
+
+    def replicated(t):
+        return (t.tier in replicate_tiers and t.rows * t.dim * 4 <= replicate_max_bytes) or \
+            t.rows * t.dim * 4 < replicate_below_bytes
+    if policy == "contiguous":
+        order = []                                      # owned tables by first appearance in the concat vector
+        for s in sorted(model.segments, key=lambda s: s.dst):
+            t = model.tables[s.table]
+            if replicated(t):
+                owner[t.id] = -1
+            elif t.id not in order:
+                order.append(t.id)
+        total = sum(model.tables[t].dim for t in order)
+        acc, r = 0, 0
+        for t in order:
+            # move on to the next rank once this one holds its share (never leave a later rank empty-handed)
+            if r < world - 1 and acc >= (r + 1) * total / world:
+                r += 1
+            owner[t] = r
+            acc += model.tables[t].dim
+        for t in model.tables:                          # tables no segment reads (none in the catalogues)
+            if owner[t.id] is None:
+                owner[t.id] = -1 if replicated(t) else 0
+        return owner
+    if policy != "balanced":
+        raise ValueError(policy)
     load = [0.0] * world          # gathered bytes per item (traffic balance)
     size = [0] * world            # resident bytes (capacity balance)
     order = sorted(model.tables, key=lambda t: (-t.dim, -t.rows * t.dim, t.id))
     for t in order:
-        if (t.tier in replicate_tiers and t.rows * t.dim * 4 <= replicate_max_bytes) or \
-                t.rows * t.dim * 4 < replicate_below_bytes:
+        if replicated(t):
             owner[t.id] = -1
             continue
         r = min(range(world), key=lambda k: (load[k], size[k], k))

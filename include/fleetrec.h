@@ -121,6 +121,38 @@ fr_status fr_fill_table_hash(fr_engine* e, int table_id, uint32_t seed);
 /* Read rows back (tests): copies [n_rows][dim] starting at first_row to host, widened to fp32. */
 fr_status fr_read_table(fr_engine* e, int table_id, int64_t first_row, int64_t n_rows, float* host_out);
 
+/* ---- engine options ------------------------------------------------------- */
+/* Set at any time between calls; a change synchronises the device and drops the worker streams' cached CUDA graphs.
+ *   FR_OPT_CUDA_GRAPHS    1 (default): a (buffers, B) combination seen before on a worker is replayed as one CUDA
+ *                         graph; 0: every step is issued as plain launches.
+ *   FR_OPT_CHECK_INDICES  1: the lookup kernels compare every index with its table's row count; offenders read row 0
+ *                         and the next fr_sync returns FR_ERR_INVALID naming one of them.  0 (default): unchecked,
+ *                         like the reference (embedding_47_krnl.cpp:925-934).  fr_ingest validates FR_INGEST_INDICES
+ *                         blocks on the host either way (they come off a socket).
+ *   FR_OPT_FUSE_LOOKUP    1: fr_infer gathers straight into layer 1's shared-memory A tile (no concat vector in
+ *                         global memory; TF32, fp32 tables, single GPU).  0 (default): separate lookup kernel.
+ *   FR_OPT_TILE_HINT      FR_HINT_LATENCY: one batch at a time -- narrow tcgen05 tiles spread over as many SMs as the
+ *                         batch allows; FR_HINT_THROUGHPUT: many batches in flight on several workers -- wide tiles,
+ *                         few CTAs per launch; FR_HINT_AUTO (default): latency when the engine has at most two
+ *                         worker streams (the reference's THREAD_NUM, cuda_server.c:554-556), else throughput.
+ *   FR_OPT_F16_OPERANDS   FR_F16_GUARDED: the tcgen05 path computes on fp16 operands and activations (same 11-bit
+ *                         significand as TF32, half the bytes, fp32 accumulate) IF a range analysis of the loaded
+ *                         tables and weights proves that no operand can leave fp16's normal range (largest table
+ *                         magnitude, |W|^T.bound + |b| layer by layer); otherwise, and for fr_mlp_only / fr_layer_only
+ *                         whose inputs it cannot bound, TF32.  FR_F16_OFF (default): TF32.  fr_f16_report says
+ *                         which one an engine runs and why. */
+enum { FR_OPT_CUDA_GRAPHS = 0, FR_OPT_CHECK_INDICES = 1, FR_OPT_FUSE_LOOKUP = 2, FR_OPT_TILE_HINT = 3,
+       FR_OPT_F16_OPERANDS = 4 };
+enum { FR_HINT_AUTO = 0, FR_HINT_LATENCY = 1, FR_HINT_THROUGHPUT = 2 };
+enum { FR_F16_OFF = 0, FR_F16_GUARDED = 1 };
+fr_status fr_set_option(fr_engine* e, int option, int value);
+/* Outcome of the FR_F16_GUARDED range analysis (run by the first fr_infer after tables / weights / the option
+ * changed; this call runs it if it is due): *active = 1 when fr_infer computes on fp16 operands; bounds[0..2] =
+ * upper bounds of |concat element|, |H1 element|, |H2 element| (must stay below 60000); bounds[3] = smallest
+ * non-zero table magnitude (must be fp16-normal, >= 2^-14); bounds[4] = largest share of a unit's weight mass that
+ * fp16 would represent inexactly (must stay below 1e-6). */
+fr_status fr_f16_report(fr_engine* e, int* active, float* bounds5);
+
 /* Layer k in 0..3.  W is the reference's layout: column-major out_k x in_k with
  * ld = out_k (cuda_server.c:215,253,291,329), i.e. row-major [in_k][out_k].
  * bias [out_k] may be NULL (treated as zeros; ignored in LINEAR mode). */
@@ -139,9 +171,17 @@ void* fr_stream_cuda(fr_stream s);
  * Both may be host or device pointers (detected); host buffers are copied
  * inside the call chain on the worker's stream (pin them for true async).
  * stream == NULL uses the engine's default worker.  Asynchronous: results are
- * valid after fr_sync().  Out-of-range indices are a caller error (checked only
- * when the engine was built with FR_CHECK_INDICES; the reference never checks). */
+ * valid after fr_sync().  Out-of-range indices are a caller error, detected only
+ * with FR_OPT_CHECK_INDICES (the reference never checks).  A (idx, scores, B)
+ * combination a worker has seen before is replayed as a CUDA graph: the buffers
+ * must stay allocated as what they were (fr_graph_flush forgets them). */
 fr_status fr_infer(fr_engine* e, const int32_t* idx, int B, float* scores, fr_stream s);
+/* n batches of B items in one call on one worker (n * B <= max_batch): idx [n][B][n_tables] and scores [n][B]
+ * contiguous.  Every batch runs through the same kernels as fr_infer, back to back; host buffers travel in ONE copy
+ * each way, which is what the call is for: a copy occupies the copy engine for ~4 us on top of its bytes, so
+ * per-batch copies of the reference's staging loop (read() -> cudaMemcpyAsync per batch, cuda_server.c:425-461)
+ * cap the end-to-end rate well below what the kernels sustain. */
+fr_status fr_infer_many(fr_engine* e, const int32_t* idx, int n, int B, float* scores, fr_stream s);
 /* Parity hook: the concat vectors [B][concat_floats] exactly as the FPGA would
  * put them on the wire (embedding_47_krnl.cpp:774 byte stream, item-major). */
 fr_status fr_gather_only(fr_engine* e, const int32_t* idx, int B, float* concat, fr_stream s);
@@ -157,6 +197,12 @@ fr_status fr_sync(fr_engine* e, fr_stream s);
 /* ---- introspection ------------------------------------------------------ */
 /* Number of kernels this library has launched on this engine so far. */
 int64_t fr_launch_count(const fr_engine* e);
+/* CUDA-graph cache of the hot-path calls: steps replayed from a graph, steps that were captured (and then launched as
+ * a graph) for the first time, steps issued as plain launches (graphs off, first call of a batch size on the
+ * engine, pageable buffers).  A steady-state loop shows only `replayed` growing. */
+fr_status fr_graph_stats(const fr_engine* e, int64_t* replayed, int64_t* captured, int64_t* direct);
+/* Forget the graphs cached on a worker (its caller buffers are about to be freed or re-used differently). */
+fr_status fr_graph_flush(fr_engine* e, fr_stream s);
 /* Device bytes currently held by tables / by everything. */
 int64_t fr_table_bytes(const fr_engine* e);
 /* Device time (ms) between two marks on a worker stream: fr_mark(s, 0) ...
@@ -191,11 +237,12 @@ fr_status fr_shard_attach_local(fr_engine* e, fr_engine* const* peers);
 fr_status fr_shard_gather_push(fr_engine* e, const int32_t* idx, int B_global, fr_stream s);
 fr_status fr_shard_mlp(fr_engine* e, int B_global, float* scores_local, fr_stream s);
 /* The same step as ONE asynchronous call with device-side synchronisation: push ->
- * publish a per-rank step flag into every peer's exchange region -> spin until all
+ * publish a per-rank step flag into every peer's exchange region (by the push kernel's last block) ->
+ * the first MLP kernel polls, right before its first load of the concat buffer, until all
  * ranks have published this step -> MLP.  No host barrier, no NCCL on the data path.
  * Every rank must issue the same sequence of calls with the same global batch.
- * world <= 32.  A peer that never arrives makes the wait give up after ~2 s and the
- * next call return FR_ERR_STATE. */
+ * world <= 32.  A peer that never arrives makes the wait give up after ~2 s (4e9 SM cycles): the step's
+ * scores are then invalid, and fr_sync and every later sharded call return FR_ERR_STATE. */
 fr_status fr_shard_infer(fr_engine* e, const int32_t* idx, int B_global, float* scores_local, fr_stream s);
 
 /* The same step fed with column-sliced index blocks -- what every FPGA of the reference receives: only the indices

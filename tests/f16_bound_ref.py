@@ -1,4 +1,5 @@
-"""Host-side range analysis for the fp16-operand MLP path (FR_TC_F16=1, experimental).
+"""numpy restatement of the range analysis behind FR_OPT_F16_OPERANDS = FR_F16_GUARDED (csrc/fr_precision.cu).
+TEST HELPER: the library decides on the device; the tests cross-check its bounds against this.
 
 The tcgen05 kernels can run on fp16 operands and activations (csrc/fr_mlp_tc.cu, ELT = 2): the 11-bit
 significand the TF32 path keeps, in half the bytes -- and with fp16's range.  An operand above 65 504 is
@@ -11,7 +12,7 @@ TMEM, the output layer runs in fp32).  The bound is propagated unit by unit:
 
 It is a worst-case bound (every input at its largest magnitude with the sign that hurts), so "safe" is a
 guarantee and "unsafe" only means "not provable" -- the reference's all-ones known answer is genuinely
-unsafe (352 * 1024 at layer 2).  Mirrors what a C++ host would do before exporting FR_TC_F16=1.
+unsafe (352 * 1024 at layer 2).
 """
 import numpy as np
 
@@ -36,7 +37,7 @@ def layer_bounds(ub_in, W, b=None):
 
 
 def f16_safe(model, table_max_abs, W, b=None, margin=2.0):
-    """(safe, report): may the engine run FR_TC_F16=1 on these tables and weights?
+    """(safe, report): may the engine compute on fp16 operands with these tables and weights?
 
     safe   -- every stored operand (x, W1..W3, h1, h2) is provably below F16_MAX / margin
     report -- dict of the largest bound per stored tensor, for the log

@@ -770,29 +770,3 @@ def test_ingest_total_batches_and_truncated_stream():
     assert np.all(ing.scores[0, 0] == np.float32(KAT["small"]))
     ing.close()
     eng.close()
-
-
-@pytest.mark.parametrize("model", ("small", "medium"))
-@pytest.mark.parametrize("B", (1, 333, 2048, 4099))
-def test_tc_f16_operands_vs_oracle(model, B, monkeypatch):
-    """FR_TC_F16=1 (experimental): the tcgen05 MLP on fp16 operands and activations (kind::f16, FP32 accumulate) --
-    the 11-bit significand TF32 keeps, in half the bytes.  Same gate as the TF32 path: <= 1e-3 of the fp32 oracle,
-    through fr_infer (lookup writes fp16 concat vectors) and fr_mlp_only (fp32 input converted on the device); the
-    lookup hook stays fp32 and bit-exact."""
-    monkeypatch.setenv("FR_TC_F16", "1")
-    cat = catalogue.load(model).with_row_cap(20000)
-    dims = cat.layer_dims
-    tables = oracle.make_tables(cat, "hash", seed=41)
-    W, b = oracle.make_weights(dims, seed=42)
-    eng = fleetrec.Engine(cat, max_batch=max(B, 256))
-    eng.load_tables(tables)
-    eng.load_mlp(W, b)
-    idx = oracle.zipf_indices(cat, B, seed=B)
-    x = oracle.gather(cat, tables, idx)
-    exp = oracle.mlp(x, dims, W, b, mode=1)
-    assert_bits_equal(eng.gather_only(idx), x)
-    for _ in range(2):
-        got = eng.infer(idx)
-    assert rel_err(got, exp) <= TOL, rel_err(got, exp)
-    assert rel_err(eng.mlp_only(x), exp) <= TOL
-    eng.close()

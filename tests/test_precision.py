@@ -1,7 +1,9 @@
-"""Range analysis that decides whether the fp16-operand MLP path (FR_TC_F16=1) may be used -- host logic, no GPU."""
+"""The numpy restatement of the fp16 range analysis (tests/f16_bound_ref.py) behaves as specified -- no GPU.
+The library's own analysis (csrc/fr_precision.cu) is checked against it in tests/test_round2_gpu.py."""
 import numpy as np
 
-from fleetrec import catalogue, precision
+import f16_bound_ref as precision
+from fleetrec import catalogue
 from oracle import oracle
 
 

@@ -1,5 +1,7 @@
-"""Multi-GPU path: host logic on CPU (world-size-2 gloo processes) and, when two
-GPUs are visible, the device path (peer-store push + device-side step barrier)."""
+"""Multi-GPU path: host logic on CPU (world-size-2 gloo processes) and the device path (peer-store push +
+device-side step flags).  The device tests run their ranks as separate engines of ONE process: on separate
+GPUs when the box has them, otherwise all on GPU 0 (fr_shard_attach_local allows it: same kernels, same
+flags, same exchange buffers, only the peer stores stay on-device), so a 1-GPU box covers them too."""
 import os
 import socket
 
@@ -148,10 +150,8 @@ def _n_gpus():
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", (1, 2))
 def test_sharded_device_path_single_process(world):
-    """Two engines on two GPUs of one process (fr_shard_attach_local): peer-store push,
-    then the one-call step with the device-side barrier, against the oracle."""
-    if _n_gpus() < world:
-        pytest.skip(f"needs {world} GPUs")
+    """Two engines of one process (fr_shard_attach_local): peer-store push, then the one-call step with the
+    device-side flags, against the oracle."""
     import torch
     cat = catalogue.load("small").with_row_cap(5000)
     dims = cat.layer_dims
@@ -161,7 +161,7 @@ def test_sharded_device_path_single_process(world):
     B = 256
     engs = []
     for r in range(world):
-        e = fleetrec.Engine(cat, device=r, max_batch=B)
+        e = fleetrec.Engine(cat, device=r % _n_gpus(), max_batch=B)
         e.shard_init(r, world, owner)
         for t in cat.tables:
             e.load_table(t.id, tables[t.id])         # no-op for tables this rank does not own
@@ -215,8 +215,6 @@ def test_sharded_multi_worker_graph_replay(world):
     buffers, flags and device-side step counter), and a step seen before on the same buffers is
     replayed as a CUDA graph (one per buffer parity).  New index CONTENTS in the same pinned
     buffers must give new, correct scores on every rank, for both workers, over many steps."""
-    if _n_gpus() < world:
-        pytest.skip(f"needs {world} GPUs")
     import torch
     cat = catalogue.load("small").with_row_cap(5000)
     dims = cat.layer_dims
@@ -226,7 +224,7 @@ def test_sharded_multi_worker_graph_replay(world):
     B, per, n_workers = 512, 512 // world, 2
     engs, workers = [], []
     for r in range(world):
-        e = fleetrec.Engine(cat, device=r, max_batch=B)
+        e = fleetrec.Engine(cat, device=r % _n_gpus(), max_batch=B)
         e.shard_init(r, world, owner)
         for t in cat.tables:
             e.load_table(t.id, tables[t.id])
@@ -256,8 +254,11 @@ def test_sharded_multi_worker_graph_replay(world):
             assert err <= 1e-3, (step, w, err)
     # same kernels per step whether launched directly or replayed from the graph
     per_step = (engs[0].launch_count() - l0[0]) / (7 * n_workers)
-    # [index staging kernel] + push (+ replicated lookup) + flags + 3 GEMM launches (or one chain launch)
-    assert per_step == int(per_step) and 3 <= per_step <= 7, per_step
+    # exchange kernel (push + replicated lookup + publish) + 3 GEMM launches, the first of which waits for the peers
+    assert per_step == 4, per_step
+    for e in engs:   # every step after a worker's first replayed a graph (both buffer parities captured together)
+        gs = e.graph_stats()
+        assert gs["direct"] <= 1 and gs["captured"] <= n_workers and gs["replayed"] >= 7 * n_workers - n_workers - 1, gs
     for r, e in enumerate(engs):
         for w in workers[r]:
             w.close()
@@ -270,8 +271,6 @@ def test_sharded_step_from_column_sliced_indices_matches_full_rows(world):
     """fr_shard_infer_sliced (each rank uploads only [B][owned tables] + [B/world][replicated tables]) gives the
     bits fr_shard_infer gives from the full [B][T] rows: same lookups, same exchange, same MLP; direct and
     graph-replayed, from pinned host blocks whose CONTENTS change between steps."""
-    if _n_gpus() < world:
-        pytest.skip(f"needs {world} GPUs")
     import torch
     cat = catalogue.load("small").with_row_cap(5000)
     dims = cat.layer_dims
@@ -281,7 +280,7 @@ def test_sharded_step_from_column_sliced_indices_matches_full_rows(world):
     B, per = 1024, 1024 // world
     engs = []
     for r in range(world):
-        e = fleetrec.Engine(cat, device=r, max_batch=B)
+        e = fleetrec.Engine(cat, device=r % _n_gpus(), max_batch=B)
         e.shard_init(r, world, owner)
         for t in cat.tables:
             e.load_table(t.id, tables[t.id])
