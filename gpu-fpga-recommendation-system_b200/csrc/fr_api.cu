@@ -30,6 +30,36 @@ struct fr_builtin_model {
 
 static thread_local std::string g_tls_err;
 
+// The ONLY place the library reads the environment (once per fr_create).
+static void fr_read_knobs(FrKnobs* k) {
+  if (const char* env = getenv("FR_TC_TILES")) {
+    sscanf(env, "%d,%d,%d,%d", &k->tiles[0], &k->tiles[1], &k->tiles[2], &k->tile_ctas);
+    k->tiles[2] = 256;   // layer 3 keeps its whole row (the output layer is folded into its epilogue)
+    k->tiles_pinned = true;
+  }
+  if (const char* env = getenv("FR_TC_MAX_CLUSTERS")) k->max_clusters = atoi(env);
+#ifdef FR_EXPERIMENTS
+  auto num = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
+  k->min_kb = num("FR_TC_MIN_KB", k->min_kb) > 0 ? num("FR_TC_MIN_KB", k->min_kb) : 1;
+  k->pdl_mask = num("FR_PDL", 0) & 7;
+  const int zc = num("FR_ZEROCOPY", 0);
+  k->zero_copy_pct = zc == 1 ? 100 : (zc < 0 ? 0 : (zc > 100 ? 100 : zc));
+  k->mcast = num("FR_TC_MCAST", 0) != 0;
+  k->a_lsu = num("FR_TC_ALSU", 0) != 0;
+  k->chain = num("FR_CHAIN", 0) != 0;
+  k->chain_prof = num("FR_CHAIN_PROF", 0) != 0;
+#endif
+}
+
+// 1 when the library was built with -DFR_EXPERIMENTS (the measured-slower kernel variants and their switches exist)
+extern "C" int fr_build_has_experiments(void) {
+#ifdef FR_EXPERIMENTS
+  return 1;
+#else
+  return 0;
+#endif
+}
+
 fr_status fr_fail(const fr_engine* e, fr_status code, const char* fmt, ...) {
   char buf[1024];
   va_list ap;
@@ -163,13 +193,7 @@ extern "C" fr_status fr_create(const fr_model_desc* desc, int n_gpus, const int*
   e->precision = desc->precision;
   e->table_dtype = desc->table_dtype;
   e->max_batch = desc->max_batch;
-  if (const char* env = getenv("FR_GRAPHS")) e->use_graphs = atoi(env) != 0;
-  if (const char* env = getenv("FR_PDL")) e->pdl_mask = atoi(env) & 7;
-  if (const char* env = getenv("FR_FUSE")) e->fuse_lookup = atoi(env) != 0;
-  if (const char* env = getenv("FR_ZEROCOPY")) {
-    const int v = atoi(env);
-    e->zero_copy_pct = v == 1 ? 100 : (v < 0 ? 0 : (v > 100 ? 100 : v));
-  }
+  fr_read_knobs(&e->knobs);
   e->tables.resize(desc->n_tables);
   for (int t = 0; t < desc->n_tables; t++) {
     e->tables[t].rows = desc->tables[t].rows;
@@ -408,7 +432,7 @@ static bool is_device_ptr(const void* p) {
 // The device-side alias of a page-locked, mapped host buffer (cudaHostAlloc / cudaHostRegister under UVA),
 // null for pageable or device memory.
 static void* mapped_host_alias(const fr_engine* e, const void* p) {
-  if (e->zero_copy_pct <= 0 || !p) return nullptr;
+  if (e->knobs.zero_copy_pct <= 0 || !p) return nullptr;
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
     cudaGetLastError();
@@ -465,7 +489,7 @@ static fr_status stage_idx(fr_engine* e, fr_stream_s* s, const int32_t* idx, int
   const char* alias = static_cast<const char*>(mapped_host_alias(e, idx));
   size_t head = bytes;
   if (alias && (reinterpret_cast<uintptr_t>(alias) & 15) == 0 && bytes % 16 == 0)
-    head = (bytes / 16) * (size_t)(100 - e->zero_copy_pct) / 100 * 16;
+    head = (bytes / 16) * (size_t)(100 - e->knobs.zero_copy_pct) / 100 * 16;
   if (head > 0) FR_CUDA(e, cudaMemcpyAsync(s->d_idx, idx, head, cudaMemcpyHostToDevice, s->stream));
   if (head < bytes)
     return frk_stage_idx(e, alias + head, reinterpret_cast<int32_t*>(reinterpret_cast<char*>(s->d_idx) + head), bytes - head,

@@ -78,8 +78,30 @@ struct FrPeer {
   bool ipc = false;
 };
 
+// Tuning / test knobs of one engine, read ONCE from the environment by fr_create (fr_read_knobs, fr_api.cu).  A
+// release build reads only the two test hooks that pin the tcgen05 tile shapes; everything else -- the measured-slower
+// kernel variants and their switches -- exists only in a library built with -DFR_EXPERIMENTS
+// (`make exp` -> libfleetrec_exp.so).
+struct FrKnobs {
+  // test hooks (release and experiments builds)
+  bool tiles_pinned = false;      // FR_TC_TILES=N1,N2,N3[,ctas]: tile width of layers 1..3, CTAs per tile
+  int tiles[3] = {256, 256, 256};
+  int tile_ctas = 2;
+  int max_clusters = 0;           // FR_TC_MAX_CLUSTERS: cap the persistent grids (several tiles per cluster)
+  // tuning
+  int min_kb = 32;                // K slices of main loop a cluster should get before short tiles stop being ganged
+  // experiments (FR_EXPERIMENTS builds only; the defaults below are what a release build runs)
+  int pdl_mask = 0;               // FR_PDL: programmatic dependent launch edges (bit 0 GEMM->GEMM, 1 lookup->layer 1, 2 layer 3->lookup)
+  int zero_copy_pct = 0;          // FR_ZEROCOPY: share of a pinned index batch the SMs fetch over PCIe themselves
+  bool mcast = false;             // FR_TC_MCAST: 4-CTA clusters multicasting the weight slices
+  bool a_lsu = false;             // FR_TC_ALSU: A operand through cp.async instead of TMA
+  bool chain = false;             // FR_CHAIN: the whole MLP as one persistent launch
+  bool chain_prof = false;        // FR_CHAIN_PROF: phase timeline of the chain kernel's CTA 0
+};
+
 struct fr_engine {
   int device = 0;
+  FrKnobs knobs;
   int sm_count = 0;
   std::string name;
   std::vector<fr_table_desc> tdesc;
@@ -90,39 +112,18 @@ struct fr_engine {
   int precision = FR_PREC_TF32;
   int table_dtype = FR_TABLE_F32;
   int max_batch = 0;
-  bool use_graphs = true;  // FR_GRAPHS=0 disables CUDA-graph replay of fr_infer
-  // Programmatic dependent launch between the kernels of a batch, FR_PDL bit mask: 1 = MLP layers 2 and 3
-  // start under the tail of the layer before, 2 = layer 1 under the lookup, 4 = the lookup under the
-  // previous batch's last layer.  0 = every launch fully serialised.  Default 6: with bit 0 set (a
-  // Default 0: with programmatic edges inside the replayed graphs, 8-12 deep-queued worker streams
-  // deadlocked on the device intermittently on B200 / driver 580 (bit 0: 8 of 12 runs; mask 6: 1 of ~12),
-  // never without them; with 8 workers in flight the edges buy <= 2% anyway (10% with 4 workers).
-  int pdl_mask = 0;
-  // Page-locked (mapped) caller buffers can be read / written by the kernels themselves over PCIe instead of
-  // through memcpy nodes: indices by a staging kernel, scores by the last MLP kernel.  On this box one 385 KB
-  // index copy occupies the copy engine for ~12.5 us (7 us of transfer at 55 GB/s + ~5 us of fixed cost per copy,
-  // whatever the number of streams), and SM reads of host memory alone sustain ~29 GB/s (13.1 us per batch), so
-  // neither path alone keeps up with the kernels (9.2 us per batch).  zero_copy_pct = the share of every index
-  // batch the SMs fetch while the copy engine moves the rest (FR_ZEROCOPY=0..100; 1 means 100); the two run in
-  // parallel across the worker streams.  0 = cudaMemcpyAsync only.
-  int zero_copy_pct = 0;
-
+  bool use_graphs = true;  // FR_OPT_CUDA_GRAPHS
   std::vector<FrTable> tables;
   FrChunk* d_chunks = nullptr;  // [D/4]
   FrFuseChunk* d_fchunks = nullptr;  // [D/4]
-  // FR_FUSE=1: fr_infer gathers straight into layer 1's A tile (no concat in global memory).  Off by
-  // default: parity-green but slower on B200 (small model, batch 2048: 36 us against 5 + 22 us, 150 M
-  // against 179 M inferences/s) -- the lookup then runs on the 32 SMs of the GEMM's CTAs with 256
-  // threads each instead of on all 148 SMs at full occupancy.
+  // FR_OPT_FUSE_LOOKUP: fr_infer gathers straight into layer 1's A tile (no concat in global memory).  Off by default:
+  // parity-green but slower on B200.
   bool fuse_lookup = false;
   bool chunks_dirty = true;
 
   float* d_W[FR_MAX_LAYERS] = {nullptr, nullptr, nullptr, nullptr};    // [in][out] fp32 (reference layout)
   float* d_Wt[FR_MAX_LAYERS] = {nullptr, nullptr, nullptr, nullptr};   // [out][in] tf32-rounded (tcgen05 B operand)
   void* d_Wt16[FR_MAX_LAYERS] = {nullptr, nullptr, nullptr, nullptr};  // the same as fp16 (tc_f16)
-  // FR_TC_F16=1 (experimental): the tcgen05 path computes on fp16 operands / activations (kind::f16, FP32
-  // accumulate): the 11-bit significand TF32 keeps, in half the bytes, within fp16's range.  Single-GPU fr_infer
-  // and fr_mlp_only only; the chain / fused / multicast / cp.async variants and fr_layer_only stay TF32-only.
   bool tc_f16 = false;            // the decision: fr_infer computes on fp16 operands
   int f16_mode = FR_F16_OFF;      // FR_OPT_F16_OPERANDS
   bool f16_dirty = true;          // tables / weights / the option changed since the range analysis last ran

@@ -241,7 +241,7 @@ void launch_gather(const fr_engine* e, const int* d_ids, int n_chunks, const int
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = ((e->pdl_mask & 4) && !PUSH) ? 1 : 0;   // the sharded push is ordered by its own flag kernel
+  cfg.numAttrs = ((e->knobs.pdl_mask & 4) && !PUSH) ? 1 : 0;
   auto kern = e->table_dtype == FR_TABLE_F32 ? gather_concat_kernel<ROUND, PUSH, FR_TABLE_F32>
               : e->table_dtype == FR_TABLE_F16 ? gather_concat_kernel<ROUND, PUSH, FR_TABLE_F16>
                                                : gather_concat_kernel<ROUND, PUSH, FR_TABLE_BF16>;

@@ -1424,10 +1424,8 @@ fr_status encode_2d(fr_engine* e, TcState* st, CUtensorMap* map, const void* bas
   const cuuint64_t strides[1] = {(cuuint64_t)K * elt};
   const cuuint32_t box[2] = {(cuuint32_t)(128 / elt), (cuuint32_t)box_rows};   // one 128-byte swizzle row of K
   const cuuint32_t estr[2] = {1, 1};
-  static const int promo = getenv("FR_TMA_L2PROMO") ? atoi(getenv("FR_TMA_L2PROMO")) : 3;   // experiment knob
-  const CUtensorMapL2promotion l2p = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
-                                     : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-                                     : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  // (L2 promotion 256 B / 128 B / none measured identical to 0.1 us per phase of the chain timeline)
+  const CUtensorMapL2promotion l2p = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   CUresult r = st->encode(map, elt == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                           const_cast<void*>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p,
@@ -1438,13 +1436,11 @@ fr_status encode_2d(fr_engine* e, TcState* st, CUtensorMap* map, const void* bas
   return FR_OK;
 }
 
-int g_max_clusters = 0;   // FR_TC_MAX_CLUSTERS: cap the persistent grid (tests force several tiles per cluster)
 // A cluster's fixed cost (pipeline fill, last epilogue, teardown: ~4 us) is only hidden behind further
-// tiles, so short tiles are ganged: every cluster gets at least this many K-slices of main loop
-// (FR_TC_MIN_KB; small model layer 1 has 11 per tile -> three tiles per cluster, layer 3 has 16 -> two).
+// tiles, so short tiles are ganged: every cluster gets at least knobs.min_kb K-slices of main loop
+// (small model layer 1 has 11 per tile -> three tiles per cluster, layer 3 has 16 -> two).
 // Measured with 12 workers in flight, small model, batch 2048: 16 -> 214, 32 -> 223, 48 -> 212, 64 -> 201 M
 // inferences/s (a longer gang leaves too few clusters per launch to keep 148 SMs busy).
-int g_min_kb = 32;
 
 template <int BLOCK_N, int STAGES, int EPI, int CTAS, int PAIRS = 1, bool A_LSU = false, int ELT = 4>
 fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const TcParams& p,
@@ -1464,11 +1460,11 @@ fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const
   // persistent: one cluster per tile up to one CTA per SM
   const int n_tiles = (p.M + BLOCK_M * CS - 1) / (BLOCK_M * CS) * (p.N / BLOCK_N);
   int max_clusters = e->sm_count / CS;
-  if (g_max_clusters > 0 && g_max_clusters < max_clusters) max_clusters = g_max_clusters;   // test knob
+  if (e->knobs.max_clusters > 0 && e->knobs.max_clusters < max_clusters) max_clusters = e->knobs.max_clusters;   // test hook
   const int num_kb = (p.K + 128 / ELT - 1) / (128 / ELT);
   // (ganging only pays when the epilogue of one tile runs under the next tile's MMAs: two accumulator stages)
   // an fp16 K slice carries twice the K of a TF32 one in the same bytes: half as many slices make the same gang
-  const int min_kb = ELT == 2 ? (g_min_kb + 1) / 2 : g_min_kb;
+  const int min_kb = ELT == 2 ? (e->knobs.min_kb + 1) / 2 : e->knobs.min_kb;
   // ... and only for launches that could not fill half the machine anyway: a launch with that many tiles is spread
   // over all the SMs it can use (layer 3 at batch 16384 is 64 tiles: ganged in twos it ran on 64 of the 148 SMs)
   const int gang = (num_kb >= min_kb || L::kAcc == 1 || p.latency || 2 * n_tiles >= max_clusters)
@@ -1514,16 +1510,6 @@ fr_status get_a_map(fr_engine* e, TcState* st, const void* ptr, int K, int rows,
   if (st->a_maps.size() < 1024) st->a_maps.push_back(m);
   *out = m.map;
   return FR_OK;
-}
-
-// tile shapes: "N1,N2,N3[,ctas]" e.g. FR_TC_TILES=256,256,256,2 ; layer 3 must be 256 (whole row)
-bool parse_tiles(TcLayerCfg cfg[3]) {
-  int n[3] = {256, 256, 256}, ctas = 2;
-  const char* env = getenv("FR_TC_TILES");
-  if (env) sscanf(env, "%d,%d,%d,%d", &n[0], &n[1], &n[2], &ctas);
-  for (int k = 0; k < 3; k++) cfg[k] = {n[k], ctas};
-  cfg[2].block_n = 256;
-  return env != nullptr;
 }
 
 // Automatic tile width of a storing layer (pair tiles).  A launch whose 256-wide tiles cannot fill the
@@ -1583,10 +1569,8 @@ fr_status frtc_prepare(fr_engine* e) {
   if (e->dims[3] != 256)
     return fr_fail(e, FR_ERR_UNSUPPORTED, "TF32 path folds the output layer into layer 3 and needs hidden[2] == 256 "
                    "(got %d)", e->dims[3]);
-  st->auto_tiles = !parse_tiles(st->cfg);
-  const char* cap = getenv("FR_TC_MAX_CLUSTERS");
-  g_max_clusters = cap ? atoi(cap) : 0;
-  if (const char* env = getenv("FR_TC_MIN_KB")) g_min_kb = atoi(env) > 0 ? atoi(env) : 1;
+  st->auto_tiles = !e->knobs.tiles_pinned;
+  for (int k = 0; k < 3; k++) st->cfg[k] = {e->knobs.tiles[k], e->knobs.tile_ctas};
   if (!e->h_watch) {
     FR_CUDA(e, cudaHostAlloc(&e->h_watch, 8 * sizeof(int), cudaHostAllocMapped));
     memset(e->h_watch, 0, 8 * sizeof(int));
@@ -1613,12 +1597,12 @@ fr_status frtc_prepare(fr_engine* e) {
     if (s != FR_OK) return s;
     for (int k = 0; k < 3; k++)
       if ((s = encode_2d(e, st, &st->w_map64[k], e->d_Wt[k], e->dims[k + 1], e->dims[k], 64)) != FR_OK) return s;
-    if (const char* env = getenv("FR_TC_MCAST")) st->mcast = atoi(env) != 0;
-    if (const char* env = getenv("FR_TC_ALSU")) st->a_lsu = atoi(env) != 0;
+    st->mcast = e->knobs.mcast;
+    st->a_lsu = e->knobs.a_lsu;
     for (int k = 0; k < 3; k++)
       if ((s = encode_2d(e, st, &st->w_map128[k], e->d_Wt[k], e->dims[k + 1], e->dims[k], 128)) != FR_OK) return s;
-    if (const char* env = getenv("FR_CHAIN")) st->chain = atoi(env) != 0;
-    if (getenv("FR_CHAIN_PROF") && atoi(getenv("FR_CHAIN_PROF")) != 0 && !st->d_prof) {
+    st->chain = e->knobs.chain;
+    if (e->knobs.chain_prof && !st->d_prof) {
       FR_CUDA(e, cudaMalloc(&st->d_prof, kProfIters * kProfPhases * kProfSlots * sizeof(long long)));
       FR_CUDA(e, cudaMemset(st->d_prof, 0, kProfIters * kProfPhases * kProfSlots * sizeof(long long)));
     }
@@ -1643,6 +1627,7 @@ fr_status frtc_prepare_f16(fr_engine* e) {
 // alone to the SMs it occupied.
 extern "C" int frdbg_layer_ctas(const fr_engine* e, int k) { return (e && k >= 0 && k < 4) ? e->tc_layer_ctas[k] : 0; }
 
+#ifdef FR_EXPERIMENTS
 // Debug hook (not part of the ABI in include/fleetrec.h; tools/chain_timeline.py binds it by name): the clock64
 // stamps the last chain launch's CTA 0 wrote, [kProfIters][kProfPhases][kProfSlots]; returns the number of values.
 extern "C" int frdbg_chain_timeline(fr_engine* e, long long* out, int n) {
@@ -1653,6 +1638,8 @@ extern "C" int frdbg_chain_timeline(fr_engine* e, long long* out, int n) {
   if (cudaMemcpy(out, st->d_prof, total * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
   return total;
 }
+
+#endif
 
 void frtc_destroy(fr_engine* e) {
   if (TcState* st = static_cast<TcState*>(e->tc_state)) cudaFree(st->d_prof);
@@ -1697,7 +1684,7 @@ fr_status frtc_fused_layer1(fr_engine* e, fr_stream_s* s, const int32_t* d_idx, 
   }
   const int n_tiles = (B + 2 * BLOCK_M - 1) / (2 * BLOCK_M) * (p.N / kFuseN);
   int max_clusters = e->sm_count / 2;
-  if (g_max_clusters > 0 && g_max_clusters < max_clusters) max_clusters = g_max_clusters;
+  if (e->knobs.max_clusters > 0 && e->knobs.max_clusters < max_clusters) max_clusters = e->knobs.max_clusters;
   const int n_clusters = n_tiles < max_clusters ? n_tiles : max_clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n_clusters * 2, 1, 1);
@@ -1721,6 +1708,12 @@ fr_status frtc_fused_layer1(fr_engine* e, fr_stream_s* s, const int32_t* d_idx, 
 // storing layers are multiples of 512 wide (small / medium: 1024-512-256, large: 2048-512-256) when the
 // tile shapes are not pinned by FR_TC_TILES; batches <= kLatencyBatch keep the per-layer 128-wide tiles,
 // which spread one small batch over more SMs.
+#ifndef FR_EXPERIMENTS
+bool frtc_can_chain(const fr_engine*, int) { return false; }
+fr_status frtc_chain(fr_engine* e, fr_stream_s*, const float*, int, float*) {
+  return fr_fail(e, FR_ERR_UNSUPPORTED, "the one-launch MLP chain exists in FR_EXPERIMENTS builds only");
+}
+#else
 bool frtc_can_chain(const fr_engine* e, int B) {
   const TcState* st = static_cast<const TcState*>(e->tc_state);
   if (!st || !st->ready || !st->chain || !st->auto_tiles || e->precision != FR_PREC_TF32 || fr_tc_f16(e)) return false;
@@ -1743,7 +1736,7 @@ static fr_status launch_chain(fr_engine* e, cudaStream_t stream, const ChainMaps
   }
   const int n_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   int max_clusters = e->sm_count / 2;
-  if (g_max_clusters > 0 && g_max_clusters < max_clusters) max_clusters = g_max_clusters;
+  if (e->knobs.max_clusters > 0 && e->knobs.max_clusters < max_clusters) max_clusters = e->knobs.max_clusters;
   const int n_clusters = n_tiles < max_clusters ? n_tiles : max_clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n_clusters * 2, 1, 1);
@@ -1785,12 +1778,10 @@ fr_status frtc_chain(fr_engine* e, fr_stream_s* s, const float* in, int B, float
   p.prof = st->d_prof;
   p.probe_src = in;
   p.probe_vecs = (uint32_t)((size_t)B * e->dims[0] / 4);
-  static const bool probe = getenv("FR_CHAIN_PROBE") && atoi(getenv("FR_CHAIN_PROBE")) != 0;
-  if (probe) return launch_chain<3, true>(e, s->stream, maps, p);
-  static const int stages = getenv("FR_CHAIN_STAGES") ? atoi(getenv("FR_CHAIN_STAGES")) : 3;   // experiment knob
-  if (stages == 2) return launch_chain<2>(e, s->stream, maps, p);
   return launch_chain<3>(e, s->stream, maps, p);
 }
+
+#endif   // FR_EXPERIMENTS
 
 // One launch: layer k (0,1: store tf32-rounded activations into s->d_h[k]; 2: layer 3 with the
 // output layer + sigmoid folded in, writes d_scores).
@@ -1857,8 +1848,8 @@ static fr_status frtc_layer_impl(fr_engine* e, fr_stream_s* s, int k, const floa
   p.sigmoid = act ? 1 : 0;
   p.w4 = e->d_W[3];
   p.b4 = act ? e->d_bias[3] : nullptr;
-  p.pdl = e->pdl_mask ? 1 : 0;
-  const bool pa = (e->pdl_mask & (k == 0 ? 2 : 1)) != 0;   // may this layer start under the tail of its predecessor
+  p.pdl = e->knobs.pdl_mask ? 1 : 0;
+  const bool pa = (e->knobs.pdl_mask & (k == 0 ? 2 : 1)) != 0;   // may this layer start under the tail of its predecessor
   p.out = d_scores;
   p.wait_flags = wait ? wait->flags : nullptr;
   p.wait_step = wait ? wait->step : nullptr;
@@ -1869,6 +1860,7 @@ static fr_status frtc_layer_impl(fr_engine* e, fr_stream_s* s, int k, const floa
   const CUtensorMap& w = (st->auto_tiles && k < 2 && c.block_n == 128) ? st->w_map64[k] : st->w_map[k];
   p.latency = (st->auto_tiles && latency_mode(e, B)) ? 1 : 0;
   cudaStream_t cs = s->stream;
+#ifdef FR_EXPERIMENTS
   // throughput-sized batches: two pairs per cluster share every weight slice by TMA multicast (each CTA loads
   // half of its share: 128-row boxes for 512-wide tiles, 64-row boxes for 256-wide ones)
   if (!wait && st->mcast && st->auto_tiles && B > kLatencyBatch && c.ctas == 2 && c.block_n >= 256) {
@@ -1882,6 +1874,7 @@ static fr_status frtc_layer_impl(fr_engine* e, fr_stream_s* s, int k, const floa
     if (k < 2) return launch<256, 5, EPI_STORE, 2, 1, true>(e, a, w, o, p, pa, cs);
     return launch<256, 5, EPI_DOT, 2, 1, true>(e, a, w, o, p, pa, cs);
   }
+#endif
   if (k < 2) {
     if (c.block_n == 512) return launch<512, 3, EPI_STORE, 2>(e, a, w, o, p, pa, cs);
     if (c.ctas == 2) return c.block_n == 256 ? launch<256, 5, EPI_STORE, 2>(e, a, w, o, p, pa, cs) : launch<128, 7, EPI_STORE, 2>(e, a, w, o, p, pa, cs);

@@ -9,7 +9,8 @@ import os
 import subprocess
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(PKG_DIR, "libfleetrec.so")
+# FLEETREC_LIB: another build of the same library (libfleetrec_exp.so, `make exp`: the experimental kernel variants)
+LIB_PATH = os.environ.get("FLEETREC_LIB") or os.path.join(PKG_DIR, "libfleetrec.so")
 
 FR_OK, FR_ERR_INVALID, FR_ERR_CUDA, FR_ERR_OOM, FR_ERR_STATE, FR_ERR_UNSUPPORTED = range(6)
 FR_MLP_LINEAR, FR_MLP_BIAS_RELU_SIGMOID = 0, 1
@@ -111,6 +112,7 @@ SIGNATURES = {
     "fr_ingest_wait": (_I, [_P, C.POINTER(IngestStats)]),
     "fr_ingest_last_scores": (_I, [_P, _I, _P, C.POINTER(C.c_int64)]),
     "fr_ingest_destroy": (None, [_P]),
+    "fr_build_has_experiments": (_I, []),
 }
 
 _LIB = None

@@ -121,6 +121,13 @@ fr_status fr_fill_table_hash(fr_engine* e, int table_id, uint32_t seed);
 /* Read rows back (tests): copies [n_rows][dim] starting at first_row to host, widened to fp32. */
 fr_status fr_read_table(fr_engine* e, int table_id, int64_t first_row, int64_t n_rows, float* host_out);
 
+/* 1 when the library was built with -DFR_EXPERIMENTS (`make exp`): the measured-slower kernel variants of DESIGN.md
+ * section 4 (one-launch MLP chain, multicast clusters, cp.async A loader, zero-copy index staging, programmatic
+ * dependent launch) and the environment variables that select them exist only there.  A release build reads two
+ * environment variables, both test hooks, once per fr_create: FR_TC_TILES=N1,N2,N3[,ctas] (pin the tcgen05 tile width
+ * of layers 1..3 and the CTAs per tile) and FR_TC_MAX_CLUSTERS=n (cap the persistent grids). */
+int fr_build_has_experiments(void);
+
 /* ---- engine options ------------------------------------------------------- */
 /* Set at any time between calls; a change synchronises the device and drops the worker streams' cached CUDA graphs.
  *   FR_OPT_CUDA_GRAPHS    1 (default): a (buffers, B) combination seen before on a worker is replayed as one CUDA
