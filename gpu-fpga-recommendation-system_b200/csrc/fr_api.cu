@@ -48,6 +48,8 @@ static void fr_read_knobs(FrKnobs* k) {
   k->a_lsu = num("FR_TC_ALSU", 0) != 0;
   k->chain = num("FR_CHAIN", 0) != 0;
   k->chain_prof = num("FR_CHAIN_PROF", 0) != 0;
+  k->tc_prof = num("FR_TC_PROF", 0) != 0;
+  k->dbg_nostore = num("FR_TC_NOSTORE", 0);
 #endif
 }
 
@@ -583,6 +585,24 @@ static fr_status infer_enqueue(fr_engine* e, fr_stream_s* s, const int32_t* idx,
   if ((st = frk_gather(e, d_idx, B, s->d_x, e->precision == FR_PREC_TF32, s->stream, fr_tc_f16(e))) != FR_OK) return st;
   if ((st = run_mlp(e, s, s->d_x, B, d_scores)) != FR_OK) return st;
   return emit_scores(e, s, scores, B, d_scores);
+}
+
+// Do two addresses lie in ONE allocation (a single copy may span them)?  Two separately pinned buffers can sit back to
+// back in the address space; a copy across the seam is an invalid argument.
+static bool same_allocation(const void* a, const void* b) {
+  typedef int (*PFN_attr)(void*, int, unsigned long long);   // CUresult cuPointerGetAttribute(void*, CUpointer_attribute, CUdeviceptr)
+  static PFN_attr fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    cudaGetLastError();
+    return reinterpret_cast<PFN_attr>(f);
+  }();
+  if (!fn) return false;
+  unsigned long long sa = 0, sb = 0;
+  constexpr int kRangeStart = 11;   // CU_POINTER_ATTRIBUTE_RANGE_START_ADDR
+  if (fn(&sa, kRangeStart, (unsigned long long)(uintptr_t)a) != 0 || fn(&sb, kRangeStart, (unsigned long long)(uintptr_t)b) != 0) return false;
+  return sa != 0 && sa == sb;
 }
 
 // device memory or page-locked host memory: the only buffers a captured memcpy node may reference
@@ -1195,7 +1215,7 @@ static fr_status shard_infer_sliced_enqueue(fr_engine* e, fr_stream_s* s, const 
   const int32_t* d_o = idx_owned;
   const int32_t* d_r = idx_repl;
   int32_t* stage_r = s->d_idx + (n_o + 3) / 4 * 4;   // both blocks fit: n_owned + n_repl <= T
-  if (n_o && n_r && idx_repl == idx_owned + (n_o + 3) / 4 * 4 && !is_device_ptr(idx_owned)) {
+  if (n_o && n_r && idx_repl == idx_owned + (n_o + 3) / 4 * 4 && !is_device_ptr(idx_owned) && same_allocation(idx_owned, idx_repl)) {
     // one host buffer, the replicated block right behind the owned one (16-byte aligned): ONE copy -- every copy
     // costs the engine ~5 us on top of its bytes
     FR_CUDA(e, cudaMemcpyAsync(s->d_idx, idx_owned, ((n_o + 3) / 4 * 4 + n_r) * sizeof(int32_t), cudaMemcpyHostToDevice,

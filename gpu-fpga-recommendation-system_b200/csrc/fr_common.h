@@ -97,6 +97,8 @@ struct FrKnobs {
   bool a_lsu = false;             // FR_TC_ALSU: A operand through cp.async instead of TMA
   bool chain = false;             // FR_CHAIN: the whole MLP as one persistent launch
   bool chain_prof = false;        // FR_CHAIN_PROF: phase timeline of the chain kernel's CTA 0
+  int dbg_nostore = 0;            // FR_TC_NOSTORE: storing epilogues skip their stores (timing experiments; results are garbage)
+  bool tc_prof = false;           // FR_TC_PROF: cycle counters of the per-layer kernel's pipelines (tools/tc_prof.py)
 };
 
 struct fr_engine {

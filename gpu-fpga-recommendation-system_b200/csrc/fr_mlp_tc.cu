@@ -171,6 +171,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 16 consecutive fp32 columns of this thread's TMEM lane.
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // fp32 -> tf32, round to nearest with ties away from zero (what cvt.rna.tf32.f32 computes for finite
 // values): add half an ulp of the 10-bit mantissa to the magnitude and clear the 13 low bits.  Two
 // full-rate integer instructions; the cvt runs at 16 / clk / SM, which made it the largest single cost
@@ -414,8 +424,16 @@ constexpr int kLoaderWarps = 4;
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 constexpr int kMaxN = 2048;          // widest layer whose bias vector is staged in smem (large model H1)
-constexpr int kStoreBoxRows = 32;    // TMA store box: one epilogue warp's 32 rows x 32 fp32 columns
+constexpr int kStoreBoxRows = 32;    // TMA store box of the fused / chain kernels: one epilogue warp's 32 rows x 32 fp32 columns
 constexpr int kStoreBufBytes = kStoreBoxRows * BLOCK_K * 4;   // 4 KB, 128B-swizzled
+// tc_linear_kernel stores a whole CTA's 128 rows x 128 bytes per TMA instruction.  The TMA unit of an SM retires one
+// instruction per ~340 cycles whatever its box size up to 32 KB (tools/tma_probe.cu: 16 KB boxes land at 48 B/clk/SM,
+// 32 KB boxes at 72-96), so the 32 4-KB stores a 256-wide tile used to issue cost the unit as much as 32 K slices of
+// loads -- more than the tile's MMAs.  Four epilogue warps now fill ONE 16 KB staging buffer (named barrier) and one
+// thread stores it: 8 stores per tile.
+constexpr int kCtaStoreBytes = BLOCK_M * 128;   // 16 KB
+constexpr int kCtaStoreBufs = 3;                // store i-2 has released its buffer before chunk i+1 is staged
+constexpr int kEpiBarrier = 1;                  // named barrier of the 4 epilogue warps
 
 // CTAS = 1: one CTA owns 128 x BLOCK_N tiles.  CTAS = 2: a CTA pair (cluster of 2 along M) owns
 // 256 x BLOCK_N tiles; each CTA stages its own 128 rows of A and its own BLOCK_N/2 rows of B, so per
@@ -426,8 +444,8 @@ struct SmemLayout {
   static constexpr int kBRows = BLOCK_N / CTAS;
   static constexpr int kBBytes = kBRows * BLOCK_K * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStoreOff = STAGES * kStageBytes;          // 4 epilogue warps x 2 store buffers
-  static constexpr int kAuxOff = kStoreOff + 4 * 2 * kStoreBufBytes;   // bias[kMaxN], w4[256]
+  static constexpr int kStoreOff = STAGES * kStageBytes;          // kCtaStoreBufs staging buffers of 128 rows x 128 B
+  static constexpr int kAuxOff = kStoreOff + kCtaStoreBufs * kCtaStoreBytes;   // bias[kMaxN], w4[256]
   static constexpr int kBarOff = kAuxOff + (kMaxN + 256) * 4;
   static constexpr int kNumBars = 3 * STAGES + 4;                 // full, empty, tmem_full[2], tmem_empty[2], a_full
   static constexpr int kTotal = kBarOff + kNumBars * 8 + 16;
@@ -447,7 +465,8 @@ struct SmemLayout {
 struct TcParams {
   const float* a;      // [M][K] activations (A_LSU kernels read them with cp.async; the others through tmap_a)
   const float* bias;   // [N] or null
-  float* out;          // EPI_DOT: scores [M]  (EPI_STORE writes through tmap_out)
+  float* out;          // EPI_DOT: scores [M]  (tc_linear_kernel's EPI_STORE writes through tmap_out)
+  void* out_act;       // tc_pair_kernel EPI_STORE: activations [M][N] (fp32 tf32-rounded, or fp16), row pitch N
   const float* w4;     // EPI_DOT: output-layer weights [N]
   const float* b4;     // EPI_DOT: output-layer bias [1] or null
   int M, N, K;
@@ -463,7 +482,20 @@ struct TcParams {
   const int* wait_step;
   int wait_n;
   int* wait_err;
+  // FR_EXPERIMENTS builds, FR_TC_PROF=1: where the three pipelines of the first 8 CTAs spend their cycles
+  // (tools/tc_prof.py): prof[cta][16] = {producer total, waiting for a free slot, slices | MMA issuer total, waiting
+  // for operands, waiting for a free accumulator, slices | epilogue warp total, waiting for an accumulator, waiting
+  // for a free staging buffer + barrier, tiles}
+  long long* prof;
+  int dbg_nostore;     // FR_EXPERIMENTS, FR_TC_NOSTORE=1: the storing epilogues skip their global stores (timing experiments only)
 };
+#ifdef FR_EXPERIMENTS
+#define FR_PROF_T0(v) const long long v = clock64()
+#define FR_PROF_ADD(acc, v) acc += clock64() - (v)
+#else
+#define FR_PROF_T0(v) do { } while (0)
+#define FR_PROF_ADD(acc, v) do { } while (0)
+#endif
 
 // Poll the peers' step flags (system-scope acquire: the rows were written by other GPUs); a peer that has not
 // published after ~2 s is given up on -- *err is set (fr_sync reports it) and the kernel runs on what is there.
@@ -544,6 +576,18 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* a_full_bar = tmem_empty_bar + 2;        // [STAGES], A_LSU: this CTA's A slice has landed (cp.async arrivals)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_full_bar + STAGES);
 
+#ifdef FR_EXPERIMENTS
+  // launch timeline of CTA 0 (FR_TC_PROF): prof[112 + 3 * (launch % 4) + {0, 1, 2}] = %globaltimer at kernel entry, after
+  // the prologue, at exit; prof[127] counts launches
+  long long* pf_tl = nullptr;
+  if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) {
+    const long long n = atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 127), 1ull);
+    pf_tl = p.prof + 112 + 3 * (n & 3);
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    pf_tl[0] = t;
+  }
+#endif
   static_assert(PAIRS == 1 || CTAS == 2, "multicast clusters are made of CTA pairs");
   constexpr int CS = CTAS * PAIRS;   // CTAs per cluster
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -586,11 +630,20 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   if (p.pdl) griddep_wait();           // activations of the previous kernel are complete and visible from here
+#ifdef FR_EXPERIMENTS
+  if (pf_tl) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    pf_tl[1] = t;
+  }
+#endif
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs of a pair) =====
     if (lane == 0) {
       if (p.wait_flags) wait_for_peers(p);
+      long long pf_wait = 0;
+      FR_PROF_T0(pf_start);
       uint32_t kc = 0;   // k-slices issued so far (ring position runs on across tiles)
       for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
         const int m0 = (((tile / n_tiles_n) * PAIRS + (int)pair) * CTAS + (int)rank) * BLOCK_M;
@@ -598,7 +651,9 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int kb = 0; kb < num_kb; kb++, kc++) {
           const int s = kc % STAGES;
           const uint32_t ph = (kc / STAGES) & 1;
+          FR_PROF_T0(pf_t);
           mbar_wait(&empty_bar[s], ph ^ 1, 1, kc, tile);
+          FR_PROF_ADD(pf_wait, pf_t);
           uint8_t* a_dst = smem + s * L::kStageBytes;
           uint8_t* b_dst = a_dst + L::kABytes;
           if (PAIRS == 2) {
@@ -628,6 +683,13 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
       if (p.pdl) griddep_launch();
+#ifdef FR_EXPERIMENTS
+      if (p.prof && blockIdx.x < 8) {
+        long long* o = p.prof + blockIdx.x * 16;
+        o[0] = clock64() - pf_start; o[1] = pf_wait; o[2] = kc;
+      }
+#endif
+      (void)pf_wait;
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -647,9 +709,13 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (leader) {
       constexpr uint32_t idesc = ELT == 2 ? make_idesc_f16_m(BLOCK_M * CTAS, L::kMmaN) : make_idesc_tf32_m(BLOCK_M * CTAS, L::kMmaN);
       uint32_t kc = 0, it = 0;
+      long long pf_full = 0, pf_tmem = 0;
+      FR_PROF_T0(pf_start);
       for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
         const uint32_t as = it % L::kAcc;
+        FR_PROF_T0(pf_t0);
         mbar_wait(&tmem_empty_bar[as], ((it / L::kAcc) & 1) ^ 1, 2, kc, tile);   // the epilogue has drained this accumulator stage
+        FR_PROF_ADD(pf_tmem, pf_t0);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         for (int kb = 0; kb < num_kb; kb++, kc++) {
@@ -661,7 +727,9 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             // (no fence.proxy.async here: issued by the thread that has MMAs in flight it drains them, one K slice
             // at a time -- 0.9 us per slice; cp.async completion -> mbarrier -> tcgen05.mma is ordered as it is)
           } else {
+            FR_PROF_T0(pf_t1);
             mbar_wait(&full_bar[s], ph, 3, kc, tile);
+            FR_PROF_ADD(pf_full, pf_t1);
           }
           tc_fence_after();
           if (elect_one()) {
@@ -694,6 +762,13 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           __syncwarp();
         }
       }
+#ifdef FR_EXPERIMENTS
+      if (p.prof && blockIdx.x < 8 && lane == 0) {
+        long long* o = p.prof + blockIdx.x * 16 + 4;
+        o[0] = clock64() - pf_start; o[1] = pf_full; o[2] = pf_tmem; o[3] = kc;
+      }
+#endif
+      (void)pf_full; (void)pf_tmem;
     }
   } else if (A_LSU && warp >= kLoaderWarp0) {
     // ===== A loaders: thread t copies piece j = t % 8 of rows t / 8 + 16 i (i < 8) of every K slice =====
@@ -723,54 +798,57 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else {
     // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
     const int q = warp % 4;
-    uint8_t* store_buf = smem + L::kStoreOff + (warp - kEpiWarp0) * 2 * kStoreBufBytes;
+    uint8_t* store_base = smem + L::kStoreOff;
+    const bool issuer = (warp == kEpiWarp0 && lane == 0);   // the one thread that issues (and tracks) this CTA's TMA stores
     const uint32_t empty_remote = mapa_u32(smem_u32(&tmem_empty_bar[0]), crank & ~1u);   // my pair leader's tmem_empty_bar[0]
     uint32_t it = 0, sc = 0;   // tiles done, store chunks issued
+    long long pf_acc = 0, pf_buf = 0;
+    FR_PROF_T0(pf_start);
     for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
       const uint32_t as = it % L::kAcc;
-      const int row0 = (((tile / n_tiles_n) * PAIRS + (int)pair) * CTAS + (int)rank) * BLOCK_M + q * 32;
+      const int m0 = (((tile / n_tiles_n) * PAIRS + (int)pair) * CTAS + (int)rank) * BLOCK_M;   // this CTA's first row
+      const int row0 = m0 + q * 32;
       const int n0 = (tile % n_tiles_n) * BLOCK_N;
+      FR_PROF_T0(pf_t0);
       mbar_wait(&tmem_full_bar[as], (it / L::kAcc) & 1, 4, it, tile);
+      FR_PROF_ADD(pf_acc, pf_t0);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
       float dot = 0.f;
-      if (EPI == EPI_STORE && ELT == 2) {
-        // fp16 activations: 64 accumulator columns fill one 128-byte row of the 32-row store box
+      if (EPI == EPI_STORE) {
+        // one chunk = 128 bytes of every row of the CTA (32 fp32 / 64 fp16 columns): each warp stages its 32 rows in
+        // its quarter of the 16 KB buffer, one thread stores the buffer
+        constexpr int kChunkCols = 128 / ELT;
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 64) {
-          uint32_t r0[32], r1[32];
-          tmem_ld32(taddr + c, r0);
-          tmem_ld32(taddr + c + 32, r1);
-          uint8_t* buf = store_buf + (sc & 1) * kStoreBufBytes;
-          if (lane == 0) bulk_wait_read<1>();
-          __syncwarp();
-          epi_chunk64_to_smem_f16(r0, r1, smem_u32(s_bias + n0 + c), smem_u32(buf), lane, p.relu);
+        for (int c = 0; c < BLOCK_N; c += kChunkCols, sc++) {
+          uint8_t* buf = store_base + (sc % kCtaStoreBufs) * kCtaStoreBytes;
+          const uint32_t mine = smem_u32(buf) + q * (32 * 128);
+          if (ELT == 2) {
+            uint32_t r0[32], r1[32];
+            tmem_ld32(taddr + c, r0);
+            tmem_ld32(taddr + c + 32, r1);
+            epi_chunk64_to_smem_f16(r0, r1, smem_u32(s_bias + n0 + c), mine, lane, p.relu);
+          } else {
+            uint32_t r[32];
+            tmem_ld32(taddr + c, r);
+            epi_chunk_to_smem(r, smem_u32(s_bias + n0 + c), mine, lane, p.relu);
+          }
           fence_proxy_async();
-          __syncwarp();
-          if (lane == 0 && row0 < p.M) {
-            tma_store_2d(&tmap_out, buf, n0 + c, row0);
+          // the store issued two chunks ago has finished READING its buffer -- the one chunk sc + 1 will be staged in
+          FR_PROF_T0(pf_t1);
+          if (issuer) bulk_wait_read<1>();
+          asm volatile("bar.sync %0, %1;" ::"n"(kEpiBarrier), "n"(128) : "memory");
+          FR_PROF_ADD(pf_buf, pf_t1);
+          if (issuer && m0 < p.M) {   // rows past M inside the box are clipped by the TMA unit
+            tma_store_2d(&tmap_out, buf, n0 + c, m0);
             bulk_commit();
           }
-          sc++;
         }
-      } else
+      } else {
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c, r);
-        if (EPI == EPI_STORE) {
-          uint8_t* buf = store_buf + (sc & 1) * kStoreBufBytes;
-          if (lane == 0) bulk_wait_read<1>();   // the store issued two chunks ago no longer reads `buf`
-          __syncwarp();
-          epi_chunk_to_smem(r, smem_u32(s_bias + n0 + c), smem_u32(buf), lane, p.relu);
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0 && row0 < p.M) {   // rows past M inside the box are clipped by the TMA unit
-            tma_store_2d(&tmap_out, buf, n0 + c, row0);
-            bulk_commit();
-          }
-          sc++;
-        } else {
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c, r);
           dot = epi_chunk_dot(r, smem_u32(s_bias + c), smem_u32(s_w4 + c), p.relu, dot);
         }
       }
@@ -783,7 +861,14 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         p.out[row0 + lane] = p.sigmoid ? 1.f / (1.f + __expf(-dot)) : dot;
       }
     }
-    if (EPI == EPI_STORE && lane == 0) bulk_wait_all<0>();   // stores complete before the CTA retires
+    if (EPI == EPI_STORE && issuer) bulk_wait_all<0>();   // stores complete before the CTA retires
+#ifdef FR_EXPERIMENTS
+    if (p.prof && blockIdx.x < 8 && issuer) {
+      long long* o = p.prof + blockIdx.x * 16 + 8;
+      o[0] = clock64() - pf_start; o[1] = pf_acc; o[2] = pf_buf; o[3] = it;
+    }
+#endif
+    (void)pf_acc; (void)pf_buf;
     tc_fence_before();
   }
   if (CTAS == 2) cluster_sync_all();   // the peer's smem / TMEM must stay alive until the pair is done
@@ -792,6 +877,344 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tc_fence_after();
     if (CTAS == 2) tmem_dealloc_pair(tmem_base, L::kTmemCols);
     else tmem_dealloc(tmem_base, L::kTmemCols);
+  }
+#ifdef FR_EXPERIMENTS
+  if (pf_tl) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    pf_tl[2] = t;
+  }
+#endif
+}
+
+// ---- the production kernel: CTA pairs, multi-slice TMA boxes, eight epilogue warps ------------------------------
+// tc_pair_kernel is what every layer of every batch runs through; tc_linear_kernel above survives only in
+// FR_EXPERIMENTS builds (1-CTA tiles, multicast clusters, the cp.async A loader).  Measurements behind it
+// (tools/tma_probe.cu, tools/tc_prof.py, profiles/r02_*):
+//   * The TMA unit of an SM retires roughly one load instruction per ~270-340 cycles whatever the box holds, up to
+//     32 KB: 16 KB boxes (one 128-row x 128-byte K slice) land at 48 B/clk/SM, two per slice = 683 cycles = 0.35 us,
+//     which is what the main loop of the old kernel ran at (0.36 us per slice; the four MMAs of a slice take 0.25-0.28).
+//     So a box here holds KS = 2 K slices: the row-major operand [rows][K] is described as a 3-D tensor
+//     {128 bytes, rows, K / slice} with strides {K * elt, 128} and fetched in boxes {128 B, 128 rows, 2 slices} = 32 KB,
+//     which land as two consecutive 128B-swizzled slice tiles: 86 B/clk/SM, the MMAs become the limit.
+//   * The epilogue of a 256-wide tile took 4.2 us with four warps (one per TMEM lane quarter: ~170 dependent
+//     instructions per 32-column chunk on a single warp per scheduler, a proxy fence, a named barrier and a TMA
+//     store) -- longer than the 4.0 us main loop of a layer-1 tile (K = 352), so layer 1 was epilogue-bound and
+//     every launch ended in a 2.5-4 us tail.  Now EIGHT epilogue warps (two per lane quarter, alternate 128-byte
+//     column chunks), each on its own: TMEM -> registers (bias, ReLU, rounding) -> a private 2 KB shared-memory
+//     buffer, 16 rows at a time (128-byte swizzle, conflict-free) -> read back transposed -> coalesced 16-byte
+//     global stores (eight lanes write the 128 contiguous bytes of a row, four rows per instruction: whole lines).
+//     No proxy fences, no named barriers, no TMA stores, 16 KB of staging instead of 48: the rest went to the
+//     operand ring.  (Measured on the way: storing straight from registers -- a thread owns a row, so 32 lanes hit
+//     32 different lines per instruction -- 7.8 us per tile; half-line pieces -- 4.9 us.)
+//   * What is left at batch 16384 is the memory system: with the stores of the epilogue switched off
+//     (FR_TC_NOSTORE=1, experiments build) the main loop runs at 0.26 us per slice (layer 2: 25 instead of 35 us),
+//     i.e. 33-67 MB of activation writes per layer next to 12+ TB/s of operand reads out of L2 are what the
+//     MMAs wait for.
+// Pipelines: smem ring (full / empty) TMA producer <-> MMA issuer; TMEM (tmem_full / tmem_empty) MMA issuer <->
+// epilogue, two accumulator stages for tiles up to 256 wide.
+constexpr int kPairThreads = 320;   // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue
+constexpr int kPairEpiWarps = 8;
+constexpr int kEpiBufBytes = 32 * 64;   // one epilogue warp's transpose buffer: 64 bytes of each of its 32 rows
+
+template <int BLOCK_N, int STAGES, int KS>
+struct PairLayout {
+  static constexpr int kASlice = BLOCK_M * 128;                   // one K slice of this CTA's 128 rows of A
+  static constexpr int kABytes = kASlice * KS;
+  static constexpr int kMmaN = BLOCK_N <= 256 ? BLOCK_N : 256;    // columns per tcgen05.mma
+  static constexpr int kNSub = BLOCK_N / kMmaN;                   // MMAs per K step
+  static constexpr int kSubRows = kMmaN / 2;                      // rows of Wt this CTA stages per MMA
+  static constexpr int kSubSlice = kSubRows * 128;
+  static constexpr int kSubBytes = kSubSlice * KS;                // [KS][kSubRows][128 B]
+  static constexpr int kStageBytes = kABytes + kNSub * kSubBytes;
+  static constexpr int kStoreOff = STAGES * kStageBytes;          // 8 epilogue warps x 2 KB transpose buffer
+  static constexpr int kAuxOff = kStoreOff + kPairEpiWarps * kEpiBufBytes;   // bias[kMaxN], w4[256], dot partials [2][128]
+  static constexpr int kBarOff = kAuxOff + (kMaxN + 256 + 256) * 4;
+  static constexpr int kNumBars = 2 * STAGES + 4;                 // full, empty, tmem_full[2], tmem_empty[2]
+  static constexpr int kTotal = kBarOff + kNumBars * 8 + 16;
+  static constexpr int kDyn = kTotal + 1024;                      // slack for manual 1024-B alignment
+  static constexpr int kAcc = BLOCK_N <= 256 ? 2 : 1;
+  static constexpr int kTmemCols = kAcc * BLOCK_N;
+};
+
+// 3-D variant of the pair load: coordinates {byte column (always 0), row, K slice}
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, uint32_t bar_cluster, void* smem, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+      "[%2];" ::"r"(smem_u32(smem)),
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void stg128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <int BLOCK_N, int STAGES, int EPI, int ELT, int KS>
+__global__ void __launch_bounds__(kPairThreads, 1)
+tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcParams p) {
+  constexpr int BK = 128 / ELT;   // elements of K per slice (one 128-byte swizzle row)
+  using L = PairLayout<BLOCK_N, STAGES, KS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* s_bias = reinterpret_cast<float*>(smem + L::kAuxOff);
+  float* s_w4 = s_bias + kMaxN;
+  float* s_dot = s_w4 + 256;                           // [2 accumulator stages][128 rows]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2], the leader's are the ones used
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int num_kb = (p.K + BK - 1) / BK;             // K slices
+  const int num_st = (num_kb + KS - 1) / KS;          // ring stages per tile
+  const int n_tiles_n = p.N / BLOCK_N;
+  const int n_tiles = ((p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * n_tiles_n;   // a tile = 256 rows x BLOCK_N
+  const int cluster_id = blockIdx.x / 2, n_clusters = gridDim.x / 2;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full_bar[s], 1);    // the leader's producer arrives once, bytes of both CTAs are expected
+      mbar_init(&empty_bar[s], 1);   // one multicast tcgen05.commit per use
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(&tmem_full_bar[a], 1);                    // one multicast tcgen05.commit per tile
+      mbar_init(&tmem_empty_bar[a], 2 * kPairEpiWarps);   // every epilogue warp of both CTAs
+    }
+    fence_barrier_init();
+  } else if (warp == 1) {
+    tmem_alloc_pair(tmem_ptr, L::kTmemCols);
+  } else if (warp >= kEpiWarp0) {
+    // weights, not produced by the preceding kernel: staged before the grid dependency resolves
+    const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..255
+    for (int i = et; i < p.N; i += kPairEpiWarps * 32) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    if (EPI == EPI_DOT)
+      for (int i = et; i < BLOCK_N; i += kPairEpiWarps * 32) s_w4[i] = p.w4[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // peer barriers must exist before any remote complete_tx / commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  if (p.pdl) griddep_wait();           // activations of the previous kernel are complete and visible from here
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs of the pair) =====
+    if (lane == 0) {
+      if (p.wait_flags) wait_for_peers(p);
+      long long pf_wait = 0;
+      FR_PROF_T0(pf_start);
+      const uint32_t bar0 = mapa_u32(smem_u32(&full_bar[0]), 0);   // the leader's full barriers
+      uint32_t kc = 0;   // ring stages issued so far (the ring position runs on across tiles)
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+        const int m0 = ((tile / n_tiles_n) * 2 + (int)rank) * BLOCK_M;
+        const int nb0 = (tile % n_tiles_n) * BLOCK_N + (int)rank * L::kSubRows;
+        for (int st = 0; st < num_st; st++, kc++) {
+          const int s = kc % STAGES;
+          FR_PROF_T0(pf_t);
+          mbar_wait(&empty_bar[s], ((kc / STAGES) & 1) ^ 1, 1, kc, tile);
+          FR_PROF_ADD(pf_wait, pf_t);
+          uint8_t* a_dst = smem + s * L::kStageBytes;
+          uint8_t* b_dst = a_dst + L::kABytes;
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * L::kStageBytes);
+          if (KS == 1) {
+            tma_load_2d_pair(&tmap_a, bar0 + s * 8, a_dst, st * BK, m0);
+#pragma unroll
+            for (int h = 0; h < L::kNSub; h++) tma_load_2d_pair(&tmap_b, bar0 + s * 8, b_dst + h * L::kSubBytes, st * BK, nb0 + h * L::kMmaN);
+          } else {   // K slices past K are zero-filled by the TMA unit (and their MMAs skipped)
+            tma_load_3d_pair(&tmap_a, bar0 + s * 8, a_dst, 0, m0, st * KS);
+#pragma unroll
+            for (int h = 0; h < L::kNSub; h++) tma_load_3d_pair(&tmap_b, bar0 + s * 8, b_dst + h * L::kSubBytes, 0, nb0 + h * L::kMmaN, st * KS);
+          }
+        }
+      }
+      if (p.pdl) griddep_launch();
+#ifdef FR_EXPERIMENTS
+      if (p.prof && blockIdx.x < 8) {
+        long long* o = p.prof + blockIdx.x * 16;
+        o[0] = clock64() - pf_start; o[1] = pf_wait; o[2] = kc;
+      }
+#endif
+      (void)pf_wait;
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer (the pair leader) =====
+    if (leader) {
+      constexpr uint32_t idesc = ELT == 2 ? make_idesc_f16_m(2 * BLOCK_M, L::kMmaN) : make_idesc_tf32_m(2 * BLOCK_M, L::kMmaN);
+      uint32_t kc = 0, it = 0;
+      long long pf_full = 0, pf_tmem = 0;
+      FR_PROF_T0(pf_start);
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
+        const uint32_t as = it % L::kAcc;
+        FR_PROF_T0(pf_t0);
+        mbar_wait(&tmem_empty_bar[as], ((it / L::kAcc) & 1) ^ 1, 2, kc, tile);   // the epilogue has drained this accumulator stage
+        FR_PROF_ADD(pf_tmem, pf_t0);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int st = 0; st < num_st; st++, kc++) {
+          const int s = kc % STAGES;
+          FR_PROF_T0(pf_t1);
+          mbar_wait(&full_bar[s], (kc / STAGES) & 1, 3, kc, tile);
+          FR_PROF_ADD(pf_full, pf_t1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+            const uint32_t b_addr = a_addr + L::kABytes;
+#pragma unroll
+            for (int j = 0; j < KS; j++) {
+              if (st * KS + j < num_kb) {
+                const uint64_t a_desc = make_smem_desc(a_addr + j * L::kASlice);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {   // 32 bytes of K per instruction: +2 in the (addr >> 4) field
+#pragma unroll
+                  for (int h = 0; h < L::kNSub; h++) {
+                    const uint64_t b_desc = make_smem_desc(b_addr + h * L::kSubBytes + j * L::kSubSlice);
+                    const uint32_t acc = (st | j | k) != 0;
+                    if (ELT == 2) umma_f16_pair(d_tmem + h * L::kMmaN, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, acc);
+                    else umma_tf32_pair(d_tmem + h * L::kMmaN, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, acc);
+                  }
+                }
+              }
+            }
+            umma_commit_pair(&empty_bar[s]);                            // frees the slot in both CTAs
+            if (st == num_st - 1) umma_commit_pair(&tmem_full_bar[as]);  // accumulators complete in both CTAs
+          }
+          __syncwarp();
+        }
+      }
+#ifdef FR_EXPERIMENTS
+      if (p.prof && blockIdx.x < 8 && lane == 0) {
+        long long* o = p.prof + blockIdx.x * 16 + 4;
+        o[0] = clock64() - pf_start; o[1] = pf_full; o[2] = pf_tmem; o[3] = kc;
+      }
+#endif
+      (void)pf_full; (void)pf_tmem;
+    }
+  } else {
+    // ===== epilogue warps: TMEM lane quarter q = warp % 4, two warps per quarter on alternate chunks =====
+    const int q = warp % 4, half = (warp - kEpiWarp0) / 4;
+    const uint32_t empty_remote = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);   // the leader's tmem_empty_bar[0]
+    constexpr int CH = 128 / ELT;   // columns per chunk: 128 bytes of this thread's output row
+    uint32_t it = 0;
+    long long pf_acc = 0;
+    FR_PROF_T0(pf_start);
+    for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, it++) {
+      const uint32_t as = it % L::kAcc;
+      const int row = ((tile / n_tiles_n) * 2 + (int)rank) * BLOCK_M + q * 32 + lane;
+      const int n0 = (tile % n_tiles_n) * BLOCK_N;
+      FR_PROF_T0(pf_t0);
+      mbar_wait(&tmem_full_bar[as], (it / L::kAcc) & 1, 4, it, tile);
+      FR_PROF_ADD(pf_acc, pf_t0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
+      float dot = 0.f;
+      if (EPI == EPI_STORE) {
+        // a chunk = 128 bytes (one line) of every row of this warp: 32 fp32 / 64 fp16 output columns, staged 16 rows at
+        // a time in the warp's 2 KB buffer (classic 128-byte swizzle: piece j of row r at piece j ^ (r & 7))
+        constexpr int CH = 128 / ELT;
+        const int row_base = row - lane;
+        const uint32_t wbuf = smem_u32(smem + L::kStoreOff + (warp - kEpiWarp0) * kEpiBufBytes);
+        const uint32_t st_row = wbuf + (lane & 15) * 128, st_sw = (uint32_t)(lane & 7);
+        uint8_t* obase = reinterpret_cast<uint8_t*>(p.out_act) + (size_t)n0 * ELT;
+#pragma unroll 1
+        for (int c = half * CH; c < BLOCK_N; c += 2 * CH) {
+          uint32_t o[32];
+          const uint32_t ba = smem_u32(s_bias + n0 + c);
+          if (ELT == 2) {
+            uint32_t r0[32], r1[32];
+            tmem_ld32(taddr + c, r0);
+            tmem_ld32(taddr + c + 32, r1);
+#pragma unroll
+            for (int j = 0; j < 16; j++) {   // 4 columns -> 2 packed registers
+              const float4 bv = lds128(ba + j * 16);
+              const uint32_t* r = j < 8 ? r0 + 4 * j : r1 + 4 * (j - 8);
+              float v0 = __uint_as_float(r[0]) + bv.x, v1 = __uint_as_float(r[1]) + bv.y;
+              float v2 = __uint_as_float(r[2]) + bv.z, v3 = __uint_as_float(r[3]) + bv.w;
+              if (p.relu) {
+                v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
+              }
+              o[2 * j] = pack_f16x2(v0, v1);
+              o[2 * j + 1] = pack_f16x2(v2, v3);
+            }
+          } else {
+            uint32_t r[32];
+            tmem_ld32(taddr + c, r);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const float4 bv = lds128(ba + j * 16);
+              float v0 = __uint_as_float(r[4 * j]) + bv.x, v1 = __uint_as_float(r[4 * j + 1]) + bv.y;
+              float v2 = __uint_as_float(r[4 * j + 2]) + bv.z, v3 = __uint_as_float(r[4 * j + 3]) + bv.w;
+              if (p.relu) {
+                v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
+              }
+              o[4 * j] = __float_as_uint(round_tf32(v0)); o[4 * j + 1] = __float_as_uint(round_tf32(v1));
+              o[4 * j + 2] = __float_as_uint(round_tf32(v2)); o[4 * j + 3] = __float_as_uint(round_tf32(v3));
+            }
+          }
+#pragma unroll
+          for (int hh = 0; hh < 2; hh++) {   // rows 0..15 of the warp, then rows 16..31
+            __syncwarp();                    // the previous 16 rows have been read back
+            if ((lane >> 4) == hh) {
+#pragma unroll
+              for (int j = 0; j < 8; j++)
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(st_row + ((j ^ st_sw) << 4)), "r"(o[4 * j]), "r"(o[4 * j + 1]),
+                             "r"(o[4 * j + 2]), "r"(o[4 * j + 3]) : "memory");
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; i++) {    // eight lanes write the 128 contiguous bytes of a row, four rows per instruction
+              const int R = (lane >> 3) + 4 * i, P = lane & 7;
+              uint32_t v0, v1, v2, v3;
+              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                           : "r"(wbuf + R * 128 + ((P ^ (R & 7)) << 4)));
+              const int grow = row_base + hh * 16 + R;
+              if (grow < p.M && !p.dbg_nostore) stg128(obase + ((size_t)grow * p.N + c) * ELT + P * 16, v0, v1, v2, v3);
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = half * 32; c < BLOCK_N; c += 64) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c, r);
+          dot = epi_chunk_dot(r, smem_u32(s_bias + c), smem_u32(s_w4 + c), p.relu, dot);
+        }
+      }
+      // this warp's share of the accumulator stage has been read: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(empty_remote + as * 8);
+      if (EPI == EPI_DOT) {
+        // the two warps of a lane quarter hold the even / odd chunks' partial sums of the same rows: the second
+        // hands its sum over in shared memory (double-buffered by accumulator stage), the first finishes the row
+        float* slot = s_dot + as * BLOCK_M + q * 32 + lane;
+        if (half == 1) *slot = dot;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(64) : "memory");
+        if (half == 0 && row < p.M) {
+          dot += *slot;
+          if (p.b4) dot += p.b4[0];
+          p.out[row] = p.sigmoid ? 1.f / (1.f + __expf(-dot)) : dot;
+        }
+      }
+    }
+#ifdef FR_EXPERIMENTS
+    if (p.prof && blockIdx.x < 8 && warp == kEpiWarp0 && lane == 0) {
+      long long* o = p.prof + blockIdx.x * 16 + 8;
+      o[0] = clock64() - pf_start; o[1] = pf_acc; o[2] = 0; o[3] = it;
+    }
+#endif
+    (void)pf_acc;
+    tc_fence_before();
+  }
+  cluster_sync_all();   // the peer's smem / TMEM must stay alive until the pair is done
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, L::kTmemCols);
   }
 }
 
@@ -1404,16 +1827,21 @@ struct TcState {
   // the stores and the next phase's prefetch in that window: 65 us per tile, 192 against 223 M inferences/s.
   bool chain = false;
   long long* d_prof = nullptr;   // FR_CHAIN_PROF=1: the chain kernel's CTA 0 writes its phase timeline here
+  long long* d_tc_prof = nullptr;   // FR_TC_PROF=1 (experiments build): pipeline cycle counters of tc_linear_kernel's first 8 CTAs
   TcLayerCfg cfg[3];
   bool ready = false;
   // cached activation maps keyed by (pointer, K, rows, box rows): 128-row boxes feed the A operand,
   // 32-row boxes are the epilogue's store boxes
   struct AMap {
     const void* ptr;
-    int K, rows, box_rows, elt;
+    int K, rows, box_rows, elt, ks;   // ks = 0: 2-D map, one K slice per box; ks > 1: 3-D map, ks slices per box
     CUtensorMap map;
   };
   CUtensorMap w_map16[3];   // tc_f16: fp16 weights in 128-row x 64-element boxes
+  // 3-D views {128 bytes, rows, K slices} of the same weights, boxes of two K slices (tc_pair_kernel KS = 2): 128- and
+  // 64-row boxes of the TF32 weights, 128-row boxes of the fp16 copies; w3_ok[k]: layer k's K is a whole number of slices
+  CUtensorMap w3_128[3], w3_64[3], w3h_128[3];
+  bool w3_ok[3] = {false, false, false}, w3h_ok[3] = {false, false, false};
   std::vector<AMap> a_maps;
   std::mutex mu;
 };
@@ -1433,6 +1861,28 @@ fr_status encode_2d(fr_engine* e, TcState* st, CUtensorMap* map, const void* bas
   if (r != CUDA_SUCCESS)
     return fr_fail(e, FR_ERR_CUDA, "cuTensorMapEncodeTiled(rows=%d K=%d box=%d) failed: CUresult %d", rows, K, box_rows,
                    (int)r);
+  return FR_OK;
+}
+
+// The same row-major operand [rows][K] seen as a 3-D tensor {one 128-byte K slice, rows, K slices} with byte strides
+// {K * elt, 128}: a box {128 B, box_rows, ks} brings `ks` consecutive K slices of box_rows rows in ONE instruction and
+// lands as ks consecutive 128B-swizzled slice tiles -- the shared-memory layout the per-slice 2-D boxes produce, at a
+// quarter to half the TMA instructions per byte (tools/tma_probe.cu: 86 against 48 B/clk/SM).  K must be a whole
+// number of slices (the unit cannot know where a row ends inside a slice); slices past K read as zeros.
+fr_status encode_3d(fr_engine* e, TcState* st, CUtensorMap* map, const void* base, int rows, int K, int box_rows, int ks,
+                    int elt = 4) {
+  const int bk = 128 / elt;
+  if (K % bk) return fr_fail(e, FR_ERR_INVALID, "encode_3d: K=%d is not a whole number of %d-element slices", K, bk);
+  const cuuint64_t dims[3] = {(cuuint64_t)bk, (cuuint64_t)rows, (cuuint64_t)(K / bk)};
+  const cuuint64_t strides[2] = {(cuuint64_t)K * elt, 128};
+  const cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)box_rows, (cuuint32_t)ks};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = st->encode(map, elt == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                          const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fr_fail(e, FR_ERR_CUDA, "cuTensorMapEncodeTiled(3-D, rows=%d K=%d box=%d x %d slices) failed: CUresult %d", rows, K,
+                   box_rows, ks, (int)r);
   return FR_OK;
 }
 
@@ -1492,10 +1942,10 @@ fr_status launch(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const
 }
 
 fr_status get_a_map(fr_engine* e, TcState* st, const void* ptr, int K, int rows, int box_rows, CUtensorMap* out,
-                    int elt = 4) {
+                    int elt = 4, int ks = 0) {
   std::lock_guard<std::mutex> g(st->mu);
   for (const TcState::AMap& m : st->a_maps)
-    if (m.ptr == ptr && m.K == K && m.rows == rows && m.box_rows == box_rows && m.elt == elt) {
+    if (m.ptr == ptr && m.K == K && m.rows == rows && m.box_rows == box_rows && m.elt == elt && m.ks == ks) {
       *out = m.map;
       return FR_OK;
     }
@@ -1505,10 +1955,56 @@ fr_status get_a_map(fr_engine* e, TcState* st, const void* ptr, int K, int rows,
   m.rows = rows;
   m.box_rows = box_rows;
   m.elt = elt;
-  fr_status s = encode_2d(e, st, &m.map, ptr, rows, K, box_rows, elt);
+  m.ks = ks;
+  fr_status s = ks > 1 ? encode_3d(e, st, &m.map, ptr, rows, K, box_rows, ks, elt) : encode_2d(e, st, &m.map, ptr, rows, K, box_rows, elt);
   if (s != FR_OK) return s;
   if (st->a_maps.size() < 1024) st->a_maps.push_back(m);
   *out = m.map;
+  return FR_OK;
+}
+
+// Launch of the production kernel: persistent, one CTA pair per tile up to one CTA per SM.
+template <int BLOCK_N, int STAGES, int EPI, int ELT, int KS>
+fr_status launch_pair(fr_engine* e, const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, bool pdl_attr, cudaStream_t st) {
+  using L = PairLayout<BLOCK_N, STAGES, KS>;
+  static_assert(L::kDyn <= 227 * 1024, "tile configuration exceeds the 227 KB shared memory of an SM");
+  static_assert(L::kTmemCols == 256 || L::kTmemCols == 512, "TMEM allocation must be a power of two");
+  auto kern = tc_pair_kernel<BLOCK_N, STAGES, EPI, ELT, KS>;
+  static std::atomic<uint64_t> attr_done{0};  // bit d: opt-in smem size set on device d for this instantiation
+  const uint64_t bit = 1ull << (e->device & 63);
+  if (!(attr_done.load() & bit)) {
+    FR_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDyn));
+    attr_done.fetch_or(bit);
+  }
+  const int n_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M) * (p.N / BLOCK_N);
+  int max_clusters = e->sm_count / 2;
+  if (e->knobs.max_clusters > 0 && e->knobs.max_clusters < max_clusters) max_clusters = e->knobs.max_clusters;   // test hook
+  const int num_kb = (p.K + 128 / ELT - 1) / (128 / ELT);
+  // Short tiles are ganged (several per cluster) so that a cluster's fixed cost is paid once -- only with two
+  // accumulator stages (the epilogue of one tile under the MMAs of the next), never in latency mode, and only for
+  // launches that could not fill half the machine anyway; an fp16 K slice carries twice the K of a TF32 one.
+  const int min_kb = ELT == 2 ? (e->knobs.min_kb + 1) / 2 : e->knobs.min_kb;
+  const int gang = (num_kb >= min_kb || L::kAcc == 1 || p.latency || 2 * n_tiles >= max_clusters)
+                       ? 1 : (min_kb + num_kb - 1) / num_kb;
+  int n_clusters = (n_tiles + gang - 1) / gang;
+  if (n_clusters > max_clusters) n_clusters = max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_clusters * 2, 1, 1);
+  cfg.blockDim = dim3(kPairThreads, 1, 1);
+  cfg.dynamicSmemBytes = L::kDyn;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_attr ? 2 : 1;
+  FR_CUDA(e, cudaLaunchKernelEx(&cfg, kern, a, b, p));
+  e->launches++;
+  e->tc_last_ctas = n_clusters * 2;
   return FR_OK;
 }
 
@@ -1601,7 +2097,17 @@ fr_status frtc_prepare(fr_engine* e) {
     st->a_lsu = e->knobs.a_lsu;
     for (int k = 0; k < 3; k++)
       if ((s = encode_2d(e, st, &st->w_map128[k], e->d_Wt[k], e->dims[k + 1], e->dims[k], 128)) != FR_OK) return s;
+    for (int k = 0; k < 3; k++) {
+      st->w3_ok[k] = e->dims[k] % BLOCK_K == 0;   // (medium model layer 1: K = 880 = 27.5 slices -> one slice per box)
+      if (!st->w3_ok[k]) continue;
+      if ((s = encode_3d(e, st, &st->w3_128[k], e->d_Wt[k], e->dims[k + 1], e->dims[k], 128, 2)) != FR_OK) return s;
+      if ((s = encode_3d(e, st, &st->w3_64[k], e->d_Wt[k], e->dims[k + 1], e->dims[k], 64, 2)) != FR_OK) return s;
+    }
     st->chain = e->knobs.chain;
+    if (e->knobs.tc_prof && !st->d_tc_prof) {
+      FR_CUDA(e, cudaMalloc(&st->d_tc_prof, 8 * 16 * sizeof(long long)));
+      FR_CUDA(e, cudaMemset(st->d_tc_prof, 0, 8 * 16 * sizeof(long long)));
+    }
     if (e->knobs.chain_prof && !st->d_prof) {
       FR_CUDA(e, cudaMalloc(&st->d_prof, kProfIters * kProfPhases * kProfSlots * sizeof(long long)));
       FR_CUDA(e, cudaMemset(st->d_prof, 0, kProfIters * kProfPhases * kProfSlots * sizeof(long long)));
@@ -1619,6 +2125,8 @@ fr_status frtc_prepare_f16(fr_engine* e) {
   for (int k = 0; k < 3; k++) {
     fr_status s = encode_2d(e, st, &st->w_map16[k], e->d_Wt16[k], e->dims[k + 1], e->dims[k], 128, 2);
     if (s != FR_OK) return s;
+    st->w3h_ok[k] = e->dims[k] % 64 == 0;   // an fp16 K slice is 64 elements (small model layer 1: 352 = 5.5)
+    if (st->w3h_ok[k] && (s = encode_3d(e, st, &st->w3h_128[k], e->d_Wt16[k], e->dims[k + 1], e->dims[k], 128, 2, 2)) != FR_OK) return s;
   }
   return FR_OK;
 }
@@ -1641,8 +2149,23 @@ extern "C" int frdbg_chain_timeline(fr_engine* e, long long* out, int n) {
 
 #endif
 
+#ifdef FR_EXPERIMENTS
+// Debug hook (tools/tc_prof.py): the cycle counters the last tc_linear_kernel launch's first 8 CTAs wrote, [8][16].
+extern "C" int frdbg_tc_prof(fr_engine* e, long long* out, int n) {
+  TcState* st = e ? static_cast<TcState*>(e->tc_state) : nullptr;
+  if (!st || !st->d_tc_prof || !out || n < 128) return 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return 0;
+  if (cudaMemcpy(out, st->d_tc_prof, 128 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  cudaMemset(st->d_tc_prof, 0, 128 * sizeof(long long));
+  return 128;
+}
+#endif
+
 void frtc_destroy(fr_engine* e) {
-  if (TcState* st = static_cast<TcState*>(e->tc_state)) cudaFree(st->d_prof);
+  if (TcState* st = static_cast<TcState*>(e->tc_state)) {
+    cudaFree(st->d_prof);
+    cudaFree(st->d_tc_prof);
+  }
   delete static_cast<TcState*>(e->tc_state);
   e->tc_state = nullptr;
 }
@@ -1793,92 +2316,113 @@ fr_status frtc_layer(fr_engine* e, fr_stream_s* s, int k, const float* in, int B
   return r;
 }
 
-// fp16 operands (tc_f16): `in` and s->d_h[k] hold fp16 [B][dim]; CTA pairs, 512-wide tiles where K is long
-static fr_status frtc_layer_f16(fr_engine* e, fr_stream_s* s, int k, const float* in, int B, float* d_scores) {
-  TcState* st = static_cast<TcState*>(e->tc_state);
-  const bool act = (e->mlp_mode == FR_MLP_BIAS_RELU_SIGMOID);
+#ifdef FR_EXPERIMENTS
+// tc_linear_kernel and its variants (not instantiated in release builds): 1-CTA tiles, 4-CTA multicast clusters, the
+// cp.async A loader; TMA-store epilogue with four warps.
+static fr_status frtc_layer_legacy(fr_engine* e, fr_stream_s* s, TcState* st, int k, const float* in, int B, const TcParams& p,
+                                   TcLayerCfg c, bool pa) {
   CUtensorMap a, o;
-  fr_status r = get_a_map(e, st, in, e->dims[k], B, BLOCK_M, &a, 2);
-  if (r != FR_OK) return r;
-  o = a;
-  if (k < 2 && (r = get_a_map(e, st, s->d_h[k], e->dims[k + 1], B, kStoreBoxRows, &o, 2)) != FR_OK) return r;
-  TcParams p;
-  p.a = in;
-  p.bias = act ? e->d_bias[k] : nullptr;
-  p.M = B;
-  p.N = e->dims[k + 1];
-  p.K = e->dims[k];
-  p.relu = act ? 1 : 0;
-  p.sigmoid = act ? 1 : 0;
-  p.w4 = e->d_W[3];
-  p.b4 = act ? e->d_bias[3] : nullptr;
-  p.pdl = 0;
-  p.out = d_scores;
-  p.latency = 0;
-  p.wait_flags = p.wait_step = nullptr;
-  p.wait_n = 0;
-  p.wait_err = nullptr;
-  const int N = p.N, num_kb = (p.K + 63) / 64;
-  const int tiles256 = (B + 2 * BLOCK_M - 1) / (2 * BLOCK_M) * (N / 256);
-  if (k == 2) return launch<256, 5, EPI_DOT, 2, 1, false, 2>(e, a, st->w_map16[k], o, p, false, s->stream);
-  if (N % 512 == 0 && num_kb >= kWideMinKb && tiles256 < e->sm_count / 2)
-    return launch<512, 3, EPI_STORE, 2, 1, false, 2>(e, a, st->w_map16[k], o, p, false, s->stream);
-  return launch<256, 5, EPI_STORE, 2, 1, false, 2>(e, a, st->w_map16[k], o, p, false, s->stream);
-}
-
-static fr_status frtc_layer_impl(fr_engine* e, fr_stream_s* s, int k, const float* in, int B, float* d_scores,
-                                 const FrPeerWait* wait) {
-  if (s->f16) return frtc_layer_f16(e, s, k, in, B, d_scores);   // (single-GPU engines only: never with a wait)
-  TcState* st = static_cast<TcState*>(e->tc_state);
-  const bool act = (e->mlp_mode == FR_MLP_BIAS_RELU_SIGMOID);
-  CUtensorMap a, o;
-  // rows = B: TMA zero-fills the M tail on load and clips it on store, so no stale rows are ever
-  // multiplied or written
   fr_status r = get_a_map(e, st, in, e->dims[k], B, BLOCK_M, &a);
   if (r != FR_OK) return r;
   o = a;
-  if (k < 2 && (r = get_a_map(e, st, s->d_h[k], e->dims[k + 1], B, kStoreBoxRows, &o)) != FR_OK) return r;
-  TcParams p;
-  p.a = in;
-  p.bias = act ? e->d_bias[k] : nullptr;
-  p.M = B;
-  p.N = e->dims[k + 1];
-  p.K = e->dims[k];
-  p.relu = act ? 1 : 0;
-  p.sigmoid = act ? 1 : 0;
-  p.w4 = e->d_W[3];
-  p.b4 = act ? e->d_bias[3] : nullptr;
-  p.pdl = e->knobs.pdl_mask ? 1 : 0;
-  const bool pa = (e->knobs.pdl_mask & (k == 0 ? 2 : 1)) != 0;   // may this layer start under the tail of its predecessor
-  p.out = d_scores;
-  p.wait_flags = wait ? wait->flags : nullptr;
-  p.wait_step = wait ? wait->step : nullptr;
-  p.wait_n = wait ? wait->world : 0;
-  p.wait_err = wait ? wait->err : nullptr;
-  TcLayerCfg c = st->cfg[k];
-  if (st->auto_tiles && k < 2) c.block_n = pick_block_n(e, k, B);   // same 128-row weight boxes for 256 and 512
+  if (k < 2 && (r = get_a_map(e, st, s->d_h[k], e->dims[k + 1], B, BLOCK_M, &o)) != FR_OK) return r;
   const CUtensorMap& w = (st->auto_tiles && k < 2 && c.block_n == 128) ? st->w_map64[k] : st->w_map[k];
-  p.latency = (st->auto_tiles && latency_mode(e, B)) ? 1 : 0;
   cudaStream_t cs = s->stream;
-#ifdef FR_EXPERIMENTS
-  // throughput-sized batches: two pairs per cluster share every weight slice by TMA multicast (each CTA loads
-  // half of its share: 128-row boxes for 512-wide tiles, 64-row boxes for 256-wide ones)
-  if (!wait && st->mcast && st->auto_tiles && B > kLatencyBatch && c.ctas == 2 && c.block_n >= 256) {
+  if (st->mcast && st->auto_tiles && c.ctas == 2 && c.block_n >= 256) {
     if (k < 2 && c.block_n == 512) return launch<512, 3, EPI_STORE, 2, 2>(e, a, st->w_map128[k], o, p, pa, cs);
     if (k < 2) return launch<256, 5, EPI_STORE, 2, 2>(e, a, st->w_map64[k], o, p, pa, cs);
     return launch<256, 5, EPI_DOT, 2, 2>(e, a, st->w_map64[k], o, p, pa, cs);
   }
-  // throughput-sized batches on plain pairs: the A operand goes through the LSU (cp.async), TMA carries the weights
-  if (!wait && st->a_lsu && st->auto_tiles && B > kLatencyBatch && c.ctas == 2 && c.block_n >= 256) {
+  if (st->a_lsu && st->auto_tiles && c.ctas == 2 && c.block_n >= 256) {
     if (k < 2 && c.block_n == 512) return launch<512, 3, EPI_STORE, 2, 1, true>(e, a, w, o, p, pa, cs);
     if (k < 2) return launch<256, 5, EPI_STORE, 2, 1, true>(e, a, w, o, p, pa, cs);
     return launch<256, 5, EPI_DOT, 2, 1, true>(e, a, w, o, p, pa, cs);
   }
-#endif
   if (k < 2) {
     if (c.block_n == 512) return launch<512, 3, EPI_STORE, 2>(e, a, w, o, p, pa, cs);
     if (c.ctas == 2) return c.block_n == 256 ? launch<256, 5, EPI_STORE, 2>(e, a, w, o, p, pa, cs) : launch<128, 7, EPI_STORE, 2>(e, a, w, o, p, pa, cs);
     return c.block_n == 256 ? launch<256, 3, EPI_STORE, 1>(e, a, w, o, p, pa, cs) : launch<128, 5, EPI_STORE, 1>(e, a, w, o, p, pa, cs);
   }
   return c.ctas == 2 ? launch<256, 5, EPI_DOT, 2>(e, a, w, o, p, pa, cs) : launch<256, 3, EPI_DOT, 1>(e, a, w, o, p, pa, cs);
+}
+#endif
+
+static void fill_params(fr_engine* e, fr_stream_s* s, TcState* st, int k, const float* in, int B, float* d_scores,
+                        const FrPeerWait* wait, TcParams* p) {
+  const bool act = (e->mlp_mode == FR_MLP_BIAS_RELU_SIGMOID);
+  p->a = in;
+  p->bias = act ? e->d_bias[k] : nullptr;
+  p->M = B;
+  p->N = e->dims[k + 1];
+  p->K = e->dims[k];
+  p->relu = act ? 1 : 0;
+  p->sigmoid = act ? 1 : 0;
+  p->w4 = e->d_W[3];
+  p->b4 = act ? e->d_bias[3] : nullptr;
+  p->pdl = e->knobs.pdl_mask ? 1 : 0;
+  p->out = d_scores;
+  p->out_act = k < 2 ? s->d_h[k] : nullptr;
+  p->latency = (st->auto_tiles && latency_mode(e, B)) ? 1 : 0;
+  p->wait_flags = wait ? wait->flags : nullptr;
+  p->wait_step = wait ? wait->step : nullptr;
+  p->wait_n = wait ? wait->world : 0;
+  p->wait_err = wait ? wait->err : nullptr;
+  p->prof = st->d_tc_prof;
+  p->dbg_nostore = e->knobs.dbg_nostore;
+}
+
+// fp16 operands (s->f16): `in` and s->d_h[k] hold fp16 [B][dim]; 512-wide tiles where K is long, else 256-wide
+static fr_status frtc_layer_f16(fr_engine* e, fr_stream_s* s, int k, const float* in, int B, float* d_scores) {
+  TcState* st = static_cast<TcState*>(e->tc_state);
+  TcParams p;
+  fill_params(e, s, st, k, in, B, d_scores, nullptr, &p);
+  const bool ks2 = st->w3h_ok[k];
+  CUtensorMap a;
+  fr_status r = get_a_map(e, st, in, e->dims[k], B, BLOCK_M, &a, 2, ks2 ? 2 : 0);
+  if (r != FR_OK) return r;
+  const int N = p.N, num_kb = (p.K + 63) / 64;
+  const int tiles256 = (B + 2 * BLOCK_M - 1) / (2 * BLOCK_M) * (N / 256);
+  cudaStream_t cs = s->stream;
+  if (k == 2) return ks2 ? launch_pair<256, 3, EPI_DOT, 2, 2>(e, a, st->w3h_128[k], p, false, cs)
+                         : launch_pair<256, 6, EPI_DOT, 2, 1>(e, a, st->w_map16[k], p, false, cs);
+  if (N % 512 == 0 && num_kb >= kWideMinKb && tiles256 < e->sm_count / 2 && !p.latency) {
+    if (ks2) {   // (512-wide tiles take one slice per box: three instructions per 48 KB keep up with their eight MMAs)
+      r = get_a_map(e, st, in, e->dims[k], B, BLOCK_M, &a, 2, 0);
+      if (r != FR_OK) return r;
+    }
+    return launch_pair<512, 4, EPI_STORE, 2, 1>(e, a, st->w_map16[k], p, false, cs);
+  }
+  return ks2 ? launch_pair<256, 3, EPI_STORE, 2, 2>(e, a, st->w3h_128[k], p, false, cs)
+             : launch_pair<256, 6, EPI_STORE, 2, 1>(e, a, st->w_map16[k], p, false, cs);
+}
+
+static fr_status frtc_layer_impl(fr_engine* e, fr_stream_s* s, int k, const float* in, int B, float* d_scores,
+                                 const FrPeerWait* wait) {
+  if (s->f16) return frtc_layer_f16(e, s, k, in, B, d_scores);   // (single-GPU engines only: never with a wait)
+  TcState* st = static_cast<TcState*>(e->tc_state);
+  TcParams p;
+  fill_params(e, s, st, k, in, B, d_scores, wait, &p);
+  const bool pa = (e->knobs.pdl_mask & (k == 0 ? 2 : 1)) != 0;   // may this layer start under the tail of its predecessor
+  TcLayerCfg c = st->cfg[k];
+  if (st->auto_tiles && k < 2) c.block_n = pick_block_n(e, k, B);
+  cudaStream_t cs = s->stream;
+#ifdef FR_EXPERIMENTS
+  // the older kernel with its variants: 1-CTA tiles (FR_TC_TILES=...,1), multicast clusters, cp.async A loader
+  if (c.ctas == 1 || ((st->mcast || st->a_lsu) && !wait && st->auto_tiles && B > kLatencyBatch && c.block_n >= 256))
+    return frtc_layer_legacy(e, s, st, k, in, B, p, c, pa);
+#else
+  if (c.ctas != 2) return fr_fail(e, FR_ERR_UNSUPPORTED, "1-CTA tcgen05 tiles exist in FR_EXPERIMENTS builds only");
+#endif
+  // rows = B: TMA zero-fills the M tail on load; the epilogue masks its stores by the row count
+  const bool ks2 = st->w3_ok[k] && c.block_n != 512;
+  CUtensorMap a;
+  fr_status r = get_a_map(e, st, in, e->dims[k], B, BLOCK_M, &a, 4, ks2 ? 2 : 0);
+  if (r != FR_OK) return r;
+  if (k == 2) return ks2 ? launch_pair<256, 3, EPI_DOT, 4, 2>(e, a, st->w3_128[k], p, pa, cs)
+                         : launch_pair<256, 6, EPI_DOT, 4, 1>(e, a, st->w_map128[k], p, pa, cs);
+  if (c.block_n == 512) return launch_pair<512, 4, EPI_STORE, 4, 1>(e, a, st->w_map128[k], p, pa, cs);
+  if (c.block_n == 256) return ks2 ? launch_pair<256, 3, EPI_STORE, 4, 2>(e, a, st->w3_128[k], p, pa, cs)
+                                   : launch_pair<256, 6, EPI_STORE, 4, 1>(e, a, st->w_map128[k], p, pa, cs);
+  return ks2 ? launch_pair<128, 4, EPI_STORE, 4, 2>(e, a, st->w3_64[k], p, pa, cs)
+             : launch_pair<128, 8, EPI_STORE, 4, 1>(e, a, st->w_map64[k], p, pa, cs);
 }
