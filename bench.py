@@ -835,14 +835,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="small")
     ap.add_argument("--batch", type=int, default=2048)
-    ap.add_argument("--streams", type=int, default=12)
+    ap.add_argument("--streams", type=int, default=0,
+                    help="worker streams = batches in flight; 0 = 12 on one GPU (more only adds L2 pressure: 8 -> 184, 10-12 -> 209, 16 -> 204 M/s),\n"
+                         "16 for a table-sharded multi-GPU run (more steps in flight hide the exchange: 12 -> 1314, 16 -> 1453 M/s at 8 GPUs)")
     ap.add_argument("--rounds", type=int, default=64, help="a step = this many batches on every worker stream")
     ap.add_argument("--group", type=int, default=4, help="e2e: batches per fr_infer_many call (one copy each way per call)")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--tiles", default="", help="FR_TC_TILES override: N1,N2,N3,ctas")
     ap.add_argument("--shard", default="tables", choices=["replicated", "tables"],
                     help="N > 1: shard tables across ranks with the NVLink push exchange (north star), or replicate")
-    ap.add_argument("--plan", default="balanced", choices=["balanced", "contiguous"],
+    ap.add_argument("--plan", default="contiguous", choices=["balanced", "contiguous"],
                     help="table sharding: owner plan (fleetrec.shard.plan_owners policy)")
     ap.add_argument("--replicate-mb", type=int, default=0,
                     help="table sharding: also replicate any table smaller than this many MiB (0: only the on-chip class)")
@@ -863,6 +865,8 @@ def main():
                     help="stress workload: storage type of the tables (SURVEY.md 8(f)4)")
     ap.add_argument("--sweep-launches", type=int, default=1000)
     args = ap.parse_args()
+    if args.streams <= 0:
+        args.streams = 12 if int(os.environ.get("WORLD_SIZE", "1")) == 1 or args.shard != "tables" else 16
     if args.tiles:
         os.environ["FR_TC_TILES"] = args.tiles
     if args.rounds % args.group:

@@ -50,6 +50,7 @@ static void fr_read_knobs(FrKnobs* k) {
   k->chain_prof = num("FR_CHAIN_PROF", 0) != 0;
   k->tc_prof = num("FR_TC_PROF", 0) != 0;
   k->dbg_nostore = num("FR_TC_NOSTORE", 0);
+  k->shard_fold_wait = num("FR_SHARD_FOLD", 0);
 #endif
 }
 
@@ -236,7 +237,6 @@ extern "C" void fr_destroy(fr_engine* e) {
   cudaFree(e->d_peer_ptrs);
   cudaFree(e->d_xchg);
   cudaFree(e->d_step);
-  cudaFree(e->d_done);
   if (e->h_shard_err) cudaFreeHost(e->h_shard_err);
   if (e->h_idx_err) cudaFreeHost(e->h_idx_err);
   if (e->h_watch) cudaFreeHost(e->h_watch);
@@ -529,8 +529,9 @@ static fr_status run_mlp_step(fr_engine* e, fr_stream_s* s, int step, const floa
   return frk_final_dot(e, in, e->d_W[3], act ? e->d_bias[3] : nullptr, d_scores, B, e->dims[3], act, s->stream);
 }
 
-// wait_slot >= 0: the MLP of a table-sharded step -- d_x is the slot's concat buffer, complete once every rank has
-// published the slot's current step.  The tcgen05 path polls the flags inside its first kernel; the others wait first.
+// wait_slot >= 0 (FR_SHARD_FOLD, experiments build): the exchange published without waiting; d_x is the slot's concat
+// buffer, complete once every rank has published the slot's current step -- the tcgen05 path polls the flags inside
+// its first kernel, the others follow a wait kernel.
 static fr_status run_mlp(fr_engine* e, fr_stream_s* s, const float* d_x, int B, float* d_scores, int wait_slot = -1) {
   if (B == 0) return wait_slot >= 0 ? frk_shard_wait(e, wait_slot, s->stream) : FR_OK;
   FrPeerWait pw = {nullptr, nullptr, 0, nullptr};
@@ -906,7 +907,11 @@ extern "C" fr_status fr_set_option(fr_engine* e, int option, int value) {
     case FR_OPT_CHECK_INDICES: e->check_indices = value != 0; break;
     case FR_OPT_FUSE_LOOKUP: e->fuse_lookup = value != 0; break;
     case FR_OPT_TILE_HINT: e->tile_hint = value; break;
-    case FR_OPT_F16_OPERANDS: e->f16_mode = value; e->f16_dirty = true; break;
+    case FR_OPT_F16_OPERANDS:
+      e->f16_mode = value;
+      e->f16_dirty = true;
+      if (value == FR_F16_OFF) e->tc_f16 = false;
+      break;
   }
   return FR_OK;
 }
@@ -1036,8 +1041,6 @@ extern "C" fr_status fr_shard_init(fr_engine* e, int rank, int world, const int*
   FR_CUDA(e, cudaMemsetAsync(e->d_xchg, 0, bytes, e->default_stream->stream));
   FR_CUDA(e, cudaMalloc(&e->d_step, sizeof(int) * e->n_slots));
   FR_CUDA(e, cudaMemsetAsync(e->d_step, 0, sizeof(int) * e->n_slots, e->default_stream->stream));
-  FR_CUDA(e, cudaMalloc(&e->d_done, sizeof(int) * e->n_slots));
-  FR_CUDA(e, cudaMemsetAsync(e->d_done, 0, sizeof(int) * e->n_slots, e->default_stream->stream));
   FR_CUDA(e, cudaHostAlloc(&e->h_shard_err, sizeof(int), cudaHostAllocMapped));
   *e->h_shard_err = 0;
   FR_CUDA(e, cudaStreamSynchronize(e->default_stream->stream));
@@ -1125,7 +1128,7 @@ extern "C" fr_status fr_shard_gather_push(fr_engine* e, const int32_t* idx, int 
   if (B_global == 0) return FR_OK;
   const int T = (int)e->tables.size();
   return frk_shard_exchange(e, e->d_chunks, d_idx, T, d_idx + (size_t)e->rank * (B_global / e->world) * T, T, B_global,
-                            s->slot, 0, s->stream);
+                            s->slot, 0, false, s->stream);   // (the host barriers the ranks before fr_shard_mlp)
 }
 
 extern "C" fr_status fr_shard_mlp(fr_engine* e, int B_global, float* scores_local, fr_stream s) {
@@ -1169,11 +1172,12 @@ static fr_status shard_infer_enqueue(fr_engine* e, fr_stream_s* s, const int32_t
   if (st != FR_OK) return st;
   const int T = (int)e->tables.size();
   const int Bl = B_global / e->world;
+  const bool fold = e->knobs.shard_fold_wait != 0;
   if ((st = frk_shard_exchange(e, e->d_chunks, d_idx, T, d_idx + (size_t)e->rank * Bl * T, T, B_global, s->slot, parity,
-                               s->stream)) != FR_OK) return st;
+                               !fold, s->stream)) != FR_OK) return st;
   float* d_scores = score_target(e, s, scores, Bl);
   const float* x = e->d_xchg + fr_xchg_concat_off(e, s->slot, parity);
-  if ((st = run_mlp(e, s, x, Bl, d_scores, s->slot)) != FR_OK) return st;
+  if ((st = run_mlp(e, s, x, Bl, d_scores, fold ? s->slot : -1)) != FR_OK) return st;
   return emit_scores(e, s, scores, Bl, d_scores);
 }
 
@@ -1232,12 +1236,13 @@ static fr_status shard_infer_sliced_enqueue(fr_engine* e, fr_stream_s* s, const 
   }
   const FrChunk* chunks = frk_sliced_chunks(e);
   if (!chunks) return FR_ERR_CUDA;   // (message left by the failing upload)
+  const bool fold = e->knobs.shard_fold_wait != 0;
   fr_status st = frk_shard_exchange(e, chunks, d_o, (int)e->owned_tables.size(), d_r, (int)e->repl_tables.size(), B_global,
-                                    s->slot, parity, s->stream);
+                                    s->slot, parity, !fold, s->stream);
   if (st != FR_OK) return st;
   float* d_scores = score_target(e, s, scores, Bl);
   const float* x = e->d_xchg + fr_xchg_concat_off(e, s->slot, parity);
-  if ((st = run_mlp(e, s, x, Bl, d_scores, s->slot)) != FR_OK) return st;
+  if ((st = run_mlp(e, s, x, Bl, d_scores, fold ? s->slot : -1)) != FR_OK) return st;
   return emit_scores(e, s, scores, Bl, d_scores);
 }
 

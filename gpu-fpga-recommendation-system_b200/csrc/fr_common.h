@@ -97,6 +97,12 @@ struct FrKnobs {
   bool a_lsu = false;             // FR_TC_ALSU: A operand through cp.async instead of TMA
   bool chain = false;             // FR_CHAIN: the whole MLP as one persistent launch
   bool chain_prof = false;        // FR_CHAIN_PROF: phase timeline of the chain kernel's CTA 0
+  // FR_SHARD_FOLD=1: the first MLP kernel of a sharded step polls the peers' flags itself instead of following a
+  // 1-warp wait kernel.  Off, and not offered in release builds: a persistent tcgen05 grid that spins holds its SMs
+  // (shared memory), so with several worker streams in flight two ranks that happen to start different workers'
+  // layer-1 kernels first wait for each other's exchange kernels behind launches that cannot get an SM -- measured:
+  // 15.7 instead of 13.x us per step at two ranks (small model), time-outs on the large model (148-CTA grids).
+  int shard_fold_wait = 0;
   int dbg_nostore = 0;            // FR_TC_NOSTORE: storing epilogues skip their stores (timing experiments; results are garbage)
   bool tc_prof = false;           // FR_TC_PROF: cycle counters of the per-layer kernel's pipelines (tools/tc_prof.py)
 };
@@ -147,7 +153,6 @@ struct fr_engine {
   int n_slots = 0;               // in-flight sharded steps (one per worker stream)
   int next_slot = 0;             // slot handed to the next stream created
   int* d_step = nullptr;         // [n_slots] device-side step counters (the flag kernel increments its slot's)
-  int* d_done = nullptr;         // [n_slots] blocks of the running exchange kernel that have finished their stores
   std::vector<FrPeer> peers;     // [world]
   float** d_peer_ptrs = nullptr; // device copy of peers[].concat
   int* d_owned_ids = nullptr;    // concat pieces this rank produces for every item
@@ -179,7 +184,9 @@ fr_status fr_fail(const fr_engine* e, fr_status code, const char* fmt, ...);
 // fr_infer with the CUDA-graph cache bypassed on request (one-shot buffer / batch-size combinations)
 fr_status fr_infer_opts(fr_engine* e, const int32_t* idx, int B, float* scores, fr_stream s, bool no_graph);
 // the tcgen05 path runs on fp16 operands (FR_TC_F16=1 and the engine's precision is the tensor-core one)
-inline bool fr_tc_f16(const fr_engine* e) { return e->tc_f16 && e->precision == FR_PREC_TF32 && e->world == 1; }
+inline bool fr_tc_f16(const fr_engine* e) {
+  return e->tc_f16 && e->f16_mode == FR_F16_GUARDED && e->precision == FR_PREC_TF32 && e->world == 1;
+}
 #define FR_CUDA(e, call)                                                                          \
   do {                                                                                            \
     cudaError_t err__ = (call);                                                                   \
@@ -208,12 +215,13 @@ fr_status frk_to_f16(fr_engine* e, const float* src, void* dst, int64_t n, cudaS
 fr_status frk_round_tf32(fr_engine* e, const float* src, float* dst, int64_t n, cudaStream_t st);
 // copy `bytes` (a multiple of 16) of indices from a mapped page-locked host buffer into device memory with SM loads
 fr_status frk_stage_idx(fr_engine* e, const void* mapped_src, int32_t* d_dst, size_t bytes, cudaStream_t st);
-// The exchange of a table-sharded step in one launch: this rank's owned pieces of every item of the global batch are
-// stored into the concat buffer (slot, parity) of the rank that owns the item, the replicated pieces of its own items
-// into its own, and the last block publishes the step to every peer.  idx_owned [B_global][T_owned], idx_repl
-// [B_global / world][T_repl] (row 0 = this rank's first item); chunks[].table names the column in those blocks.
+// The exchange of a table-sharded step: this rank's owned pieces of every item of the global batch are stored into
+// the concat buffer (slot, parity) of the rank that owns the item, the replicated pieces of its own items into its
+// own, then a one-warp kernel publishes the step to every peer and (wait = true) waits for theirs.  idx_owned
+// [B_global][T_owned], idx_repl [B_global / world][T_repl] (row 0 = this rank's first item); chunks[].table names the
+// column in those blocks.
 fr_status frk_shard_exchange(fr_engine* e, const FrChunk* chunks, const int32_t* d_idx_owned, int T_owned,
-                             const int32_t* d_idx_repl, int T_repl, int B_global, int slot, int parity, cudaStream_t st);
+                             const int32_t* d_idx_repl, int T_repl, int B_global, int slot, int parity, bool wait, cudaStream_t st);
 const FrChunk* frk_sliced_chunks(fr_engine* e);   // descriptors whose `table` is the column of a column-sliced block
 void fr_shard_table_lists(fr_engine* e);   // fills owned_tables / repl_tables from owner[] (idempotent)
 // wait (on the device) until every rank has published the slot's current step; the tcgen05 path does this inside

@@ -228,8 +228,12 @@ void launch_gather(const fr_engine* e, const int* d_ids, int n_chunks, const int
   }
   const int C = e->D / 4;
   const int n_items = b_end - b_begin;
+  // pieces along x: rounded up to a multiple of 32 (at most 128), or -- a rank's share of a sharded model can be a
+  // handful of pieces -- to 8 / 16, so that a warp covers several items instead of idling most of its lanes
   int bx = (n_chunks + 31) / 32 * 32;
   if (bx > 128) bx = 128;
+  if (n_chunks <= 8) bx = 8;
+  else if (n_chunks <= 16) bx = 16;
   const int by = 256 / bx;
   dim3 block(bx, by);
   dim3 grid((n_chunks + bx - 1) / bx, (n_items + by * kItems - 1) / (by * kItems));
@@ -464,92 +468,46 @@ void fr_shard_table_lists(fr_engine* e) {
   }
 }
 
-// ---- the exchange of a table-sharded step in ONE launch ------------------------------------------
-// Blocks [0, g1): this rank's OWNED pieces for every item of the global batch, stored straight into
-// the concat buffer of the rank that owns the item (128-bit NVLink peer stores: lookup and all-to-all
-// are one kernel).  Blocks [g1, g1 + g2): the REPLICATED (on-chip class) pieces for this rank's own
-// items.  The block that finishes last (a device-wide counter, the threadfence-reduction pattern)
-// bumps the slot's step counter and publishes "rank r has pushed step n of this slot" into every
-// peer's flag block (st.release.sys).  Nobody waits here: the first MLP kernel of the step polls the
-// flags right before its first load of the concat buffer (tc_linear_kernel, TcParams::wait_*), so its
-// set-up and the other workers' kernels run while the peers' rows are still in flight; the FP32 path
-// waits in shard_wait_kernel.  The step number lives in device memory, so the launch has no per-step
-// argument and the whole step replays as a CUDA graph.
-//
-// Index blocks: idx_owned [B_global][T_owned] over all items, idx_repl [per][T_repl] over this rank's
-// items (for full rows both point into the same [B_global][T] block); `chunks[].table` is the column.
+// ---- the exchange of a table-sharded step ---------------------------------------------------------
+// 1. push: gather_concat_kernel<_, PUSH = true> looks up this rank's OWNED pieces for every item of the global batch
+//    and stores them straight into the concat buffer of the rank that owns the item (128-bit NVLink peer stores:
+//    lookup and all-to-all are one kernel);
+// 2. the REPLICATED (on-chip class) pieces of this rank's own items, gathered locally into its own buffer;
+// 3. shard_signal_wait_kernel (one warp): the kernel boundary has completed the pushes; a system fence, then lane t
+//    publishes "rank r has pushed step n of this slot" into rank t's flag block (st.release.sys) and polls this rank's
+//    own flag of rank t (ld.acquire.sys) until it shows step n.  The step number lives in device memory (bumped
+//    here), so no launch has a per-step argument and the whole step replays as a CUDA graph.
+// A waiting warp costs nothing, which matters: with a dozen worker streams in flight some step is always waiting.
+// (Folding publish into the push kernel's last block -- every block then needs its own system fence -- and the wait
+// into the first MLP kernel -- a spinning tcgen05 grid holds its SMs -- were both measured slower: 15.2-15.7 against
+// 12-13 us per step at two ranks; the second can even deadlock two ranks that start different workers first.)
 namespace {
-template <bool ROUND, int DT>
-__global__ void __launch_bounds__(256)
-shard_exchange_kernel(const FrChunk* __restrict__ chunks, const int* __restrict__ owned_ids, int n_owned,
-                      const int* __restrict__ repl_ids, int n_repl, const int32_t* __restrict__ idx_owned, int T_owned,
-                      const int32_t* __restrict__ idx_repl, int T_repl, int B_global, int per, int rank, int world,
-                      float4* const* __restrict__ peer_out, int C, long long peer_off4, int g1, int gx1, int gx2,
-                      float* const* __restrict__ peer_base, long long flags_off_floats, int* step_counter,
-                      int* done_counter, int* __restrict__ idx_err) {
-  const int part = (int)blockIdx.x < g1 ? 0 : 1;
-  const int lb = part ? (int)blockIdx.x - g1 : (int)blockIdx.x;
-  const int gx = part ? gx2 : gx1;
-  const int n_chunks = part ? n_repl : n_owned;
-  const int* ids = part ? repl_ids : owned_ids;
-  const int32_t* idx = part ? idx_repl : idx_owned;
-  const int T = part ? T_repl : T_owned;
-  const int n_items = part ? per : B_global;          // rows of `idx`
-  const int item0 = part ? rank * per : 0;            // global item of idx row 0
-  const int ci = (lb % gx) * 32 + threadIdx.x;
-  const int i0 = ((lb / gx) * 8 + threadIdx.y) * kItems;
-  if (ci < n_chunks && i0 < n_items) {
-    const int c = ids[ci];
-    const FrChunk ch = chunks[c];
-    int64_t row[kItems];
-#pragma unroll
-    for (int i = 0; i < kItems; i++) row[i] = (i0 + i < n_items) ? (int64_t)__ldg(idx + (size_t)(i0 + i) * T + ch.table) : 0;
-    if (idx_err) {
-#pragma unroll
-      for (int i = 0; i < kItems; i++) row[i] = checked_row(row[i], ch, item0 + i0 + i, idx_err);
-    }
-    float4 v[kItems];
-#pragma unroll
-    for (int i = 0; i < kItems; i++)
-      v[i] = DT == FR_TABLE_F32 ? ld_row16(ch.base + row[i] * ch.stride4 + ch.col4)
-                                : ld_row8<DT == FR_TABLE_F32 ? FR_TABLE_F16 : DT>(ch.base, row[i] * ch.stride4 + ch.col4);
-#pragma unroll
-    for (int i = 0; i < kItems; i++) {
-      if (i0 + i >= n_items) break;
-      const int b = item0 + i0 + i;
-      float4 o = v[i];
-      if (ROUND) {
-        o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
-      }
-      const int r = part ? rank : b / per;
-      peer_out[r][peer_off4 + (size_t)(b - r * per) * C + c] = o;
-    }
-  }
-  // ---- last block out publishes ----
-  __shared__ int s_last;
-  __syncthreads();                             // the block's stores are ordered before thread 0's fence (CTA barrier),
-  if (threadIdx.x == 0 && threadIdx.y == 0) {  // and the fence is cumulative: one system fence per block, not 256
-    __threadfence_system();
-    s_last = (atomicAdd(done_counter, 1) == (int)gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!s_last || threadIdx.y != 0) return;
-  __threadfence_system();                      // every other block's stores, ordered before their atomicAdd
+__global__ void shard_signal_wait_kernel(float* const* __restrict__ peer_base, long long flags_off_floats, int rank,
+                                         int world, int* step_counter, int* err, long long timeout_cycles, int do_wait) {
   const int t = threadIdx.x;
-  const int step = *reinterpret_cast<volatile int*>(step_counter) + 1;   // launches of one slot are stream-ordered
+  const int step = *reinterpret_cast<volatile int*>(step_counter) + 1;   // kernels of one slot are stream-ordered
   __syncwarp();
-  if (t == 0) {
-    *done_counter = 0;
-    *step_counter = step;
-  }
+  __threadfence_system();   // the push kernel(s) before this one are complete; make their stores visible system-wide
   if (t < world) {
     int* f = reinterpret_cast<int*>(peer_base[t] + flags_off_floats) + rank;
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f), "r"(step) : "memory");
   }
+  if (t == 0) *step_counter = step;
+  if (t < world && do_wait) {
+    const int* mine = reinterpret_cast<const int*>(peer_base[rank] + flags_off_floats) + t;
+    const long long t0 = clock64();
+    int v;
+    do {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if (v < step && clock64() - t0 > timeout_cycles) {
+        *reinterpret_cast<volatile int*>(err) = 1;   // reported by fr_sync and by the next sharded call
+        break;
+      }
+    } while (v < step);
+  }
 }
 
-// Wait until every rank has published the slot's current step (FP32 path and the two-phase API; the tcgen05 path
-// waits inside its first kernel).  One warp, lane t watches rank t.
+// Wait only (the first MLP kernel's own poll, FR_SHARD_FOLD, has nothing to follow in the FP32 path).
 __global__ void shard_wait_kernel(const int* __restrict__ flags, int world, const int* step_counter, int* err,
                                   long long timeout_cycles) {
   const int t = threadIdx.x;
@@ -560,7 +518,7 @@ __global__ void shard_wait_kernel(const int* __restrict__ flags, int world, cons
   do {
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + t) : "memory");
     if (v < step && clock64() - t0 > timeout_cycles) {
-      *reinterpret_cast<volatile int*>(err) = 1;   // reported by fr_sync and by the next sharded call
+      *reinterpret_cast<volatile int*>(err) = 1;
       break;
     }
   } while (v < step);
@@ -575,28 +533,31 @@ static fr_status ensure_shard_lists(fr_engine* e) {
 }
 
 fr_status frk_shard_exchange(fr_engine* e, const FrChunk* chunks, const int32_t* d_idx_owned, int T_owned,
-                             const int32_t* d_idx_repl, int T_repl, int B_global, int slot, int parity, cudaStream_t st) {
+                             const int32_t* d_idx_repl, int T_repl, int B_global, int slot, int parity, bool wait, cudaStream_t st) {
   fr_status s = ensure_shard_lists(e);
   if (s != FR_OK) return s;
   const int per = B_global / e->world;
-  const int gx1 = (e->n_owned + 31) / 32, gy1 = e->n_owned ? (B_global + 8 * kItems - 1) / (8 * kItems) : 0;
-  const int gx2 = (e->n_repl + 31) / 32, gy2 = e->n_repl ? (per + 8 * kItems - 1) / (8 * kItems) : 0;
-  const int g1 = gx1 * gy1, g2 = gx2 * gy2;
-  int* d_idx_err = nullptr;
-  if (e->check_indices && e->h_idx_err) FR_CUDA(e, cudaHostGetDevicePointer(&d_idx_err, e->h_idx_err, 0));
   const bool round = (e->precision == FR_PREC_TF32);
-  auto kern = round ? (e->table_dtype == FR_TABLE_F32   ? shard_exchange_kernel<true, FR_TABLE_F32>
-                       : e->table_dtype == FR_TABLE_F16 ? shard_exchange_kernel<true, FR_TABLE_F16>
-                                                        : shard_exchange_kernel<true, FR_TABLE_BF16>)
-                    : (e->table_dtype == FR_TABLE_F32   ? shard_exchange_kernel<false, FR_TABLE_F32>
-                       : e->table_dtype == FR_TABLE_F16 ? shard_exchange_kernel<false, FR_TABLE_F16>
-                                                        : shard_exchange_kernel<false, FR_TABLE_BF16>);
-  // a rank that holds no table at all still publishes its (empty) step: one idle block
-  kern<<<g1 + g2 > 0 ? g1 + g2 : 1, dim3(32, 8), 0, st>>>(
-      chunks, e->d_owned_ids, e->n_owned, e->d_repl_ids, e->n_repl, d_idx_owned, T_owned, d_idx_repl, T_repl, B_global, per,
-      e->rank, e->world, reinterpret_cast<float4* const*>(e->d_peer_ptrs), e->D / 4,
-      (long long)(fr_xchg_concat_off(e, slot, parity) / 4), g1, gx1 ? gx1 : 1, gx2 ? gx2 : 1, e->d_peer_ptrs,
-      (long long)fr_xchg_flags_off(e, slot), e->d_step + slot, e->d_done + slot, d_idx_err);
+  // concat buffer `parity` of slot `slot` in every rank's exchange region (same layout on all ranks)
+  const long long off4 = (long long)(fr_xchg_concat_off(e, slot, parity) / 4);
+  float4* const* peers = reinterpret_cast<float4* const*>(e->d_peer_ptrs);
+  if (e->n_owned) {
+    if (round) launch_gather<true, true>(e, e->d_owned_ids, e->n_owned, d_idx_owned, 0, B_global, nullptr, peers, per, st, off4, chunks, T_owned);
+    else launch_gather<false, true>(e, e->d_owned_ids, e->n_owned, d_idx_owned, 0, B_global, nullptr, peers, per, st, off4, chunks, T_owned);
+    e->launches++;
+  }
+  if (e->n_repl) {
+    // local items only, written into this rank's own buffer; the index block's row 0 is global item rank * per
+    float4* own = reinterpret_cast<float4*>(e->d_xchg) + off4;
+    if (round) launch_gather<true, false>(e, e->d_repl_ids, e->n_repl, d_idx_repl, 0, per, own, nullptr, 1, st, 0, chunks, T_repl);
+    else launch_gather<false, false>(e, e->d_repl_ids, e->n_repl, d_idx_repl, 0, per, own, nullptr, 1, st, 0, chunks, T_repl);
+    e->launches++;
+  }
+  FR_CUDA(e, cudaGetLastError());
+  int* d_err = nullptr;
+  FR_CUDA(e, cudaHostGetDevicePointer(&d_err, e->h_shard_err, 0));
+  shard_signal_wait_kernel<<<1, 32, 0, st>>>(e->d_peer_ptrs, (long long)fr_xchg_flags_off(e, slot), e->rank, e->world,
+                                             e->d_step + slot, d_err, kShardTimeoutCycles, wait ? 1 : 0);
   e->launches++;
   FR_CUDA(e, cudaGetLastError());
   return FR_OK;
