@@ -271,7 +271,7 @@ def run_ours(args):
     sharded = world > 1 and args.shard == "tables"
     Bg = B * world if sharded else B
     extras = world == 1 and not args.quick          # the per-kernel / large-batch / latency / stress / fp16 legs
-    mb = max(Bg, G * B if not sharded else 0, args.gather_batch if extras else 0)
+    mb = max(Bg, args.gather_batch if extras else 0)
     eng = fleetrec.Engine(cat, device=local, precision=prec, max_batch=(mb + world - 1) // world * world)
     eng.set_option(fleetrec.FR_OPT_TILE_HINT, fleetrec.FR_HINT_THROUGHPUT)   # `--streams` batches in flight
     if sharded:
@@ -314,6 +314,18 @@ def run_ours(args):
         sl_bufs = [packed(t) for t in idx_host]          # keep the buffers alive
         sl_host = [views for _, views in sl_bufs]
         sl_dev = [tuple(a.cuda(non_blocking=True) for a in pair) for pair in sl_host]
+
+        def packed_group(ts):   # G consecutive steps for fr_shard_infer_sliced_many: [owned blocks of all G | replicated blocks]
+            o = np.concatenate([shard.slice_indices(t.numpy(), owner, world, rank)[0].reshape(-1) for t in ts])
+            r = np.concatenate([shard.slice_indices(t.numpy(), owner, world, rank)[1].reshape(-1) for t in ts])
+            n_o = (o.size + 3) // 4 * 4
+            buf = torch.zeros(n_o + r.size, dtype=torch.int32).pin_memory()
+            buf[:o.size] = torch.from_numpy(o)
+            buf[n_o:] = torch.from_numpy(r)
+            return buf, (buf[:o.size], buf[n_o:])
+        slg_bufs = [packed_group(idx_host[g * G:(g + 1) * G]) for g in range(pool // G)]
+        slg_host = [views for _, views in slg_bufs]
+        slg_sc = [torch.empty(G * B, dtype=torch.float32).pin_memory() for _ in range(args.streams)]
     sc_dev = [torch.empty(B, dtype=torch.float32, device="cuda") for _ in range(args.streams)]
     sc_host = [torch.empty(B, dtype=torch.float32).pin_memory() for _ in range(args.streams)]
     torch.cuda.synchronize()
@@ -399,7 +411,8 @@ def run_ours(args):
     p_sc_dev, p_sc_host = [t.data_ptr() for t in sc_dev], [t.data_ptr() for t in sc_host]
     if sharded:
         p_sl_dev = [(a.data_ptr(), r.data_ptr()) for a, r in sl_dev]
-        p_sl_host = [(a.data_ptr(), r.data_ptr()) for a, r in sl_host]
+        p_slg_host = [(a.data_ptr(), r.data_ptr() if r.numel() else None) for a, r in slg_host]
+        p_slg_sc = [t.data_ptr() for t in slg_sc]
     else:
         p_grp_host, p_grp_sc = [t.data_ptr() for t in grp_host], [t.data_ptr() for t in grp_sc]
 
@@ -413,7 +426,8 @@ def run_ours(args):
     def batch_e2e(j):
         w = j % S
         if sharded:
-            eng.shard_infer_sliced(p_sl_host[j % pool][0], p_sl_host[j % pool][1], Bg, p_sc_host[w], workers[w])
+            g = j % len(p_slg_host)
+            eng.shard_infer_sliced_many(p_slg_host[g][0], p_slg_host[g][1], G, Bg, p_slg_sc[w], workers[w])
         else:
             eng.infer_many_async(p_grp_host[j % len(p_grp_host)], p_grp_sc[w], G, B, workers[w])
 
@@ -421,7 +435,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     ms_dev, launches = timed(batch_dev, 1, args.steps, args.warmup, "value")
-    ms_e2e, _ = timed(batch_e2e, 1 if sharded else G, args.steps, args.warmup, "e2e")
+    ms_e2e, _ = timed(batch_e2e, G, args.steps, args.warmup, "e2e")
     clocks = sampler.stop() if rank == 0 else None
 
     items_per_step = world * R * S * B
@@ -448,7 +462,7 @@ def run_ours(args):
             "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": B * 4 * world * R * S,
                     "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_rank_max": h2d_rank_max,
-                    "call": "fr_shard_infer_sliced per batch" if sharded else f"fr_infer_many, {G} batches per call"},
+                    "call": f"fr_shard_infer_sliced_many, {G} steps per call" if sharded else f"fr_infer_many, {G} batches per call"},
             "us_per_batch": ms_batch * 1e3, "gpu_launches": int(launches), "host_enqueue_us_per_batch": host_us,
             "graph_misses_in_timed_region": graph_misses, "parity_gate_max_rel_err": gate_err, "clocks": clocks}
 

@@ -135,6 +135,8 @@ static fr_status alloc_stream(fr_engine* e, fr_stream_s** out) {
   FR_CUDA(e, cudaMalloc(&s->d_x, mb * e->D * sizeof(float)));
   for (int k = 0; k < 3; k++) FR_CUDA(e, cudaMalloc(&s->d_h[k], mb * e->dims[k + 1] * sizeof(float)));
   FR_CUDA(e, cudaMalloc(&s->d_scores, mb * sizeof(float)));
+  s->idx_cap = mb * e->tables.size();
+  s->scores_cap = mb;
   FR_CUDA(e, cudaEventCreate(&s->ev[0]));
   FR_CUDA(e, cudaEventCreate(&s->ev[1]));
   s->slot = e->next_slot++;   // creation order: identical on every rank of a sharded job
@@ -730,6 +732,31 @@ extern "C" fr_status fr_graph_stats(const fr_engine* e, int64_t* replayed, int64
   return FR_OK;
 }
 
+// The *_many calls stage the indices of several batches with one copy: grow the worker's index / score staging buffers
+// to what the call needs (the activation buffers stay one batch deep).  Growing synchronises the worker and drops its
+// graphs, which reference the old buffers; it happens once per worker.
+static fr_status ensure_group_capacity(fr_engine* e, fr_stream_s* s, size_t idx_ints, size_t n_scores) {
+  if (idx_ints <= s->idx_cap && n_scores <= s->scores_cap) return FR_OK;
+  FR_CUDA(e, cudaStreamSynchronize(s->stream));
+  for (fr_stream_s::Graph& g : s->graphs) drop_graph(g);
+  s->graphs.clear();
+  if (idx_ints > s->idx_cap) {
+    FR_CUDA(e, cudaFree(s->d_idx));
+    s->d_idx = nullptr;
+    s->idx_cap = 0;
+    FR_CUDA(e, cudaMalloc(&s->d_idx, idx_ints * sizeof(int32_t)));
+    s->idx_cap = idx_ints;
+  }
+  if (n_scores > s->scores_cap) {
+    FR_CUDA(e, cudaFree(s->d_scores));
+    s->d_scores = nullptr;
+    s->scores_cap = 0;
+    FR_CUDA(e, cudaMalloc(&s->d_scores, n_scores * sizeof(float)));
+    s->scores_cap = n_scores;
+  }
+  return FR_OK;
+}
+
 fr_status fr_infer_opts(fr_engine* e, const int32_t* idx, int B, float* scores, fr_stream s, bool no_graph) {
   fr_status st = prep(e, &s, B, true, true);
   if (st != FR_OK) return st;
@@ -748,13 +775,13 @@ extern "C" fr_status fr_infer(fr_engine* e, const int32_t* idx, int B, float* sc
 // travel in one copy each way (a copy costs the engine ~4 us on top of its bytes, whatever its size), the
 // batches then run back to back on the worker's stream, each through the same kernels as fr_infer.
 extern "C" fr_status fr_infer_many(fr_engine* e, const int32_t* idx, int n, int B, float* scores, fr_stream s) {
-  if (n < 0 || B < 0 || (int64_t)n * B > INT_MAX) return fr_fail(e, FR_ERR_INVALID, "fr_infer_many: n=%d B=%d", n, B);
-  fr_status st = prep(e, &s, n * B, true, true);   // the worker's index / score buffers hold max_batch items
+  if (n < 0 || n > 4095 || B < 0 || (int64_t)n * B > INT_MAX) return fr_fail(e, FR_ERR_INVALID, "fr_infer_many: n=%d B=%d", n, B);
+  fr_status st = prep(e, &s, B, true, true);
   if (st != FR_OK) return st;
   if (n == 0 || B == 0) return FR_OK;
   if (!idx || !scores) return fr_fail(e, FR_ERR_INVALID, "null idx/scores");
   if (e->world > 1) return fr_fail(e, FR_ERR_STATE, "engine is table-sharded over %d ranks: use fr_shard_infer", e->world);
-  if (n > 4095) return fr_fail(e, FR_ERR_INVALID, "fr_infer_many: at most 4095 batches per call");
+  if ((st = ensure_group_capacity(e, s, (size_t)n * B * e->tables.size(), (size_t)n * B)) != FR_OK) return st;
   return run_or_replay(e, s, idx, scores, B, FR_GV_MANY | (n << 4), 1, 0, [&](int) {
     s->f16 = fr_tc_f16(e);
     const int32_t* d_idx = nullptr;
@@ -1212,16 +1239,17 @@ extern "C" fr_status fr_shard_tables(fr_engine* e, int which, int32_t* ids, int*
 // idx_repl [B_global / world][n_repl] for the replicated tables of this rank's own items.  A rank then uploads
 // B_global * n_owned + B_local * n_repl indices per step instead of B_global * T.
 static fr_status shard_infer_sliced_enqueue(fr_engine* e, fr_stream_s* s, const int32_t* idx_owned, const int32_t* idx_repl,
-                                            int B_global, float* scores, int parity) {
+                                            int n, int B_global, float* scores, int parity0) {
   s->f16 = false;
   const int Bl = B_global / e->world;
-  const size_t n_o = (size_t)B_global * e->owned_tables.size(), n_r = (size_t)Bl * e->repl_tables.size();
+  const size_t o1 = (size_t)B_global * e->owned_tables.size(), r1 = (size_t)Bl * e->repl_tables.size();   // ints per batch
+  const size_t n_o = o1 * n, n_r = r1 * n;
   const int32_t* d_o = idx_owned;
   const int32_t* d_r = idx_repl;
-  int32_t* stage_r = s->d_idx + (n_o + 3) / 4 * 4;   // both blocks fit: n_owned + n_repl <= T
+  int32_t* stage_r = s->d_idx + (n_o + 3) / 4 * 4;
   if (n_o && n_r && idx_repl == idx_owned + (n_o + 3) / 4 * 4 && !is_device_ptr(idx_owned) && same_allocation(idx_owned, idx_repl)) {
     // one host buffer, the replicated block right behind the owned one (16-byte aligned): ONE copy -- every copy
-    // costs the engine ~5 us on top of its bytes
+    // costs the engine ~4 us on top of its bytes
     FR_CUDA(e, cudaMemcpyAsync(s->d_idx, idx_owned, ((n_o + 3) / 4 * 4 + n_r) * sizeof(int32_t), cudaMemcpyHostToDevice,
                                s->stream));
     d_o = s->d_idx;
@@ -1237,30 +1265,46 @@ static fr_status shard_infer_sliced_enqueue(fr_engine* e, fr_stream_s* s, const 
   const FrChunk* chunks = frk_sliced_chunks(e);
   if (!chunks) return FR_ERR_CUDA;   // (message left by the failing upload)
   const bool fold = e->knobs.shard_fold_wait != 0;
-  fr_status st = frk_shard_exchange(e, chunks, d_o, (int)e->owned_tables.size(), d_r, (int)e->repl_tables.size(), B_global,
-                                    s->slot, parity, !fold, s->stream);
-  if (st != FR_OK) return st;
-  float* d_scores = score_target(e, s, scores, Bl);
-  const float* x = e->d_xchg + fr_xchg_concat_off(e, s->slot, parity);
-  if ((st = run_mlp(e, s, x, Bl, d_scores, fold ? s->slot : -1)) != FR_OK) return st;
-  return emit_scores(e, s, scores, Bl, d_scores);
+  float* d_scores = score_target(e, s, scores, n * Bl);
+  for (int i = 0; i < n; i++) {   // consecutive steps of this worker's slot: the exchange buffers alternate
+    const int parity = (parity0 + i) & 1;
+    fr_status st = frk_shard_exchange(e, chunks, d_o + i * o1, (int)e->owned_tables.size(), d_r + i * r1,
+                                      (int)e->repl_tables.size(), B_global, s->slot, parity, !fold, s->stream);
+    if (st != FR_OK) return st;
+    const float* x = e->d_xchg + fr_xchg_concat_off(e, s->slot, parity);
+    if ((st = run_mlp(e, s, x, Bl, d_scores + (size_t)i * Bl, fold ? s->slot : -1)) != FR_OK) return st;
+  }
+  return emit_scores(e, s, scores, n * Bl, d_scores);
 }
 
-extern "C" fr_status fr_shard_infer_sliced(fr_engine* e, const int32_t* idx_owned, const int32_t* idx_repl, int B_global,
-                                           float* scores_local, fr_stream s) {
+// n consecutive sharded steps in ONE call on one worker: idx_owned [n][B_global][n_owned], idx_repl [n][B_global / world]
+// [n_repl], scores_local [n][B_global / world], all contiguous.  Host blocks travel in one copy each way (two when
+// idx_repl does not start right behind idx_owned in the same allocation).
+extern "C" fr_status fr_shard_infer_sliced_many(fr_engine* e, const int32_t* idx_owned, const int32_t* idx_repl, int n,
+                                                int B_global, float* scores_local, fr_stream s) {
+  if (n < 0 || n > 4095) return fr_fail(e, FR_ERR_INVALID, "fr_shard_infer_sliced_many: n=%d", n);
   fr_status st = prep(e, &s, B_global, true, true);
   if (st != FR_OK) return st;
   if ((st = shard_check(e, s, B_global)) != FR_OK) return st;
-  if (B_global == 0) return FR_OK;
+  if (B_global == 0 || n == 0) return FR_OK;
   fr_shard_table_lists(e);
   if (!scores_local || (!idx_owned && !e->owned_tables.empty()) || (!idx_repl && !e->repl_tables.empty()))
     return fr_fail(e, FR_ERR_INVALID, "null idx/scores");
   if (*e->h_shard_err) return fr_fail(e, FR_ERR_STATE, "a previous sharded step timed out waiting for a peer rank");
-  const int parity = (++s->shard_step) & 1;
+  const int Bl = B_global / e->world;
+  const size_t ints = ((size_t)n * B_global * e->owned_tables.size() + 3) / 4 * 4 + (size_t)n * Bl * e->repl_tables.size();
+  if ((st = ensure_group_capacity(e, s, ints, (size_t)n * Bl)) != FR_OK) return st;
+  const int parity0 = (s->shard_step + 1) & 1;   // the first step's exchange buffer; the graphs come in pairs by it
+  s->shard_step += n;
   const void* key = idx_owned ? (const void*)idx_owned : (const void*)idx_repl;
-  return run_or_replay(e, s, key, scores_local, B_global, FR_GV_SHARD_SLICED, 2, parity,
-                       [&](int par) { return shard_infer_sliced_enqueue(e, s, idx_owned, idx_repl, B_global, scores_local, par); },
+  return run_or_replay(e, s, key, scores_local, B_global, FR_GV_SHARD_SLICED | (n << 4), 2, parity0,
+                       [&](int par) { return shard_infer_sliced_enqueue(e, s, idx_owned, idx_repl, n, B_global, scores_local, par); },
                        idx_owned ? idx_repl : nullptr);
+}
+
+extern "C" fr_status fr_shard_infer_sliced(fr_engine* e, const int32_t* idx_owned, const int32_t* idx_repl, int B_global,
+                                           float* scores_local, fr_stream s) {
+  return fr_shard_infer_sliced_many(e, idx_owned, idx_repl, 1, B_global, scores_local, s);
 }
 
 

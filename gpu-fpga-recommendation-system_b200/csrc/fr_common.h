@@ -44,7 +44,8 @@ struct FrTable {
 
 struct fr_stream_s {
   cudaStream_t stream = nullptr;
-  int32_t* d_idx = nullptr;   // [max_batch][T]
+  int32_t* d_idx = nullptr;   // [max_batch][T] (grown by the *_many calls: idx_cap ints)
+  size_t idx_cap = 0, scores_cap = 0;   // capacity of d_idx (ints) / d_scores (floats)
   float* d_x = nullptr;       // [max_batch][D]      concat activations
   float* d_x32 = nullptr;     // tc_f16: landing zone of fr_mlp_only's fp32 input before the conversion
   float* d_h[3] = {nullptr, nullptr, nullptr};  // [max_batch][hidden k]

@@ -99,6 +99,7 @@ SIGNATURES = {
     "fr_shard_infer": (_I, [_P, _P, _I, _P, _P]),
     "fr_shard_tables": (_I, [_P, _I, _P, _P]),
     "fr_shard_infer_sliced": (_I, [_P, _P, _P, _I, _P, _P]),
+    "fr_shard_infer_sliced_many": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "fr_shard_read_concat": (_I, [_P, _I, _P, _P]),
     "fr_merge_index": (_I64, [_I64, _I64, _I64]),
     "fr_merge_tables": (_I, [_P, _I, _I, _I]),

@@ -278,6 +278,12 @@ class Engine:
         self._chk(self._L.fr_shard_infer_sliced(self._h, _ptr(idx_owned), _ptr(idx_repl), B_global, _ptr(scores),
                                                 worker._h if worker else None))
 
+    def shard_infer_sliced_many(self, idx_owned, idx_repl, n, B_global, scores, worker=None):
+        """n consecutive sharded steps in one call: idx_owned [n][B_global][owned], idx_repl [n][B_global/world][repl],
+        scores [n][B_global/world]."""
+        self._chk(self._L.fr_shard_infer_sliced_many(self._h, _ptr(idx_owned), _ptr(idx_repl), n, B_global, _ptr(scores),
+                                                     worker._h if worker else None))
+
     def shard_read_concat(self, B_global, worker=None):
         out = np.empty((B_global // self.world, self.model.concat_floats), np.float32)
         self._chk(self._L.fr_shard_read_concat(self._h, B_global, out.ctypes.data, worker._h if worker else None))

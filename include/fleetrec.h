@@ -183,7 +183,7 @@ void* fr_stream_cuda(fr_stream s);
  * combination a worker has seen before is replayed as a CUDA graph: the buffers
  * must stay allocated as what they were (fr_graph_flush forgets them). */
 fr_status fr_infer(fr_engine* e, const int32_t* idx, int B, float* scores, fr_stream s);
-/* n batches of B items in one call on one worker (n * B <= max_batch): idx [n][B][n_tables] and scores [n][B]
+/* n batches of B items (B <= max_batch) in one call on one worker: idx [n][B][n_tables] and scores [n][B]
  * contiguous.  Every batch runs through the same kernels as fr_infer, back to back; host buffers travel in ONE copy
  * each way, which is what the call is for: a copy occupies the copy engine for ~4 us on top of its bytes, so
  * per-batch copies of the reference's staging loop (read() -> cudaMemcpyAsync per batch, cuda_server.c:425-461)
@@ -263,6 +263,11 @@ fr_status fr_shard_tables(fr_engine* e, int which, int32_t* ids, int* n);
 fr_status fr_shard_infer_sliced(fr_engine* e, const int32_t* idx_owned /* [B_global][n_owned] */,
                                 const int32_t* idx_repl /* [B_global / world][n_repl] */, int B_global,
                                 float* scores_local, fr_stream s);
+/* n consecutive sharded steps in one call on one worker: idx_owned [n][B_global][n_owned], idx_repl [n][B_global / world]
+ * [n_repl], scores_local [n][B_global / world], each contiguous; host blocks travel in one copy each way (the same
+ * adjacency rule).  Every rank must call it with the same n.  What fr_infer_many is to fr_infer. */
+fr_status fr_shard_infer_sliced_many(fr_engine* e, const int32_t* idx_owned, const int32_t* idx_repl, int n, int B_global,
+                                     float* scores_local, fr_stream s);
 /* Local concat buffer after the exchange (parity hook), [B_global/world][concat_floats]. */
 fr_status fr_shard_read_concat(fr_engine* e, int B_global, float* concat_local, fr_stream s);
 

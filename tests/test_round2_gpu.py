@@ -147,6 +147,64 @@ def test_sharded_step_every_model(model, world, B):
         e.close()
 
 
+def test_sharded_steps_grouped_equal_single_steps():
+    """fr_shard_infer_sliced_many (n steps, one copy each way) gives, bit for bit, what n fr_shard_infer_sliced calls
+    give, on every rank, from one pinned buffer holding [owned blocks | replicated blocks]; direct, captured, replayed,
+    with an odd n so that consecutive calls start on alternating exchange buffers."""
+    import torch
+    world, n, B = 2, 3, 512
+    per = B // world
+    cat = catalogue.load("small").with_row_cap(3000)
+    dims = cat.layer_dims
+    owner = shard.plan_owners(cat, world, policy="contiguous")
+    tables = oracle.make_tables(cat, "hash", seed=37)
+    W, b = oracle.make_weights(dims, seed=42)
+    engs = []
+    for r in range(world):
+        e = fleetrec.Engine(cat, device=r % _n_gpus(), max_batch=B)
+        e.shard_init(r, world, owner)
+        for t in cat.tables:
+            e.load_table(t.id, tables[t.id])
+        e.load_mlp(W, b)
+        engs.append(e)
+    for e in engs:
+        e.shard_attach_local(engs)
+    idx = [oracle.zipf_indices(cat, B, seed=800 + i) for i in range(n)]
+    exp = np.concatenate([oracle.mlp(oracle.gather(cat, tables, ix), dims, W, b, mode=1) for ix in idx])
+    single = [torch.empty(n * per, dtype=torch.float32).pin_memory() for _ in engs]
+    for i in range(n):
+        for r, e in enumerate(engs):
+            o, p = shard.slice_indices(idx[i], owner, world, r)
+            e.shard_infer_sliced(torch.from_numpy(o).pin_memory().numpy(), torch.from_numpy(p).pin_memory().numpy(), B,
+                                 single[r][i * per:(i + 1) * per].numpy())
+        for e in engs:
+            e.sync()
+    bufs, outs = [], [torch.empty(n * per, dtype=torch.float32).pin_memory() for _ in engs]
+    for r in range(world):
+        o = np.concatenate([shard.slice_indices(ix, owner, world, r)[0].reshape(-1) for ix in idx])
+        p = np.concatenate([shard.slice_indices(ix, owner, world, r)[1].reshape(-1) for ix in idx])
+        n_o = (o.size + 3) // 4 * 4
+        buf = torch.zeros(n_o + p.size, dtype=torch.int32).pin_memory()
+        buf[:o.size] = torch.from_numpy(o)
+        buf[n_o:] = torch.from_numpy(p)
+        bufs.append((buf, buf[:o.size], buf[n_o:]))
+    for rep in range(4):
+        for t in outs:
+            t.zero_()
+        for r, e in enumerate(engs):
+            e.shard_infer_sliced_many(bufs[r][1].numpy(), bufs[r][2].numpy(), n, B, outs[r].numpy())
+        for e in engs:
+            e.sync()
+        for r in range(world):
+            assert_bits_equal(outs[r].numpy(), single[r].numpy())
+    got = np.concatenate([np.concatenate([outs[r][i * per:(i + 1) * per].numpy() for r in range(world)]) for i in range(n)])
+    assert rel_err(got, exp) <= TOL
+    for e in engs:
+        gs = e.graph_stats()
+        assert gs["captured"] >= 1 and gs["replayed"] >= 2, gs
+        e.close()
+
+
 def test_sharded_step_reports_a_missing_peer():
     """A rank whose peer never issues the step gives up after ~2 s: fr_sync and later sharded calls return
     FR_ERR_STATE instead of handing out scores computed on an incomplete concat buffer."""
@@ -224,7 +282,7 @@ def test_graph_cache_steady_state_lru_and_flush():
 def test_infer_many_equals_per_batch_infer(kind):
     """fr_infer_many (n batches, one copy each way) gives, bit for bit, what n fr_infer calls give."""
     import torch
-    cat, tables, W, b, eng = _small_engine(max_batch=4 * 512)
+    cat, tables, W, b, eng = _small_engine(max_batch=512)      # one batch deep: the staging buffers grow on the first call
     w = fleetrec.Worker(eng)
     n, B = 4, 512
     idx = oracle.zipf_indices(cat, n * B, seed=77)
@@ -243,7 +301,7 @@ def test_infer_many_equals_per_batch_infer(kind):
         assert_bits_equal(so.cpu().numpy(), one)
     assert eng.launch_count() - l0 == 3 * n * 4   # lookup + 3 GEMM launches per batch, no extra kernels
     with pytest.raises(fleetrec.FleetRecError):
-        eng.infer_many_async(ti if kind == "device" else ti.numpy(), so if kind == "device" else so.numpy(), 5, B, w)   # > max_batch
+        eng.infer_many_async(ti if kind == "device" else ti.numpy(), so if kind == "device" else so.numpy(), 1, 4 * B + 1, w)   # B > max_batch
     w.close()
     eng.close()
 
