@@ -73,7 +73,8 @@ def ncu_traffic(kernel_substr):
         for i, h in enumerate(hdr):
             if h.startswith("dram__bytes_read.sum") or h.startswith("dram__bytes_write.sum"):
                 cols.append((i, scale.get(h[h.index("[") + 1:-1], 1.0)))
-        vals = [sum(float(r[i]) * k for i, k in cols) for r in rows[1:] if kernel_substr in r[0]]
+        norm = lambda n: n.replace("(int)", "").replace("(bool)", "").replace(" ", "")   # noqa: E731
+        vals = [sum(float(r[i]) * k for i, k in cols) for r in rows[1:] if norm(kernel_substr) in norm(r[0])]
         if vals and len(cols) == 2:
             best = dict(bytes_per_launch=sum(vals) / len(vals), source=os.path.relpath(path, ROOT), launches=len(vals))
     return best
@@ -514,8 +515,8 @@ def run_ours(args):
             kernels.append(k)
     dom = max(kernels, key=lambda k: k["ms"])
     # the committed ncu --set full capture of the same command: which kernel instance is the dominant one
-    ncu_name = {"gather_concat": "gather_concat_kernel", "mlp_layer1": "tc_linear_kernel<256, 5, 0",
-                "mlp_layer2": "tc_linear_kernel<512, 3, 0", "mlp_layer3+out": "tc_linear_kernel<256, 5, 1"}.get(dom["name"])
+    ncu_name = {"gather_concat": "gather_concat_kernel", "mlp_layer1": "tc_pair_kernel<256,3,0,4,2",
+                "mlp_layer2": "tc_pair_kernel<512,4,0,4,1", "mlp_layer3+out": "tc_pair_kernel<256,3,1,4,2"}.get(dom["name"])
     tr = ncu_traffic(ncu_name) if (ncu_name and args.model == "small" and B == 2048) else None
     roofline = dict(bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"], unit=dom["unit"], frac=dom["frac"],
                     traffic=tr["bytes_per_launch"] if tr else None, traffic_source=tr["source"] if tr else None,

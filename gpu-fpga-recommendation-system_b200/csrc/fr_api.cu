@@ -104,8 +104,8 @@ static fr_status validate_desc(const fr_model_desc* d) {
     return fr_fail(nullptr, FR_ERR_INVALID, "fr_create: concat_floats=%d must be a positive multiple of 16 (one 512-bit "
                    "network word, constants.hpp:9)", d->concat_floats);
   if (d->max_batch <= 0) return fr_fail(nullptr, FR_ERR_INVALID, "fr_create: max_batch must be > 0");
-  if (d->table_dtype < FR_TABLE_F32 || d->table_dtype > FR_TABLE_BF16)
-    return fr_fail(nullptr, FR_ERR_INVALID, "fr_create: table_dtype %d (FR_TABLE_F32 | F16 | BF16)", d->table_dtype);
+  if (d->table_dtype < FR_TABLE_F32 || d->table_dtype > FR_TABLE_FP8)
+    return fr_fail(nullptr, FR_ERR_INVALID, "fr_create: table_dtype %d (FR_TABLE_F32 | F16 | BF16 | FP8)", d->table_dtype);
   for (int t = 0; t < d->n_tables; t++) {
     const fr_table_desc& td = d->tables[t];
     if (td.dim <= 0 || td.dim % 4) return fr_fail(nullptr, FR_ERR_INVALID, "table %d: dim=%d must be a multiple of 4 "
@@ -127,8 +127,8 @@ static fr_status validate_desc(const fr_model_desc* d) {
   return FR_OK;
 }
 
-static fr_status alloc_stream(fr_engine* e, fr_stream_s** out) {
-  fr_stream_s* s = new fr_stream_s();
+static void free_stream(fr_stream_s* s);
+static fr_status alloc_stream_parts(fr_engine* e, fr_stream_s* s) {
   const size_t mb = (size_t)e->max_batch;
   FR_CUDA(e, cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   FR_CUDA(e, cudaMalloc(&s->d_idx, mb * e->tables.size() * sizeof(int32_t)));
@@ -139,6 +139,16 @@ static fr_status alloc_stream(fr_engine* e, fr_stream_s** out) {
   s->scores_cap = mb;
   FR_CUDA(e, cudaEventCreate(&s->ev[0]));
   FR_CUDA(e, cudaEventCreate(&s->ev[1]));
+  return FR_OK;
+}
+
+static fr_status alloc_stream(fr_engine* e, fr_stream_s** out) {
+  fr_stream_s* s = new fr_stream_s();
+  const fr_status st = alloc_stream_parts(e, s);
+  if (st != FR_OK) {   // whatever was allocated before the failing call goes back
+    free_stream(s);
+    return st;
+  }
   s->slot = e->next_slot++;   // creation order: identical on every rank of a sharded job
   *out = s;
   return FR_OK;
@@ -152,7 +162,7 @@ static void free_stream(fr_stream_s* s) {
       if (g.exec[f]) cudaGraphExecDestroy(g.exec[f]);
   cudaFree(s->d_idx);
   cudaFree(s->d_x);
-  cudaFree(s->d_x32);
+  for (void* p : s->retired) cudaFree(p);
   for (int k = 0; k < 3; k++) cudaFree(s->d_h[k]);
   cudaFree(s->d_scores);
   if (s->ev[0]) cudaEventDestroy(s->ev[0]);
@@ -284,7 +294,7 @@ extern "C" fr_status fr_load_table(fr_engine* e, int table_id, const float* host
   if (e->table_dtype == FR_TABLE_F32) {
     FR_CUDA(e, fr_h2d(e, tb.d, host_rows, (size_t)rows * dim * sizeof(float)));
   } else {
-    // fp32 image -> 2-byte rows on the device, through a bounded fp32 staging buffer
+    // fp32 image -> 2- or 1-byte rows on the device, through a bounded fp32 staging buffer
     const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)(64 << 20) / ((int64_t)dim * 4));
     float* stage = nullptr;
     FR_CUDA(e, cudaMalloc(&stage, (size_t)std::min(chunk_rows, rows) * dim * sizeof(float)));
@@ -292,7 +302,7 @@ extern "C" fr_status fr_load_table(fr_engine* e, int table_id, const float* host
       const int64_t n = std::min(chunk_rows, rows - r0) * dim;
       cudaError_t ce = fr_h2d(e, stage, host_rows + r0 * dim, (size_t)n * sizeof(float));
       if (ce == cudaSuccess) {
-        st = frk_quantize(e, stage, reinterpret_cast<char*>(tb.d) + (size_t)r0 * dim * 2, n, e->default_stream->stream);
+        st = frk_quantize(e, stage, reinterpret_cast<char*>(tb.d) + (size_t)r0 * dim * fr_table_esize(e), n, e->default_stream->stream);
         ce = cudaStreamSynchronize(e->default_stream->stream);
       }
       if (ce != cudaSuccess || st != FR_OK) {
@@ -351,7 +361,7 @@ extern "C" fr_status fr_read_table(fr_engine* e, int table_id, int64_t first_row
   if (n_rows == 0) return FR_OK;
   float* tmp = nullptr;
   FR_CUDA(e, cudaMalloc(&tmp, (size_t)n_rows * tb.dim * sizeof(float)));
-  st = frk_dequantize(e, reinterpret_cast<const char*>(tb.d) + (size_t)first_row * tb.dim * 2, tmp, n_rows * tb.dim,
+  st = frk_dequantize(e, reinterpret_cast<const char*>(tb.d) + (size_t)first_row * tb.dim * fr_table_esize(e), tmp, n_rows * tb.dim,
                       e->default_stream->stream);
   cudaError_t ce = st == FR_OK ? cudaStreamSynchronize(e->default_stream->stream) : cudaSuccess;
   if (st == FR_OK && ce == cudaSuccess)
@@ -740,15 +750,17 @@ static fr_status ensure_group_capacity(fr_engine* e, fr_stream_s* s, size_t idx_
   FR_CUDA(e, cudaStreamSynchronize(s->stream));
   for (fr_stream_s::Graph& g : s->graphs) drop_graph(g);
   s->graphs.clear();
+  // (the outgrown buffers are kept until the worker is destroyed: cudaFree synchronises the whole device, and another
+  // engine of this process may have a sharded step spinning there that waits for THIS engine's next launch)
   if (idx_ints > s->idx_cap) {
-    FR_CUDA(e, cudaFree(s->d_idx));
+    s->retired.push_back(s->d_idx);
     s->d_idx = nullptr;
     s->idx_cap = 0;
     FR_CUDA(e, cudaMalloc(&s->d_idx, idx_ints * sizeof(int32_t)));
     s->idx_cap = idx_ints;
   }
   if (n_scores > s->scores_cap) {
-    FR_CUDA(e, cudaFree(s->d_scores));
+    s->retired.push_back(s->d_scores);
     s->d_scores = nullptr;
     s->scores_cap = 0;
     FR_CUDA(e, cudaMalloc(&s->d_scores, n_scores * sizeof(float)));

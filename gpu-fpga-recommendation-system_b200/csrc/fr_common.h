@@ -47,7 +47,7 @@ struct fr_stream_s {
   int32_t* d_idx = nullptr;   // [max_batch][T] (grown by the *_many calls: idx_cap ints)
   size_t idx_cap = 0, scores_cap = 0;   // capacity of d_idx (ints) / d_scores (floats)
   float* d_x = nullptr;       // [max_batch][D]      concat activations
-  float* d_x32 = nullptr;     // tc_f16: landing zone of fr_mlp_only's fp32 input before the conversion
+  std::vector<void*> retired;  // staging buffers outgrown by a *_many call (freed with the worker)
   float* d_h[3] = {nullptr, nullptr, nullptr};  // [max_batch][hidden k]
   float* d_scores = nullptr;  // [max_batch]
   cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -248,7 +248,9 @@ inline size_t fr_xchg_flags_off(const fr_engine* e, int slot) {
   return (size_t)slot * fr_xchg_slot_floats(e) + 2 * fr_xchg_buf_floats(e);
 }
 // element size of the table storage type
-inline size_t fr_table_esize(const fr_engine* e) { return e->table_dtype == FR_TABLE_F32 ? 4 : 2; }
+inline size_t fr_table_esize(const fr_engine* e) {
+  return e->table_dtype == FR_TABLE_F32 ? 4 : (e->table_dtype == FR_TABLE_FP8 ? 1 : 2);
+}
 fr_status frk_fill_reference(fr_engine* e, float* d, int64_t rows, int dim, int64_t debug_rows, cudaStream_t st);
 fr_status frk_fill_hash(fr_engine* e, float* d, uint32_t seed, int table, int64_t rows, int dim, cudaStream_t st);
 // fp32 -> table storage type (round to nearest even) and back (exact), n elements

@@ -19,6 +19,7 @@
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 #include "fr_common.h"
 
@@ -71,6 +72,18 @@ __device__ __forceinline__ int64_t checked_row(int64_t row, const FrChunk& ch, i
   return 0;
 }
 
+// FR_TABLE_FP8: one 4-float piece is 4 bytes of E4M3, widened exactly (through fp16) to fp32.
+__device__ __forceinline__ float fp8_to_float(uint32_t byte) {
+  const __half_raw h = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)byte, __NV_E4M3);
+  return __half2float(*reinterpret_cast<const __half*>(&h));
+}
+__device__ __forceinline__ float4 ld_row4(const float4* base, int64_t piece) {
+  uint32_t w;
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(base) + piece;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(w) : "l"(p));
+  return make_float4(fp8_to_float(w & 0xFFu), fp8_to_float((w >> 8) & 0xFFu), fp8_to_float((w >> 16) & 0xFFu), fp8_to_float(w >> 24));
+}
+
 // PUSH = false: out4 is the local [B][C] buffer.
 // PUSH = true : peer_out[r] is rank r's exchange buffer; item b lands on rank
 //               b / items_per_rank at local row b % items_per_rank (NVLink peer stores).
@@ -105,7 +118,8 @@ __global__ void __launch_bounds__(256) gather_concat_kernel(const FrChunk* __res
 #pragma unroll
   for (int i = 0; i < kItems; i++)  // 64-bit addressing: 100 M rows x 128 B = 12.8 GB tables
     v[i] = DT == FR_TABLE_F32 ? ld_row16(ch.base + row[i] * ch.stride4 + ch.col4)
-                              : ld_row8<DT == FR_TABLE_F32 ? FR_TABLE_F16 : DT>(ch.base, row[i] * ch.stride4 + ch.col4);
+           : DT == FR_TABLE_FP8 ? ld_row4(ch.base, row[i] * ch.stride4 + ch.col4)
+                                : ld_row8<DT == FR_TABLE_BF16 ? FR_TABLE_BF16 : FR_TABLE_F16>(ch.base, row[i] * ch.stride4 + ch.col4);
   // Programmatic dependent launch: indices and tables are not written by the kernels of the
   // preceding batch, so everything above overlaps its tail; the concat buffer is (the first MLP
   // layer of the previous batch read it), so the stores wait for the grid dependency.  Both
@@ -149,6 +163,21 @@ __global__ void dequantize_kernel(const uint16_t* __restrict__ src, float* __res
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = dequant16(src[i], dt);
 }
+// FP8 (E4M3): round to nearest even, saturating at +-448 (NaN stays NaN)
+__device__ __forceinline__ uint8_t quant8(float x) { return (uint8_t)__nv_cvt_float_to_fp8(x, __NV_SATFINITE, __NV_E4M3); }
+__global__ void quantize8_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = quant8(src[i]);
+}
+__global__ void dequantize8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = fp8_to_float(src[i]);
+}
+__global__ void fill_reference8_kernel(uint8_t* __restrict__ t, int64_t n, int dim, int64_t filled_rows) {
+  const uint8_t one = quant8(1.f);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / dim;
+    t[i] = (r < filled_rows && (r & 1) == 0) ? one : (uint8_t)0;
+  }
+}
 // 2-byte variants of the two device fills: the fp32 value of the fp32 fill, rounded to nearest even
 __global__ void fill_reference16_kernel(uint16_t* __restrict__ t, int64_t n, int dim, int64_t filled_rows, int dt) {
   const uint16_t one = quant16(1.f, dt);
@@ -184,6 +213,11 @@ __global__ void fill_hash_kernel(uint32_t* __restrict__ t, int64_t n, int dim, u
 __global__ void fill_hash16_kernel(uint16_t* __restrict__ t, int64_t n, int dim, uint32_t seed, uint32_t table, int dt) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     t[i] = quant16(__uint_as_float(hash_bits(seed, table, (uint64_t)(i / dim), (uint32_t)(i % dim))), dt);
+}
+
+__global__ void fill_hash8_kernel(uint8_t* __restrict__ t, int64_t n, int dim, uint32_t seed, uint32_t table) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    t[i] = quant8(__uint_as_float(hash_bits(seed, table, (uint64_t)(i / dim), (uint32_t)(i % dim))));
 }
 
 __global__ void merge_kernel(const float4* __restrict__ A, int dimA4, const float4* __restrict__ B, int64_t rowsB,
@@ -248,11 +282,13 @@ void launch_gather(const fr_engine* e, const int* d_ids, int n_chunks, const int
   cfg.numAttrs = ((e->knobs.pdl_mask & 4) && !PUSH) ? 1 : 0;
   auto kern = e->table_dtype == FR_TABLE_F32 ? gather_concat_kernel<ROUND, PUSH, FR_TABLE_F32>
               : e->table_dtype == FR_TABLE_F16 ? gather_concat_kernel<ROUND, PUSH, FR_TABLE_F16>
-                                               : gather_concat_kernel<ROUND, PUSH, FR_TABLE_BF16>;
+              : e->table_dtype == FR_TABLE_BF16 ? gather_concat_kernel<ROUND, PUSH, FR_TABLE_BF16>
+                                                : gather_concat_kernel<ROUND, PUSH, FR_TABLE_FP8>;
   if (out_f16 && !PUSH)
     kern = e->table_dtype == FR_TABLE_F32 ? gather_concat_kernel<false, false, FR_TABLE_F32, true>
            : e->table_dtype == FR_TABLE_F16 ? gather_concat_kernel<false, false, FR_TABLE_F16, true>
-                                            : gather_concat_kernel<false, false, FR_TABLE_BF16, true>;
+           : e->table_dtype == FR_TABLE_BF16 ? gather_concat_kernel<false, false, FR_TABLE_BF16, true>
+                                             : gather_concat_kernel<false, false, FR_TABLE_FP8, true>;
   int* d_err = nullptr;
   if (e->check_indices && e->h_idx_err) cudaHostGetDevicePointer(&d_err, e->h_idx_err, 0);
   cudaLaunchKernelEx(&cfg, kern, chunks, d_ids, n_chunks, d_idx, idx_cols, b_begin, b_end, out4, peers, C, items_per_rank,
@@ -363,7 +399,9 @@ fr_status frk_fill_reference(fr_engine* e, float* d, int64_t rows, int dim, int6
   int64_t pairs = rows / 2;
   if (debug_rows > 0 && debug_rows / 2 < pairs) pairs = debug_rows / 2;
   const int64_t n4 = rows * dim / 4;
-  if (e->table_dtype != FR_TABLE_F32)
+  if (e->table_dtype == FR_TABLE_FP8)
+    fill_reference8_kernel<<<grid_for(rows * dim, 256, e->sm_count), 256, 0, st>>>(reinterpret_cast<uint8_t*>(d), rows * dim, dim, pairs * 2);
+  else if (e->table_dtype != FR_TABLE_F32)
     fill_reference16_kernel<<<grid_for(rows * dim, 256, e->sm_count), 256, 0, st>>>(reinterpret_cast<uint16_t*>(d), rows * dim,
                                                                                    dim, pairs * 2, e->table_dtype);
   else
@@ -376,7 +414,9 @@ fr_status frk_fill_reference(fr_engine* e, float* d, int64_t rows, int dim, int6
 
 fr_status frk_fill_hash(fr_engine* e, float* d, uint32_t seed, int table, int64_t rows, int dim, cudaStream_t st) {
   const int64_t n = rows * dim;
-  if (e->table_dtype != FR_TABLE_F32)
+  if (e->table_dtype == FR_TABLE_FP8)
+    fill_hash8_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(reinterpret_cast<uint8_t*>(d), n, dim, seed, (uint32_t)table);
+  else if (e->table_dtype != FR_TABLE_F32)
     fill_hash16_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(reinterpret_cast<uint16_t*>(d), n, dim, seed,
                                                                      (uint32_t)table, e->table_dtype);
   else
@@ -388,15 +428,16 @@ fr_status frk_fill_hash(fr_engine* e, float* d, uint32_t seed, int table, int64_
 }
 
 fr_status frk_quantize(fr_engine* e, const float* src, void* dst, int64_t n, cudaStream_t st) {
-  quantize_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(src, reinterpret_cast<uint16_t*>(dst), n, e->table_dtype);
+  if (e->table_dtype == FR_TABLE_FP8) quantize8_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(src, reinterpret_cast<uint8_t*>(dst), n);
+  else quantize_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(src, reinterpret_cast<uint16_t*>(dst), n, e->table_dtype);
   e->launches++;
   FR_CUDA(e, cudaGetLastError());
   return FR_OK;
 }
 
 fr_status frk_dequantize(fr_engine* e, const void* src, float* dst, int64_t n, cudaStream_t st) {
-  dequantize_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(src), dst, n,
-                                                                  e->table_dtype);
+  if (e->table_dtype == FR_TABLE_FP8) dequantize8_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(src), dst, n);
+  else dequantize_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(src), dst, n, e->table_dtype);
   e->launches++;
   FR_CUDA(e, cudaGetLastError());
   return FR_OK;

@@ -15,6 +15,7 @@
 // mass that fp16 represents inexactly (sub-normal weights) is below 1e-6.  fr_mlp_only / fr_layer_only take
 // caller data the engine cannot bound and always run TF32.
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <math.h>
 #include <string.h>
 
@@ -30,7 +31,10 @@ __global__ void table_range_kernel(const void* __restrict__ t, int64_t n, int dt
     unsigned b;
     if (dt == FR_TABLE_F32) b = reinterpret_cast<const unsigned*>(t)[i] & 0x7FFFFFFFu;
     else if (dt == FR_TABLE_F16) b = __float_as_uint(__half2float(__ushort_as_half(reinterpret_cast<const uint16_t*>(t)[i]))) & 0x7FFFFFFFu;
-    else b = ((unsigned)reinterpret_cast<const uint16_t*>(t)[i] << 16) & 0x7FFFFFFFu;
+    else if (dt == FR_TABLE_FP8) {
+      const __half_raw h = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)reinterpret_cast<const uint8_t*>(t)[i], __NV_E4M3);
+      b = __float_as_uint(__half2float(*reinterpret_cast<const __half*>(&h))) & 0x7FFFFFFFu;
+    } else b = ((unsigned)reinterpret_cast<const uint16_t*>(t)[i] << 16) & 0x7FFFFFFFu;
     mx = max(mx, b);
     if (b) mn = min(mn, b);
   }

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("FLEETREC_LIB") or os.path.join(PKG_DIR, "libfleetrec.
 FR_OK, FR_ERR_INVALID, FR_ERR_CUDA, FR_ERR_OOM, FR_ERR_STATE, FR_ERR_UNSUPPORTED = range(6)
 FR_MLP_LINEAR, FR_MLP_BIAS_RELU_SIGMOID = 0, 1
 FR_PREC_TF32, FR_PREC_FP32 = 0, 1
-FR_TABLE_F32, FR_TABLE_F16, FR_TABLE_BF16 = 0, 1, 2
+FR_TABLE_F32, FR_TABLE_F16, FR_TABLE_BF16, FR_TABLE_FP8 = 0, 1, 2, 3
 FR_OPT_CUDA_GRAPHS, FR_OPT_CHECK_INDICES, FR_OPT_FUSE_LOOKUP, FR_OPT_TILE_HINT, FR_OPT_F16_OPERANDS = range(5)
 FR_HINT_AUTO, FR_HINT_LATENCY, FR_HINT_THROUGHPUT = 0, 1, 2
 FR_F16_OFF, FR_F16_GUARDED = 0, 1

@@ -49,10 +49,10 @@ enum { FR_PREC_TF32 = 0, FR_PREC_FP32 = 1 };
 
 /* Storage type of the embedding tables in HBM.  The reference stores
  * fp32 (constants.hpp:4,11: one axi word = 4 floats).  F16 / BF16 halve the table bytes and the
- * lookup's row traffic; rows are converted with round-to-nearest-even when loaded and widened
+ * lookup's row traffic, FP8 (E4M3) quarters them; rows are converted with round-to-nearest-even when loaded and widened
  * exactly to fp32 by the lookup, so the concat vector is bit-exact AFTER THE STATED DEQUANT:
  * concat == float32(float16(row)) element for element.  Everything after the lookup is unchanged. */
-enum { FR_TABLE_F32 = 0, FR_TABLE_F16 = 1, FR_TABLE_BF16 = 2 };
+enum { FR_TABLE_F32 = 0, FR_TABLE_F16 = 1, FR_TABLE_BF16 = 2, FR_TABLE_FP8 = 3 /* E4M3, saturating: |x| > 448 -> +-448 */ };
 
 typedef struct fr_table_desc {
   int tier;          /* FR_TIER_*                                              */

@@ -211,7 +211,7 @@ def gather_hashed(model, seed, idx):
 # ---- reduced-precision table storage: the STATED dequant --------------------
 def quantize_dequantize(x, table_dtype):
     """What a table stored as f16 / bf16 returns for fp32 contents x: round to nearest even into
-    the 2-byte type, widen exactly back to fp32.  table_dtype: 0 fp32 (identity), 1 f16, 2 bf16.
+    the 2-byte (or 1-byte) type, widen exactly back to fp32.  table_dtype: 0 fp32 (identity), 1 f16, 2 bf16, 3 fp8 e4m3.
     Quantisation is element-wise, so it commutes with the lookup: gather(quantised tables) ==
     quantize_dequantize(gather(fp32 tables))."""
     x = np.ascontiguousarray(x, np.float32)
@@ -224,4 +224,22 @@ def quantize_dequantize(x, table_dtype):
         b = x.view(np.uint32).astype(np.uint64)
         r = (b + 0x7FFF + ((b >> 16) & 1)) & 0xFFFF0000            # RNE on the upper 16 bits
         return r.astype(np.uint32).view(np.float32).reshape(x.shape)
+    if table_dtype == 3:
+        return _e4m3_round(x)
     raise ValueError(table_dtype)
+
+
+def _e4m3_round(x):
+    """fp32 -> FP8 E4M3 (1-4-3, bias 7, no infinities, max 448) -> fp32: round to nearest, ties to the code with an even
+    mantissa, saturating to +-448 (what __nv_cvt_float_to_fp8(x, __NV_SATFINITE, __NV_E4M3) stores); NaN stays NaN."""
+    codes = np.arange(127, dtype=np.int64)                       # 0x00 .. 0x7E: the non-negative finite values, ascending
+    e, m = codes >> 3, codes & 7
+    grid = np.where(e == 0, m * 2.0 ** -9, (1 + m / 8.0) * 2.0 ** (e - 7.0))
+    a = np.abs(x.astype(np.float64))
+    hi = np.clip(np.searchsorted(grid, a, side="left"), 0, 126)  # first grid value >= |x| (or the maximum)
+    lo = np.clip(hi - 1, 0, 126)
+    d_lo, d_hi = a - grid[lo], grid[hi] - a
+    pick_hi = (d_hi < d_lo) | ((d_hi == d_lo) & (hi % 2 == 0))   # tie -> even code
+    q = np.where(a >= grid[126], grid[126], np.where(pick_hi, grid[hi], grid[lo]))
+    out = np.copysign(q, x).astype(np.float32)
+    return np.where(np.isnan(x), np.float32(np.nan), out).astype(np.float32).reshape(x.shape)

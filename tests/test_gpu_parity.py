@@ -689,27 +689,40 @@ def test_fused_chain_reference_kat(monkeypatch):
 
 
 # ---------------------------------------------------------------- reduced-precision table storage (8f-4)
-@pytest.mark.parametrize("dt", (fleetrec.FR_TABLE_F16, fleetrec.FR_TABLE_BF16))
+@pytest.mark.parametrize("dt", (fleetrec.FR_TABLE_F16, fleetrec.FR_TABLE_BF16, fleetrec.FR_TABLE_FP8))
 def test_reduced_precision_tables_bit_exact_after_stated_dequant(dt):
-    """Tables stored as f16 / bf16 in HBM: rows uploaded as fp32 are converted on the device (RNE),
-    device fills produce the same 2-byte values, the lookup widens exactly -- concat ==
-    float32(round(rows)) bit for bit, scores within the MLP tolerance of the oracle run on the
-    dequantised concat.  Table bytes halve."""
+    """Tables stored as f16 / bf16 / fp8 (E4M3, saturating) in HBM: rows uploaded as fp32 are converted on the device
+    (RNE), device fills produce the same values, the lookup widens exactly -- concat == float32(round(rows)) bit for
+    bit, scores within the MLP tolerance of the oracle run on the dequantised concat.  Table bytes halve / quarter.
+    Edge values (ties, saturation, underflow, signed zero) sit in the first rows of one table."""
     cat = catalogue.load("medium").with_row_cap(3000)
     dims = cat.layer_dims
     tables = oracle.make_tables(cat, "hash", seed=0x5EED)
+    edge = np.array([0.0, -0.0, 1.0625, 1.1875, 17.0, 19.0, 448.0, 449.0, 480.0, 1e9, -1e9, 2.0 ** -9, 2.0 ** -10, 1.0001 * 2.0 ** -10,
+                     0.00097, 65504.0, 65520.0, 3.0e38, 6.0e-8, 2.0 ** -24, 2.0 ** -25, 1.0009765625, 1.00048828125, -7.0e4], np.float32)
+    edge = np.resize(edge, tables[5][:8].size).reshape(tables[5][:8].shape)
+    if dt == fleetrec.FR_TABLE_F16:
+        edge = np.clip(edge, -65504.0, 65504.0)     # (fp16 storage does not saturate: keep the edge rows finite)
+    plain5 = tables[5].copy()
+    tables[5][:8] = edge
     W, b = oracle.make_weights(dims, seed=42)
     idx = oracle.zipf_indices(cat, 700, seed=2)
     idx[0, :] = [t.rows - 1 for t in cat.tables]
     exp = oracle.quantize_dequantize(oracle.gather(cat, tables, idx), dt)
     eng = fleetrec.Engine(cat, max_batch=1024, table_dtype=dt)
     eng.load_tables(tables)                                     # fp32 in, converted on the device
-    assert eng.table_bytes() == cat.table_bytes() // 2
+    assert eng.table_bytes() == cat.table_bytes() // (4 if dt == fleetrec.FR_TABLE_FP8 else 2)
+    assert_bits_equal(eng.read_table(5, 0, 8), oracle.quantize_dequantize(tables[5][:8], dt))
     assert_bits_equal(eng.gather_only(idx), exp)
     assert_bits_equal(eng.read_table(5, 10, 20), oracle.quantize_dequantize(tables[5][10:30], dt))
     eng.load_mlp(W, b)
-    assert rel_err(eng.infer(idx), oracle.mlp(exp, dims, W, b, mode=1)) <= TOL
+    idx2 = idx.copy()
+    idx2[:, 5] = np.maximum(idx2[:, 5], 8)                      # (the MLP check stays off the edge rows: 1e9, 3e38 ...)
+    exp2 = oracle.quantize_dequantize(oracle.gather(cat, tables, idx2), dt)
+    assert rel_err(eng.infer(idx2), oracle.mlp(exp2, dims, W, b, mode=1)) <= TOL
     eng.close()
+    tables[5] = plain5
+    exp = oracle.quantize_dequantize(oracle.gather(cat, tables, idx), dt)
     eng = fleetrec.Engine(cat, max_batch=1024, table_dtype=dt)
     eng.fill_hash(seed=0x5EED)                                  # device-side fill: same values
     assert_bits_equal(eng.gather_only(idx), exp)
