@@ -194,7 +194,7 @@ extern "C" fr_status fr_ingest_start(fr_engine* e, const fr_ingest_config* cfg, 
     sockaddr_in addr;
     memset(&addr, 0, sizeof(addr));
     addr.sin_family = AF_INET;
-    addr.sin_addr.s_addr = cfg->loopback_only ? htonl(INADDR_LOOPBACK) : htonl(INADDR_ANY);   // :379
+    addr.sin_addr.s_addr = cfg->listen_any ? htonl(INADDR_ANY) : htonl(INADDR_LOOPBACK);   // :379 binds INADDR_ANY
     addr.sin_port = htons((uint16_t)(cfg->base_port + i));                                    // :380, :541
     if (bind(c.listen_fd, reinterpret_cast<sockaddr*>(&addr), sizeof(addr)) < 0)
       return fail(FR_ERR_STATE, "bind port " + std::to_string(cfg->base_port + i) + ": " + strerror(errno));

@@ -48,7 +48,7 @@ class BatcherStats(C.Structure):
 
 class IngestConfig(C.Structure):
     _fields_ = [("base_port", C.c_int), ("n_conn", C.c_int), ("batch", C.c_int), ("payload", C.c_int),
-                ("total_batches", C.c_int64), ("loopback_only", C.c_int), ("scores_out", C.c_void_p),
+                ("total_batches", C.c_int64), ("listen_any", C.c_int), ("scores_out", C.c_void_p),
                 ("max_batches_per_conn", C.c_int64)]
 
 

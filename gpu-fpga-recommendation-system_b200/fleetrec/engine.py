@@ -338,12 +338,12 @@ class Ingest:
     on every block received."""
 
     def __init__(self, engine, base_port, n_conn, batch, payload="concat", total_batches=0, max_batches_per_conn=0,
-                 loopback_only=True):
+                 listen_any=False):
         self.engine = engine
         self.scores = np.zeros((n_conn, max(max_batches_per_conn, 1), batch), np.float32)
         cfg = _capi.IngestConfig(base_port, n_conn, batch,
                                  _capi.FR_INGEST_CONCAT if payload == "concat" else _capi.FR_INGEST_INDICES,
-                                 total_batches, int(loopback_only),
+                                 total_batches, int(listen_any),
                                  self.scores.ctypes.data if max_batches_per_conn > 0 else None, max_batches_per_conn)
         h = C.c_void_p()
         engine._chk(engine._L.fr_ingest_start(engine._h, C.byref(cfg), C.byref(h)))

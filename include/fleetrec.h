@@ -321,7 +321,8 @@ typedef struct fr_ingest_config {
   int batch;                     /* BATCH_SIZE                                                  */
   int payload;                   /* FR_INGEST_*                                                 */
   int64_t total_batches;         /* TOTAL_BATCH_NUM over all connections; 0 = until senders close */
-  int loopback_only;             /* bind 127.0.0.1 instead of INADDR_ANY                        */
+  int listen_any;                /* 0 (default): bind 127.0.0.1 only; 1: INADDR_ANY like the reference
+                                    (cuda_server.c:379) -- the socket is unauthenticated            */
   float* scores_out;             /* optional sink [n_conn][max_batches_per_conn][batch]: scores of
                                     connection c's k-th block (the reference discards all but the
                                     first outputs, cuda_server.c:499-502)                       */
