@@ -81,3 +81,37 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".inc")):
                 src = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle" not in src.replace("the oracle's", "").replace("the oracle", ""), (dp, f)
+
+
+def test_header_enumerators_match_the_python_constants():
+    """The option / hint / dtype enumerators of include/fleetrec.h and fleetrec._capi agree (the binding is hand-written)."""
+    hdr = open(os.path.join(ROOT, "include", "fleetrec.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    vals = {}
+    for body in re.findall(r"enum\s*\{(.*?)\}", hdr, flags=re.S):
+        nxt = 0
+        for item in body.split(","):
+            item = item.strip()
+            if not item:
+                continue
+            name, _, v = item.partition("=")
+            nxt = int(v) if v.strip() else nxt
+            vals[name.strip()] = nxt
+            nxt += 1
+    for name in ("FR_OPT_CUDA_GRAPHS", "FR_OPT_CHECK_INDICES", "FR_OPT_FUSE_LOOKUP", "FR_OPT_TILE_HINT", "FR_OPT_F16_OPERANDS",
+                 "FR_HINT_AUTO", "FR_HINT_LATENCY", "FR_HINT_THROUGHPUT", "FR_F16_OFF", "FR_F16_GUARDED", "FR_TABLE_F32",
+                 "FR_TABLE_F16", "FR_TABLE_BF16", "FR_TABLE_FP8", "FR_PREC_TF32", "FR_PREC_FP32", "FR_MLP_LINEAR",
+                 "FR_MLP_BIAS_RELU_SIGMOID", "FR_OK", "FR_ERR_INVALID", "FR_ERR_CUDA", "FR_ERR_OOM", "FR_ERR_STATE",
+                 "FR_ERR_UNSUPPORTED", "FR_INGEST_CONCAT", "FR_INGEST_INDICES"):
+        assert vals[name] == getattr(_capi, name), name
+
+
+def test_release_library_has_no_experiments_and_reads_two_env_hooks(L):
+    assert L.fr_build_has_experiments() == 0
+    src = open(os.path.join(ROOT, "gpu-fpga-recommendation-system_b200", "csrc", "fr_api.cu")).read()
+    csrc = os.path.join(ROOT, "gpu-fpga-recommendation-system_b200", "csrc")
+    sites = [(f, i) for f in os.listdir(csrc) if f.endswith((".cu", ".h"))
+             for i, line in enumerate(open(os.path.join(csrc, f))) if "getenv(" in line and not line.strip().startswith("//")]
+    assert {f for f, _ in sites} == {"fr_api.cu"}, sites                 # one translation unit reads the environment
+    release = src[src.index("static void fr_read_knobs"):src.index("#ifdef FR_EXPERIMENTS", src.index("static void fr_read_knobs"))]
+    assert sorted(re.findall(r'getenv\("(\w+)"\)', release)) == ["FR_TC_MAX_CLUSTERS", "FR_TC_TILES"]

@@ -242,3 +242,24 @@ def test_stated_dequant_is_rne_and_idempotent():
     assert oracle.quantize_dequantize(np.float32([1 + 2.0 ** -8]), 2)[0] == np.float32(1.0)            # tie -> even
     assert oracle.quantize_dequantize(np.float32([1 + 3 * 2.0 ** -8]), 2)[0] == np.float32(1 + 2.0 ** -6)
     assert np.array_equal(oracle.quantize_dequantize(x, 0), x)
+
+
+def test_fp8_e4m3_dequant_restatement():
+    """oracle.quantize_dequantize(x, 3): what a table stored as FP8 E4M3 returns -- round to nearest, ties to the even
+    code, saturating at +-448, exact on representable values, idempotent, monotone, sign-symmetric."""
+    q = lambda a: oracle.quantize_dequantize(np.asarray(a, np.float32), 3)   # noqa: E731
+    codes = np.arange(127)
+    grid = np.where(codes >> 3 == 0, (codes & 7) * 2.0 ** -9, (1 + (codes & 7) / 8.0) * 2.0 ** ((codes >> 3) - 7.0)).astype(np.float32)
+    assert grid[-1] == 448.0 and grid[1] == 2.0 ** -9 and len(np.unique(grid)) == 127
+    assert np.array_equal(q(grid), grid) and np.array_equal(q(-grid), -grid)              # exact on the grid
+    x = np.random.default_rng(0).uniform(-500, 500, 20000).astype(np.float32)
+    y = q(x)
+    assert np.array_equal(q(y), y)                                                        # idempotent
+    assert np.all(np.isin(np.abs(y), grid)) and np.all(np.abs(y) <= 448.0)
+    xs = np.sort(x)
+    assert np.all(np.diff(q(xs)) >= 0)                                                    # monotone
+    assert np.all(np.abs(y - x)[np.abs(x) <= 448] <= np.abs(x[np.abs(x) <= 448]) * 2.0 ** -4 + 2.0 ** -10)   # half an ulp of 3 mantissa bits
+    # ties go to the even code; saturation; underflow; signed zero; NaN
+    assert list(q([1.0625, 1.1875, 17.0, 19.0, 449.0, 1e9, -1e9, 2.0 ** -10, 1.0001 * 2.0 ** -10])) == \
+        [1.0, 1.25, 16.0, 20.0, 448.0, 448.0, -448.0, 0.0, 2.0 ** -9]
+    assert np.signbit(q([-0.0]))[0] and np.isnan(q([np.nan]))[0]

@@ -33,6 +33,29 @@ def test_plan_owners_covers_every_float_once(model, world):
     assert shard.plan_owners(cat, world) == owner   # deterministic on every rank
 
 
+@pytest.mark.parametrize("model", ("small", "medium", "large"))
+@pytest.mark.parametrize("world", (2, 4, 8))
+def test_contiguous_plan_cuts_the_wire_order_into_equal_runs(model, world):
+    """policy="contiguous": every rank owns ONE run of consecutive owned tables in concat (wire) order, the runs'
+    float counts differ by at most one widest row, on-chip-class tables stay replicated, every float is produced
+    exactly once, and the plan is deterministic."""
+    cat = catalogue.load(model)
+    owner = shard.plan_owners(cat, world, policy="contiguous")
+    assert owner == shard.plan_owners(cat, world, policy="contiguous")
+    assert all((o == -1) == (t.tier == "PLRAM") for o, t in zip(owner, cat.tables))
+    seq = []                                   # owners of the owned tables in order of first appearance on the wire
+    for s in sorted(cat.segments, key=lambda s: s.dst):
+        if owner[s.table] >= 0 and (not seq or seq[-1][0] != s.table) and s.table not in [t for t, _ in seq]:
+            seq.append((s.table, owner[s.table]))
+    ranks = [o for _, o in seq]
+    assert ranks == sorted(ranks) and set(ranks) == set(range(world))      # one run per rank, in rank order, none empty
+    pushed = [shard.owned_floats(cat, owner, r)[0] for r in range(world)]
+    assert sum(pushed) + shard.owned_floats(cat, owner, 0)[1] == cat.concat_floats
+    assert max(pushed) - min(pushed) <= 2 * max(t.dim for t in cat.tables)
+    with pytest.raises(ValueError):
+        shard.plan_owners(cat, world, policy="nope")
+
+
 @pytest.mark.parametrize("model", ("small", "large"))
 @pytest.mark.parametrize("world", (2, 8))
 def test_column_sliced_index_blocks_cover_the_batch(model, world):
