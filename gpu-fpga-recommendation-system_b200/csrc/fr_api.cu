@@ -892,7 +892,7 @@ extern "C" fr_status fr_sync(fr_engine* e, fr_stream s) {
   }
   // a sharded step that gave up waiting for a peer rank ran its MLP on an incomplete concat buffer
   if (e->h_shard_err && *reinterpret_cast<volatile int*>(e->h_shard_err))
-    return fr_fail(e, FR_ERR_STATE, "a sharded step timed out waiting for a peer rank's rows (~10 s); its scores are invalid");
+    return fr_fail(e, FR_ERR_STATE, "a sharded step timed out waiting for a peer rank's rows (~2 s); its scores are invalid");
   if (e->h_idx_err) {
     volatile int* ie = e->h_idx_err;
     if (ie[0]) {
