@@ -233,6 +233,8 @@ def workload_config(args, n):
                                              f"{quantum(args)} batches = {quantum(args) * args.batch * n} items",
             "batches_per_step": quantum(args), "e2e_batches_per_copy": args.group,
             "mlp_mode": "bias_relu_sigmoid", "precision": args.precision,
+            "index_rows": "int32 per table (the reference's index stream)" if args.index_format == "i32" else
+                          "packed transport format: uint16 for tables of at most 65536 rows, int32 otherwise (FR_IDX_PACKED)",
             "sharding": "single GPU" if n == 1 else (
                 "tables sharded across ranks (on-chip-class tables replicated), every rank fed the index columns of its "
                 "own tables, pieces pushed over NVLink by the lookup kernel, batch-parallel MLP" if args.shard == "tables" else "replicated tables, independent batches"),
@@ -285,6 +287,15 @@ def run_ours(args):
     if sharded:
         eng.shard_import(shard.exchange_handles(eng, dist, device="cuda"))
         dist.barrier()
+    # index rows travel in the engine's transport format: int32 columns (the reference's index stream), or with
+    # --index-format packed uint16 columns for the tables of at most 65536 rows (packed on the host, outside the timed
+    # regions, as the index source would produce them)
+    eng.set_option(fleetrec.FR_OPT_INDEX_FORMAT, fleetrec.FR_IDX_PACKED if args.index_format == "packed" else fleetrec.FR_IDX_I32)
+    lay_full = eng.index_layout(2)
+    lay_own, lay_rep = (eng.index_layout(0), eng.index_layout(1)) if sharded else (None, None)
+
+    def pack(a, lay=None):
+        return fleetrec.pack_indices(a, lay or lay_full)
     workers = [fleetrec.Worker(eng) for _ in range(args.streams)]
     wstreams = [torch.cuda.ExternalStream(w.cuda_stream) for w in workers]
     main = torch.cuda.current_stream()
@@ -292,39 +303,43 @@ def run_ours(args):
     pool = 32
     # sharded: every rank sees the same global batch (same seed); replicated: its own batches
     idx_np = [oracle.zipf_indices(cat, Bg, seed=1234 + (0 if sharded else 1000 * rank) + i) for i in range(pool)]
-    idx_host = [torch.from_numpy(a).pin_memory() for a in idx_np]
+    idx_host = [torch.from_numpy(pack(a)).pin_memory() for a in idx_np]
     idx_dev = [t.cuda(non_blocking=True) for t in idx_host]
     # e2e, single GPU / replicated: fr_infer_many takes `G` batches per call from ONE pinned buffer [G][B][T]
     grp_host = grp_sc = None
     if not sharded:
         n_grp = pool // G
-        grp_host = [torch.from_numpy(np.concatenate(idx_np[g * G:(g + 1) * G])).pin_memory() for g in range(n_grp)]
+        grp_host = [torch.from_numpy(pack(np.concatenate(idx_np[g * G:(g + 1) * G]))).pin_memory() for g in range(n_grp)]
         grp_sc = [torch.empty(G * B, dtype=torch.float32).pin_memory() for _ in range(args.streams)]
     # sharded: every rank is fed the column slices it needs (fr_shard_infer_sliced) -- the indices of the tables it
     # owns for ALL items and of the replicated tables for its own items -- sliced on the host outside the timed
     # region, as the reference's index source feeds every FPGA only its own tables' indices
     sl_host = sl_dev = None
     if sharded:
-        def packed(t):   # one pinned buffer, the replicated block right behind the owned one: ONE copy per step
-            o, r = shard.slice_indices(t.numpy(), owner, world, rank)
+        def sliced(a):   # this rank's two column blocks of a global batch, in the transport format
+            o, r = shard.slice_indices(a, owner, world, rank)
+            return pack(o, lay_own), pack(r, lay_rep)
+
+        def packed(a):   # one pinned buffer, the replicated block right behind the owned one: ONE copy per step
+            o, r = sliced(a)
             n_o = (o.size + 3) // 4 * 4
             buf = torch.empty(n_o + r.size, dtype=torch.int32).pin_memory()
             buf[:o.size] = torch.from_numpy(o.reshape(-1))
             buf[n_o:] = torch.from_numpy(r.reshape(-1))
             return buf, (buf[:o.size], buf[n_o:])
-        sl_bufs = [packed(t) for t in idx_host]          # keep the buffers alive
+        sl_bufs = [packed(a) for a in idx_np]            # keep the buffers alive
         sl_host = [views for _, views in sl_bufs]
         sl_dev = [tuple(a.cuda(non_blocking=True) for a in pair) for pair in sl_host]
 
-        def packed_group(ts):   # G consecutive steps for fr_shard_infer_sliced_many: [owned blocks of all G | replicated blocks]
-            o = np.concatenate([shard.slice_indices(t.numpy(), owner, world, rank)[0].reshape(-1) for t in ts])
-            r = np.concatenate([shard.slice_indices(t.numpy(), owner, world, rank)[1].reshape(-1) for t in ts])
+        def packed_group(arrs):   # G consecutive steps for fr_shard_infer_sliced_many: [owned blocks of all G | replicated blocks]
+            o = np.concatenate([sliced(a)[0].reshape(-1) for a in arrs])
+            r = np.concatenate([sliced(a)[1].reshape(-1) for a in arrs])
             n_o = (o.size + 3) // 4 * 4
             buf = torch.zeros(n_o + r.size, dtype=torch.int32).pin_memory()
             buf[:o.size] = torch.from_numpy(o)
             buf[n_o:] = torch.from_numpy(r)
             return buf, (buf[:o.size], buf[n_o:])
-        slg_bufs = [packed_group(idx_host[g * G:(g + 1) * G]) for g in range(pool // G)]
+        slg_bufs = [packed_group(idx_np[g * G:(g + 1) * G]) for g in range(pool // G)]
         slg_host = [views for _, views in slg_bufs]
         slg_sc = [torch.empty(G * B, dtype=torch.float32).pin_memory() for _ in range(args.streams)]
     sc_dev = [torch.empty(B, dtype=torch.float32, device="cuda") for _ in range(args.streams)]
@@ -333,7 +348,7 @@ def run_ours(args):
 
     trace("setup done, parity gate")
     # correctness gate before timing anything: one batch against the oracle (hash-filled tables)
-    i0 = idx_host[0].numpy()
+    i0 = idx_np[0]
     lo, hi = (rank * B, (rank + 1) * B) if sharded else (0, B)
     exp_x = oracle.gather_hashed(cat, 0x5EED, i0[lo:hi])
     exp_s = oracle.mlp(exp_x, dims, W, b, mode=1)
@@ -348,7 +363,7 @@ def run_ours(args):
         eng.sync(workers[0])
         dist.barrier()
     else:
-        got = eng.gather_only(i0)
+        got = eng.gather_only(idx_host[0].numpy())
         assert np.array_equal(got.view(np.uint32), exp_x.view(np.uint32)), "concat not bit-exact"
         eng.infer_async(idx_host[0].numpy(), sc_host[0].numpy(), B, workers[0])
         eng.sync(workers[0])
@@ -452,10 +467,13 @@ def run_ours(args):
         return
 
     # bytes uploaded per step, all ranks together, counted from the tensors copied
-    if sharded:
-        per_rank = [(Bg * len(shard.rank_tables(owner, r)[0]) + B * len(shard.rank_tables(owner, r)[1])) * 4 for r in range(world)]
+    if sharded:   # (every rank's blocks: gathered so that rank 0 can report the total)
+        mine = torch.tensor([Bg * lay_own[2] + B * lay_rep[2]], device="cuda")
+        allb = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allb, mine)
+        per_rank = [int(t.item()) for t in allb]
     else:
-        per_rank = [B * T * 4] * world
+        per_rank = [B * lay_full[2]] * world
     h2d_bytes, h2d_rank_max = sum(per_rank) * R * S, max(per_rank) * R * S
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -570,7 +588,7 @@ def run_ours(args):
     large = None
     if args.gather_batch >= 4096:
         LB = args.gather_batch
-        lidx = torch.from_numpy(oracle.zipf_indices(cat, LB, seed=99)).cuda()
+        lidx = torch.from_numpy(pack(oracle.zipf_indices(cat, LB, seed=99))).cuda()
         lms = eng.time_kernels(lidx, LB, reps=max(args.kernel_reps // 2, 2), worker=workers[0])
         lfl = [f * LB / B for f in flops]
         ltot = sum(lfl[1:4])
@@ -583,7 +601,7 @@ def run_ours(args):
 
     # ---- stand-alone gather at a large batch, uniform indices (the lookup of THIS model against the HBM roofline)
     GB = args.gather_batch
-    gidx = torch.from_numpy(oracle.uniform_indices(cat, GB, seed=4321)).cuda()
+    gidx = torch.from_numpy(pack(oracle.uniform_indices(cat, GB, seed=4321))).cuda()
     gout = torch.empty(GB, cat.concat_floats, dtype=torch.float32, device="cuda")
     for _ in range(3):
         eng.gather_only_async(gidx, gout, GB, workers[0])
@@ -856,6 +874,8 @@ def main():
     ap.add_argument("--rounds", type=int, default=64, help="a step = this many batches on every worker stream")
     ap.add_argument("--group", type=int, default=4, help="e2e: batches per fr_infer_many call (one copy each way per call)")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--index-format", default="packed", choices=["packed", "i32"],
+                    help="transport format of the index rows (FR_OPT_INDEX_FORMAT): packed = uint16 columns for small tables")
     ap.add_argument("--tiles", default="", help="FR_TC_TILES override: N1,N2,N3,ctas")
     ap.add_argument("--shard", default="tables", choices=["replicated", "tables"],
                     help="N > 1: shard tables across ranks with the NVLink push exchange (north star), or replicate")

@@ -215,6 +215,7 @@ extern "C" fr_status fr_create(const fr_model_desc* desc, int n_gpus, const int*
     e->tables[t].dim = desc->tables[t].dim;
     e->tables[t].tier = desc->tables[t].tier;
   }
+  fr_index_rows(e);
   st = alloc_stream(e, &e->default_stream);
   if (st != FR_OK) {
     g_tls_err = e->err;
@@ -496,7 +497,7 @@ static fr_status stage_idx(fr_engine* e, fr_stream_s* s, const int32_t* idx, int
     *d_idx = idx;
     return FR_OK;
   }
-  const size_t bytes = (size_t)B * e->tables.size() * sizeof(int32_t);
+  const size_t bytes = (size_t)B * e->ipr_full * sizeof(int32_t);   // (ipr_full: int32 words per index row in the engine's format)
   *d_idx = s->d_idx;
   // page-locked caller buffer: the copy engine moves the head of the batch, the SMs fetch the tail over PCIe
   // (zero_copy_pct of it, in 16-byte units); pageable buffer: the driver's staged copy
@@ -793,7 +794,7 @@ extern "C" fr_status fr_infer_many(fr_engine* e, const int32_t* idx, int n, int 
   if (n == 0 || B == 0) return FR_OK;
   if (!idx || !scores) return fr_fail(e, FR_ERR_INVALID, "null idx/scores");
   if (e->world > 1) return fr_fail(e, FR_ERR_STATE, "engine is table-sharded over %d ranks: use fr_shard_infer", e->world);
-  if ((st = ensure_group_capacity(e, s, (size_t)n * B * e->tables.size(), (size_t)n * B)) != FR_OK) return st;
+  if ((st = ensure_group_capacity(e, s, (size_t)n * B * e->ipr_full, (size_t)n * B)) != FR_OK) return st;
   return run_or_replay(e, s, idx, scores, B, FR_GV_MANY | (n << 4), 1, 0, [&](int) {
     s->f16 = fr_tc_f16(e);
     const int32_t* d_idx = nullptr;
@@ -801,7 +802,7 @@ extern "C" fr_status fr_infer_many(fr_engine* e, const int32_t* idx, int n, int 
     if (r != FR_OK) return r;
     float* d_scores = score_target(e, s, scores, n * B);
     for (int i = 0; i < n; i++) {
-      const int32_t* bi = d_idx + (size_t)i * B * e->tables.size();
+      const int32_t* bi = d_idx + (size_t)i * B * e->ipr_full;
       if ((r = frk_gather(e, bi, B, s->d_x, e->precision == FR_PREC_TF32, s->stream, fr_tc_f16(e))) != FR_OK) return r;
       if ((r = run_mlp(e, s, s->d_x, B, d_scores + (size_t)i * B)) != FR_OK) return r;
     }
@@ -927,6 +928,9 @@ extern "C" fr_status fr_set_option(fr_engine* e, int option, int value) {
     case FR_OPT_TILE_HINT:
       if (value < FR_HINT_AUTO || value > FR_HINT_THROUGHPUT) return fr_fail(e, FR_ERR_INVALID, "FR_OPT_TILE_HINT: FR_HINT_*");
       break;
+    case FR_OPT_INDEX_FORMAT:
+      if (value != FR_IDX_I32 && value != FR_IDX_PACKED) return fr_fail(e, FR_ERR_INVALID, "FR_OPT_INDEX_FORMAT: FR_IDX_*");
+      break;
     case FR_OPT_F16_OPERANDS:
       if (value < FR_F16_OFF || value > FR_F16_GUARDED) return fr_fail(e, FR_ERR_INVALID, "FR_OPT_F16_OPERANDS: FR_F16_*");
       if (value != FR_F16_OFF && e->world > 1)
@@ -946,12 +950,33 @@ extern "C" fr_status fr_set_option(fr_engine* e, int option, int value) {
     case FR_OPT_CHECK_INDICES: e->check_indices = value != 0; break;
     case FR_OPT_FUSE_LOOKUP: e->fuse_lookup = value != 0; break;
     case FR_OPT_TILE_HINT: e->tile_hint = value; break;
+    case FR_OPT_INDEX_FORMAT:   // the piece descriptors carry the index offsets: rebuilt before the next lookup
+      e->index_format = value;
+      e->chunks_dirty = true;
+      e->shard_lists_built = false;
+      fr_index_rows(e);
+      break;
     case FR_OPT_F16_OPERANDS:
       e->f16_mode = value;
       e->f16_dirty = true;
       if (value == FR_F16_OFF) e->tc_f16 = false;
       break;
   }
+  return FR_OK;
+}
+
+extern "C" fr_status fr_index_layout(fr_engine* e, int which, int32_t* byte_offset, int32_t* width, int* n, int* row_bytes) {
+  if (!e || which < 0 || which > 2) return fr_fail(e, FR_ERR_INVALID, "fr_index_layout: bad argument");
+  if (which < 2 && e->owner.empty() && e->world > 1) return fr_fail(e, FR_ERR_STATE, "fr_shard_init first");
+  fr_index_rows(e);
+  const std::vector<int>& off = which == 2 ? e->idx_off_full : (which == 0 ? e->idx_off_owned : e->idx_off_repl);
+  const int words = which == 2 ? e->ipr_full : (which == 0 ? e->ipr_owned : e->ipr_repl);
+  for (size_t i = 0; i < off.size(); i++) {
+    if (byte_offset) byte_offset[i] = off[i] & 0x7FFFFFFF;
+    if (width) width[i] = off[i] < 0 ? 2 : 4;
+  }
+  if (n) *n = (int)off.size();
+  if (row_bytes) *row_bytes = 4 * words;
   return FR_OK;
 }
 
@@ -1086,6 +1111,9 @@ extern "C" fr_status fr_shard_init(fr_engine* e, int rank, int world, const int*
   e->peers.assign(world, FrPeer());
   e->peers[rank].concat = e->d_xchg;
   e->chunks_dirty = true;
+  e->owned_tables.clear();
+  e->repl_tables.clear();
+  fr_index_rows(e);
   return FR_OK;
 }
 
@@ -1165,7 +1193,7 @@ extern "C" fr_status fr_shard_gather_push(fr_engine* e, const int32_t* idx, int 
   const int32_t* d_idx = nullptr;
   if ((st = stage_idx(e, s, idx, B_global, &d_idx)) != FR_OK) return st;
   if (B_global == 0) return FR_OK;
-  const int T = (int)e->tables.size();
+  const int T = e->ipr_full;
   return frk_shard_exchange(e, e->d_chunks, d_idx, T, d_idx + (size_t)e->rank * (B_global / e->world) * T, T, B_global,
                             s->slot, 0, false, s->stream);   // (the host barriers the ranks before fr_shard_mlp)
 }
@@ -1209,7 +1237,7 @@ static fr_status shard_infer_enqueue(fr_engine* e, fr_stream_s* s, const int32_t
   const int32_t* d_idx = nullptr;
   fr_status st = stage_idx(e, s, idx, B_global, &d_idx);
   if (st != FR_OK) return st;
-  const int T = (int)e->tables.size();
+  const int T = e->ipr_full;
   const int Bl = B_global / e->world;
   const bool fold = e->knobs.shard_fold_wait != 0;
   if ((st = frk_shard_exchange(e, e->d_chunks, d_idx, T, d_idx + (size_t)e->rank * Bl * T, T, B_global, s->slot, parity,
@@ -1254,7 +1282,7 @@ static fr_status shard_infer_sliced_enqueue(fr_engine* e, fr_stream_s* s, const 
                                             int n, int B_global, float* scores, int parity0) {
   s->f16 = false;
   const int Bl = B_global / e->world;
-  const size_t o1 = (size_t)B_global * e->owned_tables.size(), r1 = (size_t)Bl * e->repl_tables.size();   // ints per batch
+  const size_t o1 = (size_t)B_global * e->ipr_owned, r1 = (size_t)Bl * e->ipr_repl;   // int32 words per batch
   const size_t n_o = o1 * n, n_r = r1 * n;
   const int32_t* d_o = idx_owned;
   const int32_t* d_r = idx_repl;
@@ -1280,8 +1308,8 @@ static fr_status shard_infer_sliced_enqueue(fr_engine* e, fr_stream_s* s, const 
   float* d_scores = score_target(e, s, scores, n * Bl);
   for (int i = 0; i < n; i++) {   // consecutive steps of this worker's slot: the exchange buffers alternate
     const int parity = (parity0 + i) & 1;
-    fr_status st = frk_shard_exchange(e, chunks, d_o + i * o1, (int)e->owned_tables.size(), d_r + i * r1,
-                                      (int)e->repl_tables.size(), B_global, s->slot, parity, !fold, s->stream);
+    fr_status st = frk_shard_exchange(e, chunks, d_o + i * o1, e->ipr_owned, d_r + i * r1, e->ipr_repl, B_global, s->slot,
+                                      parity, !fold, s->stream);
     if (st != FR_OK) return st;
     const float* x = e->d_xchg + fr_xchg_concat_off(e, s->slot, parity);
     if ((st = run_mlp(e, s, x, Bl, d_scores + (size_t)i * Bl, fold ? s->slot : -1)) != FR_OK) return st;
@@ -1304,7 +1332,8 @@ extern "C" fr_status fr_shard_infer_sliced_many(fr_engine* e, const int32_t* idx
     return fr_fail(e, FR_ERR_INVALID, "null idx/scores");
   if (*e->h_shard_err) return fr_fail(e, FR_ERR_STATE, "a previous sharded step timed out waiting for a peer rank");
   const int Bl = B_global / e->world;
-  const size_t ints = ((size_t)n * B_global * e->owned_tables.size() + 3) / 4 * 4 + (size_t)n * Bl * e->repl_tables.size();
+  fr_index_rows(e);
+  const size_t ints = ((size_t)n * B_global * e->ipr_owned + 3) / 4 * 4 + (size_t)n * Bl * e->ipr_repl;
   if ((st = ensure_group_capacity(e, s, ints, (size_t)n * Bl)) != FR_OK) return st;
   const int parity0 = (s->shard_step + 1) & 1;   // the first step's exchange buffer; the graphs come in pairs by it
   s->shard_step += n;

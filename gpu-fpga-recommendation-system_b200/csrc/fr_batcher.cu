@@ -203,7 +203,7 @@ extern "C" fr_status fr_batcher_create(fr_engine* e, const fr_batcher_config* cf
   fr_batcher* b = new fr_batcher();
   b->eng = e;
   b->max_batch = cfg->max_batch;
-  b->T = (int)e->tables.size();
+  b->T = e->ipr_full;   // int32 words per index row in the engine's index format (FR_OPT_INDEX_FORMAT)
   b->max_delay = std::chrono::microseconds(cfg->max_delay_us);
   const int n_buf = 2 * cfg->n_workers + 1;   // one being filled, one queued and one in flight per worker
   for (int i = 0; i < n_buf; i++) {

@@ -21,7 +21,10 @@ struct FrChunk {
   int stride4;         // row pitch in float4 (= dim/4)
   int col4;            // float4 offset inside the row
   int rows;            // rows of the table (clamped to INT_MAX): bound of the optional index check
+  int idx_off;         // byte offset of the table's index inside an index row; bit 31 set: the index is a uint16
+  int pad_;
 };
+constexpr int kIdx16 = (int)0x80000000;
 
 // The same piece, compact (16 bytes), for the lookup fused into layer 1 (staged in shared memory).
 struct FrFuseChunk {
@@ -175,6 +178,10 @@ struct fr_engine {
   std::vector<std::pair<int, int>> warmed;   // (entry point, B) pairs that have run un-captured once (guarded by mu)
   // fr_set_check_indices: the lookup kernels compare every index with its table's row count, count the offenders in
   // h_idx_err (pinned + mapped: {count, table column, value, item}) and read row 0 instead; fr_sync reports them
+  // FR_OPT_INDEX_FORMAT: layout of the index rows the hot-path calls are given (fr_index_rows() below)
+  int index_format = FR_IDX_I32;
+  std::vector<int> idx_off_full, idx_off_owned, idx_off_repl;   // per column: byte offset | kIdx16
+  int ipr_full = 0, ipr_owned = 0, ipr_repl = 0;                  // int32 words per row (rows are padded to 4 bytes)
   int tile_hint = 0;              // FR_HINT_*: latency- or throughput-oriented tcgen05 tiles (fr_set_option)
   bool check_indices = false;
   int* h_idx_err = nullptr;
@@ -225,6 +232,8 @@ fr_status frk_shard_exchange(fr_engine* e, const FrChunk* chunks, const int32_t*
                              const int32_t* d_idx_repl, int T_repl, int B_global, int slot, int parity, bool wait, cudaStream_t st);
 const FrChunk* frk_sliced_chunks(fr_engine* e);   // descriptors whose `table` is the column of a column-sliced block
 void fr_shard_table_lists(fr_engine* e);   // fills owned_tables / repl_tables from owner[] (idempotent)
+// (re)computes idx_off_* / ipr_* for the engine's index format and table lists
+void fr_index_rows(fr_engine* e);
 // wait (on the device) until every rank has published the slot's current step; the tcgen05 path does this inside
 // its first kernel instead (FrPeerWait)
 fr_status frk_shard_wait(fr_engine* e, int slot, cudaStream_t st);

@@ -84,13 +84,20 @@ __device__ __forceinline__ float4 ld_row4(const float4* base, int64_t piece) {
   return make_float4(fp8_to_float(w & 0xFFu), fp8_to_float((w >> 8) & 0xFFu), fp8_to_float((w >> 16) & 0xFFu), fp8_to_float(w >> 24));
 }
 
+// One index of item b: rows are row_words int32 words long; the piece's descriptor says where its table's index sits in
+// the row and whether it is an int32 or (FR_IDX_PACKED, tables of at most 65536 rows) a uint16.
+__device__ __forceinline__ int64_t ld_index(const int32_t* __restrict__ idx, size_t b, int row_words, int idx_off) {
+  const char* p = reinterpret_cast<const char*>(idx + b * (size_t)row_words) + (idx_off & 0x7FFFFFFF);
+  return idx_off < 0 ? (int64_t)__ldg(reinterpret_cast<const unsigned short*>(p)) : (int64_t)__ldg(reinterpret_cast<const int*>(p));
+}
+
 // PUSH = false: out4 is the local [B][C] buffer.
 // PUSH = true : peer_out[r] is rank r's exchange buffer; item b lands on rank
 //               b / items_per_rank at local row b % items_per_rank (NVLink peer stores).
 template <bool ROUND, bool PUSH, int DT, bool OUT16 = false>
 __global__ void __launch_bounds__(256) gather_concat_kernel(const FrChunk* __restrict__ chunks,
                                                             const int* __restrict__ chunk_ids, int n_chunks,
-                                                            const int32_t* __restrict__ idx, int T, int b_begin,
+                                                            const int32_t* __restrict__ idx, int T /* int32 words per index row */, int b_begin,
                                                             int b_end, float4* __restrict__ out4,
                                                             float4* const* __restrict__ peer_out, int C,
                                                             int items_per_rank, long long peer_off4,
@@ -108,7 +115,7 @@ __global__ void __launch_bounds__(256) gather_concat_kernel(const FrChunk* __res
 #pragma unroll
   for (int i = 0; i < kItems; i++) {
     const int b = b0 + i;
-    row[i] = (b < b_end) ? (int64_t)__ldg(idx + (size_t)b * T + ch.table) : 0;
+    row[i] = (b < b_end) ? ld_index(idx, (size_t)b, T, ch.idx_off) : 0;
   }
   if (idx_err) {   // fr_set_check_indices: the reference never checks (embedding_47_krnl.cpp:925-934)
 #pragma unroll
@@ -256,9 +263,9 @@ template <bool ROUND, bool PUSH>
 void launch_gather(const fr_engine* e, const int* d_ids, int n_chunks, const int32_t* d_idx, int b_begin, int b_end,
                    float4* out4, float4* const* peers, int items_per_rank, cudaStream_t st, long long peer_off4 = 0,
                    const FrChunk* chunks = nullptr, int idx_cols = 0, bool out_f16 = false) {
-  if (!chunks) {   // full index rows [B][T]; else a column-sliced block with its own descriptors
+  if (!chunks) {   // full index rows; else a column-sliced block with its own descriptors and row length
     chunks = e->d_chunks;
-    idx_cols = (int)e->tables.size();
+    idx_cols = e->ipr_full;
   }
   const int C = e->D / 4;
   const int n_items = b_end - b_begin;
@@ -297,8 +304,35 @@ void launch_gather(const fr_engine* e, const int* d_ids, int n_chunks, const int
 
 }  // namespace
 
+// Index-row layouts for the engine's FR_OPT_INDEX_FORMAT: full rows (all tables) and, when sharded, the two
+// column-sliced blocks.  FR_IDX_I32: column i at byte 4 i.  FR_IDX_PACKED: the int32 columns (tables of more than 65536
+// rows) first, in list order, then the uint16 columns, the row padded to a multiple of 4 bytes.
+static void index_row_layout(const fr_engine* e, const std::vector<int>& tables, std::vector<int>* off, int* words) {
+  off->assign(tables.size(), 0);
+  int pos = 0;
+  if (e->index_format == FR_IDX_I32) {
+    for (size_t i = 0; i < tables.size(); i++, pos += 4) (*off)[i] = pos;
+  } else {
+    for (size_t i = 0; i < tables.size(); i++)
+      if (e->tables[tables[i]].rows > 65536) { (*off)[i] = pos; pos += 4; }
+    for (size_t i = 0; i < tables.size(); i++)
+      if (e->tables[tables[i]].rows <= 65536) { (*off)[i] = pos | kIdx16; pos += 2; }
+  }
+  *words = (pos + 3) / 4;
+}
+
+void fr_index_rows(fr_engine* e) {
+  std::vector<int> all(e->tables.size());
+  for (size_t t = 0; t < all.size(); t++) all[t] = (int)t;
+  index_row_layout(e, all, &e->idx_off_full, &e->ipr_full);
+  fr_shard_table_lists(e);
+  index_row_layout(e, e->owned_tables, &e->idx_off_owned, &e->ipr_owned);
+  index_row_layout(e, e->repl_tables, &e->idx_off_repl, &e->ipr_repl);
+}
+
 fr_status frk_upload_chunks(fr_engine* e) {
   const int C = e->D / 4;
+  fr_index_rows(e);
   std::vector<FrChunk> h(C);
   std::vector<FrFuseChunk> hf(C);
   std::vector<char> covered(C, 0);
@@ -311,6 +345,8 @@ fr_status frk_upload_chunks(fr_engine* e) {
       c.stride4 = t.dim / 4;
       c.col4 = s.col / 4 + k;
       c.rows = t.rows > 0x7FFFFFFF ? 0x7FFFFFFF : (int)t.rows;
+      c.idx_off = e->idx_off_full[s.table];
+      c.pad_ = 0;
       hf[s.dst / 4 + k] = {c.base, c.table, (c.stride4 << 8) | c.col4};
       covered[s.dst / 4 + k] = 1;
     }
@@ -478,6 +514,9 @@ static fr_status build_shard_lists(fr_engine* e) {
   }
   e->n_owned = (int)owned.size();
   e->n_repl = (int)repl.size();
+  cudaFree(e->d_owned_ids);   // (rebuilt when the index format changes)
+  cudaFree(e->d_repl_ids);
+  e->d_owned_ids = e->d_repl_ids = nullptr;
   if (e->n_owned) {
     FR_CUDA(e, cudaMalloc(&e->d_owned_ids, sizeof(int) * owned.size()));
     FR_CUDA(e, fr_h2d(e, e->d_owned_ids, owned.data(), sizeof(int) * owned.size()));
@@ -493,7 +532,12 @@ static fr_status build_shard_lists(fr_engine* e) {
   std::vector<int> col_of(e->tables.size(), 0);
   for (size_t i = 0; i < e->owned_tables.size(); i++) col_of[e->owned_tables[i]] = (int)i;
   for (size_t i = 0; i < e->repl_tables.size(); i++) col_of[e->repl_tables[i]] = (int)i;
-  for (int c = 0; c < C; c++) ch[c].table = col_of[table_of[c]];
+  fr_index_rows(e);
+  for (int c = 0; c < C; c++) {
+    const int t = table_of[c], col = col_of[t];
+    ch[c].table = col;
+    ch[c].idx_off = (e->owner.empty() ? e->rank : e->owner[t]) < 0 ? e->idx_off_repl[col] : e->idx_off_owned[col];
+  }
   if (!e->d_chunks_sliced) FR_CUDA(e, cudaMalloc(&e->d_chunks_sliced, sizeof(FrChunk) * C));
   FR_CUDA(e, fr_h2d(e, e->d_chunks_sliced, ch.data(), sizeof(FrChunk) * C));
   e->shard_lists_built = true;

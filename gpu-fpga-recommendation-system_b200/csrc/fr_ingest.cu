@@ -160,6 +160,8 @@ extern "C" fr_status fr_ingest_start(fr_engine* e, const fr_ingest_config* cfg, 
     return fr_fail(e, FR_ERR_INVALID, "fr_ingest_start: bad configuration (n_conn %d, batch %d, base_port %d, payload %d)",
                    cfg->n_conn, cfg->batch, cfg->base_port, cfg->payload);
   if (e->world > 1) return fr_fail(e, FR_ERR_UNSUPPORTED, "fr_ingest drives fr_infer / fr_mlp_only; not for a table-sharded engine");
+  if (cfg->payload == FR_INGEST_INDICES && e->index_format != FR_IDX_I32)
+    return fr_fail(e, FR_ERR_STATE, "FR_INGEST_INDICES blocks are int32 rows (the reference's index stream): set FR_OPT_INDEX_FORMAT back to FR_IDX_I32");
   FR_CUDA(e, cudaSetDevice(e->device));
   fr_ingest* g = new fr_ingest();
   g->eng = e;

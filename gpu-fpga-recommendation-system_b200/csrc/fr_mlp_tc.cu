@@ -2176,6 +2176,7 @@ bool frtc_can_fuse(const fr_engine* e) {
   bool dims_ok = true;
   for (const FrTable& t : e->tables) dims_ok = dims_ok && t.dim / 4 < 256;
   return e->fuse_lookup && !fr_tc_f16(e) && st && st->ready && e->world == 1 && e->precision == FR_PREC_TF32 &&
+         e->index_format == FR_IDX_I32 &&
          e->table_dtype == FR_TABLE_F32 && e->dims[1] % kFuseN == 0 &&
          e->dims[1] <= kMaxN && e->D / 4 <= kFuseMaxChunks && dims_ok;
 }

@@ -16,7 +16,8 @@ FR_OK, FR_ERR_INVALID, FR_ERR_CUDA, FR_ERR_OOM, FR_ERR_STATE, FR_ERR_UNSUPPORTED
 FR_MLP_LINEAR, FR_MLP_BIAS_RELU_SIGMOID = 0, 1
 FR_PREC_TF32, FR_PREC_FP32 = 0, 1
 FR_TABLE_F32, FR_TABLE_F16, FR_TABLE_BF16, FR_TABLE_FP8 = 0, 1, 2, 3
-FR_OPT_CUDA_GRAPHS, FR_OPT_CHECK_INDICES, FR_OPT_FUSE_LOOKUP, FR_OPT_TILE_HINT, FR_OPT_F16_OPERANDS = range(5)
+FR_OPT_CUDA_GRAPHS, FR_OPT_CHECK_INDICES, FR_OPT_FUSE_LOOKUP, FR_OPT_TILE_HINT, FR_OPT_F16_OPERANDS, FR_OPT_INDEX_FORMAT = range(6)
+FR_IDX_I32, FR_IDX_PACKED = 0, 1
 FR_HINT_AUTO, FR_HINT_LATENCY, FR_HINT_THROUGHPUT = 0, 1, 2
 FR_F16_OFF, FR_F16_GUARDED = 0, 1
 
@@ -74,6 +75,7 @@ SIGNATURES = {
     "fr_set_precision": (_I, [_P, _I]),
     "fr_set_option": (_I, [_P, _I, _I]),
     "fr_f16_report": (_I, [_P, C.POINTER(C.c_int), C.POINTER(C.c_float)]),
+    "fr_index_layout": (_I, [_P, _I, _P, _P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "fr_stream_create": (_I, [_P, C.POINTER(_P)]),
     "fr_stream_destroy": (None, [_P, _P]),
     "fr_stream_cuda": (_P, [_P]),

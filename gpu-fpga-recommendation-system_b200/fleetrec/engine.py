@@ -147,6 +147,16 @@ class Engine:
         """fr_set_option: FR_OPT_CUDA_GRAPHS / CHECK_INDICES / FUSE_LOOKUP / TILE_HINT / F16_OPERANDS."""
         self._chk(self._L.fr_set_option(self._h, option, int(value)))
 
+    def index_layout(self, which=2):
+        """(byte_offsets, widths, row_bytes) of one index row under FR_OPT_INDEX_FORMAT: which = 2 full rows (all tables),
+        0 / 1 the owned / replicated column blocks of the sliced sharded step."""
+        n, rb = C.c_int(0), C.c_int(0)
+        self._chk(self._L.fr_index_layout(self._h, which, None, None, C.byref(n), C.byref(rb)))
+        off = (C.c_int32 * max(n.value, 1))()
+        wid = (C.c_int32 * max(n.value, 1))()
+        self._chk(self._L.fr_index_layout(self._h, which, off, wid, C.byref(n), C.byref(rb)))
+        return [int(off[i]) for i in range(n.value)], [int(wid[i]) for i in range(n.value)], rb.value
+
     def f16_report(self):
         """(active, bounds): does fr_infer compute on fp16 operands, and the range bounds that decided it
         ([max |x|, max |h1|, max |h2|, min non-zero |table element|, inexact weight-mass share])."""
@@ -364,6 +374,24 @@ class Ingest:
         if self._h:
             self.engine._L.fr_ingest_destroy(self._h)
             self._h = None
+
+
+def pack_indices(idx, layout):
+    """int32 index rows [B][n] -> rows in the layout Engine.index_layout() describes ([B][row_bytes] uint8, viewable as
+    int32 [B][row_bytes / 4]): int32 columns stay int32, uint16 columns are narrowed (they belong to tables of at most
+    65536 rows).  With the FR_IDX_I32 layout this is a reinterpretation of the same bytes."""
+    off, wid, row_bytes = layout
+    idx = np.ascontiguousarray(idx, np.int32)
+    assert idx.ndim == 2 and idx.shape[1] == len(off)
+    out = np.zeros((idx.shape[0], row_bytes), np.uint8)
+    for c, (o, w) in enumerate(zip(off, wid)):
+        col = idx[:, c]
+        if w == 2:
+            assert col.min(initial=0) >= 0 and col.max(initial=0) < 65536
+            out[:, o:o + 2] = col.astype("<u2").view(np.uint8).reshape(-1, 2)
+        else:
+            out[:, o:o + 4] = col.astype("<i4").view(np.uint8).reshape(-1, 4)
+    return out.view(np.int32)
 
 
 def merge_index(iA, iB, rowsB):

@@ -147,12 +147,26 @@ int fr_build_has_experiments(void);
  *                         tables and weights proves that no operand can leave fp16's normal range (largest table
  *                         magnitude, |W|^T.bound + |b| layer by layer); otherwise, and for fr_mlp_only / fr_layer_only
  *                         whose inputs it cannot bound, TF32.  FR_F16_OFF (default): TF32.  fr_f16_report says
- *                         which one an engine runs and why. */
+ *                         which one an engine runs and why.
+ *   FR_OPT_INDEX_FORMAT   FR_IDX_I32 (default): index rows are int32 [n_tables], what the reference streams
+ *                         (load_access_idx, embedding_47_krnl.cpp:899-914).  FR_IDX_PACKED: a transport format for the
+ *                         host -> device hop, which is what bounds the end-to-end rate once the kernels are fast:
+ *                         every `idx` argument of the hot-path calls then points to packed rows -- the columns of tables
+ *                         with more than 65536 rows as int32, in table order, followed by the columns of the smaller
+ *                         tables as uint16, the row padded to a multiple of 4 bytes (small model: 120 instead of 188
+ *                         bytes per item).  fr_index_layout describes the rows; the lookup kernels read either format
+ *                         through the same per-piece byte offsets.  Not with FR_OPT_FUSE_LOOKUP or FR_INGEST_INDICES. */
 enum { FR_OPT_CUDA_GRAPHS = 0, FR_OPT_CHECK_INDICES = 1, FR_OPT_FUSE_LOOKUP = 2, FR_OPT_TILE_HINT = 3,
-       FR_OPT_F16_OPERANDS = 4 };
+       FR_OPT_F16_OPERANDS = 4, FR_OPT_INDEX_FORMAT = 5 };
+enum { FR_IDX_I32 = 0, FR_IDX_PACKED = 1 };
 enum { FR_HINT_AUTO = 0, FR_HINT_LATENCY = 1, FR_HINT_THROUGHPUT = 2 };
 enum { FR_F16_OFF = 0, FR_F16_GUARDED = 1 };
 fr_status fr_set_option(fr_engine* e, int option, int value);
+/* Layout of one index row under the engine's FR_OPT_INDEX_FORMAT.  which = 2: the full rows of fr_infer / fr_infer_many /
+ * fr_shard_infer (all tables); which = 0 / 1: the column-sliced blocks of fr_shard_infer_sliced (owned / replicated
+ * tables, the lists of fr_shard_tables).  byte_offset[i], width[i] (2 or 4): where column i of that list sits in a row
+ * (either may be null); *n = columns, *row_bytes = bytes per row (a multiple of 4). */
+fr_status fr_index_layout(fr_engine* e, int which, int32_t* byte_offset, int32_t* width, int* n, int* row_bytes);
 /* Outcome of the FR_F16_GUARDED range analysis (run by the first fr_infer after tables / weights / the option
  * changed; this call runs it if it is due): *active = 1 when fr_infer computes on fp16 operands; bounds[0..2] =
  * upper bounds of |concat element|, |H1 element|, |H2 element| (must stay below 60000); bounds[3] = smallest

@@ -99,7 +99,7 @@ def test_header_enumerators_match_the_python_constants():
             vals[name.strip()] = nxt
             nxt += 1
     for name in ("FR_OPT_CUDA_GRAPHS", "FR_OPT_CHECK_INDICES", "FR_OPT_FUSE_LOOKUP", "FR_OPT_TILE_HINT", "FR_OPT_F16_OPERANDS",
-                 "FR_HINT_AUTO", "FR_HINT_LATENCY", "FR_HINT_THROUGHPUT", "FR_F16_OFF", "FR_F16_GUARDED", "FR_TABLE_F32",
+                 "FR_OPT_INDEX_FORMAT", "FR_IDX_I32", "FR_IDX_PACKED", "FR_HINT_AUTO", "FR_HINT_LATENCY", "FR_HINT_THROUGHPUT", "FR_F16_OFF", "FR_F16_GUARDED", "FR_TABLE_F32",
                  "FR_TABLE_F16", "FR_TABLE_BF16", "FR_TABLE_FP8", "FR_PREC_TF32", "FR_PREC_FP32", "FR_MLP_LINEAR",
                  "FR_MLP_BIAS_RELU_SIGMOID", "FR_OK", "FR_ERR_INVALID", "FR_ERR_CUDA", "FR_ERR_OOM", "FR_ERR_STATE",
                  "FR_ERR_UNSUPPORTED", "FR_INGEST_CONCAT", "FR_INGEST_INDICES"):
