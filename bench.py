@@ -467,11 +467,12 @@ def run_ours(args):
         return
 
     # bytes uploaded per step, all ranks together, counted from the tensors copied
-    if sharded:   # (every rank's blocks: gathered so that rank 0 can report the total)
-        mine = torch.tensor([Bg * lay_own[2] + B * lay_rep[2]], device="cuda")
-        allb = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allb, mine)
-        per_rank = [int(t.item()) for t in allb]
+    if sharded:   # (every rank's blocks, from the plan: no collective here -- the other ranks have already left)
+        def row_bytes(tabs):
+            wide = args.index_format == "i32"
+            return (sum(4 if wide or cat.tables[t].rows > 65536 else 2 for t in tabs) + 3) // 4 * 4
+        per_rank = [Bg * row_bytes(shard.rank_tables(owner, r)[0]) + B * row_bytes(shard.rank_tables(owner, r)[1]) for r in range(world)]
+        per_rank[rank] = Bg * lay_own[2] + B * lay_rep[2]     # this rank's: what fr_index_layout reported
     else:
         per_rank = [B * lay_full[2]] * world
     h2d_bytes, h2d_rank_max = sum(per_rank) * R * S, max(per_rank) * R * S
