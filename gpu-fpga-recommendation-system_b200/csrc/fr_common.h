@@ -15,7 +15,8 @@
 #define FR_MAX_LAYERS 4
 
 // One 16-byte piece of an item's concat vector: out4[b][c] = base[idx[b][table]*stride4 + col4].
-struct FrChunk {
+// (32 bytes, 16-byte aligned: the lookup kernel fetches a descriptor with two 128-bit loads)
+struct alignas(16) FrChunk {
   const float4* base;  // table base (device), NULL when the table is not resident on this rank
   int table;           // column of idx[][] to read
   int stride4;         // row pitch in float4 (= dim/4)
@@ -25,6 +26,27 @@ struct FrChunk {
   int pad_;
 };
 constexpr int kIdx16 = (int)0x80000000;
+static_assert(sizeof(FrChunk) == 32, "FrChunk is two 16-byte words");
+
+// One index out of an index row (`row` = its first int32 word; rows are whole int32 words in either format).  ONE aligned
+// 32-bit load whatever the width -- a uint16 column sits at an even byte offset, i.e. in the low or high half of its word
+// -- so a warp whose pieces mix both widths still issues a single load instruction (the lookup is bound by load/store
+// instructions on the small model: two predicated loads per index cost 4.2 -> 5.2 us per batch of 2048).
+#ifdef __CUDACC__
+__host__ __device__ __forceinline__
+#else
+inline
+#endif
+int64_t fr_index_at(const int32_t* row, int idx_off) {
+  const int off = idx_off & 0x7FFFFFFF;
+  const int32_t* p = row + (off >> 2);
+#ifdef __CUDA_ARCH__
+  const int32_t w = __ldg(p);
+#else
+  const int32_t w = *p;
+#endif
+  return idx_off < 0 ? (int64_t)(((uint32_t)w >> ((off & 2) * 8)) & 0xFFFFu) : (int64_t)w;
+}
 
 // The same piece, compact (16 bytes), for the lookup fused into layer 1 (staged in shared memory).
 struct FrFuseChunk {

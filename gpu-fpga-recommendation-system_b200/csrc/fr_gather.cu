@@ -21,6 +21,8 @@
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
 
+#include <stddef.h>
+
 #include "fr_common.h"
 
 namespace {
@@ -85,10 +87,25 @@ __device__ __forceinline__ float4 ld_row4(const float4* base, int64_t piece) {
 }
 
 // One index of item b: rows are row_words int32 words long; the piece's descriptor says where its table's index sits in
-// the row and whether it is an int32 or (FR_IDX_PACKED, tables of at most 65536 rows) a uint16.
+// the row and whether it is an int32 or (FR_IDX_PACKED, tables of at most 65536 rows) a uint16 (fr_index_at, fr_common.h).
 __device__ __forceinline__ int64_t ld_index(const int32_t* __restrict__ idx, size_t b, int row_words, int idx_off) {
-  const char* p = reinterpret_cast<const char*>(idx + b * (size_t)row_words) + (idx_off & 0x7FFFFFFF);
-  return idx_off < 0 ? (int64_t)__ldg(reinterpret_cast<const unsigned short*>(p)) : (int64_t)__ldg(reinterpret_cast<const int*>(p));
+  return fr_index_at(idx + b * (size_t)row_words, idx_off);
+}
+
+// A piece descriptor in two 128-bit loads (the compiler splits the struct copy into three or four).
+static_assert(offsetof(FrChunk, table) == 8 && offsetof(FrChunk, stride4) == 12 && offsetof(FrChunk, col4) == 16 &&
+              offsetof(FrChunk, rows) == 20 && offsetof(FrChunk, idx_off) == 24, "ld_chunk unpacks this layout");
+__device__ __forceinline__ FrChunk ld_chunk(const FrChunk* __restrict__ p) {
+  const uint4 lo = __ldg(reinterpret_cast<const uint4*>(p)), hi = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  FrChunk ch;
+  ch.base = reinterpret_cast<const float4*>((uint64_t)lo.x | ((uint64_t)lo.y << 32));
+  ch.table = (int)lo.z;
+  ch.stride4 = (int)lo.w;
+  ch.col4 = (int)hi.x;
+  ch.rows = (int)hi.y;
+  ch.idx_off = (int)hi.z;
+  ch.pad_ = 0;
+  return ch;
 }
 
 // PUSH = false: out4 is the local [B][C] buffer.
@@ -109,7 +126,7 @@ __global__ void __launch_bounds__(256) gather_concat_kernel(const FrChunk* __res
   if (ci >= n_chunks) return;
   const int b0 = b_begin + (blockIdx.y * blockDim.y + threadIdx.y) * kItems;
   const int c = chunk_ids ? chunk_ids[ci] : ci;
-  const FrChunk ch = chunks[c];
+  const FrChunk ch = ld_chunk(chunks + c);
 
   int64_t row[kItems];
 #pragma unroll
@@ -307,18 +324,29 @@ void launch_gather(const fr_engine* e, const int* d_ids, int n_chunks, const int
 // Index-row layouts for the engine's FR_OPT_INDEX_FORMAT: full rows (all tables) and, when sharded, the two
 // column-sliced blocks.  FR_IDX_I32: column i at byte 4 i.  FR_IDX_PACKED: the int32 columns (tables of more than 65536
 // rows) first, in list order, then the uint16 columns, the row padded to a multiple of 4 bytes.
-static void index_row_layout(const fr_engine* e, const std::vector<int>& tables, std::vector<int>* off, int* words) {
-  off->assign(tables.size(), 0);
+static void index_row_layout_rows(const int64_t* rows, int n, int format, int* off, int* words) {
   int pos = 0;
-  if (e->index_format == FR_IDX_I32) {
-    for (size_t i = 0; i < tables.size(); i++, pos += 4) (*off)[i] = pos;
+  if (format == FR_IDX_I32) {
+    for (int i = 0; i < n; i++, pos += 4) off[i] = pos;
   } else {
-    for (size_t i = 0; i < tables.size(); i++)
-      if (e->tables[tables[i]].rows > 65536) { (*off)[i] = pos; pos += 4; }
-    for (size_t i = 0; i < tables.size(); i++)
-      if (e->tables[tables[i]].rows <= 65536) { (*off)[i] = pos | kIdx16; pos += 2; }
+    for (int i = 0; i < n; i++)
+      if (rows[i] > 65536) { off[i] = pos; pos += 4; }
+    for (int i = 0; i < n; i++)
+      if (rows[i] <= 65536) { off[i] = pos | kIdx16; pos += 2; }
   }
   *words = (pos + 3) / 4;
+}
+static void index_row_layout(const fr_engine* e, const std::vector<int>& tables, std::vector<int>* off, int* words) {
+  std::vector<int64_t> rows(tables.size());
+  for (size_t i = 0; i < tables.size(); i++) rows[i] = e->tables[tables[i]].rows;
+  off->assign(tables.size(), 0);
+  index_row_layout_rows(rows.data(), (int)rows.size(), e->index_format, off->data(), words);
+}
+// The layout rule on its own, for the CPU tests (off[i]: byte offset, bit 31 set for a uint16 column).
+extern "C" int frdbg_index_layout(const int64_t* rows, int n, int format, int32_t* off, int* words) {
+  if (!rows || !off || !words || n < 0 || (format != FR_IDX_I32 && format != FR_IDX_PACKED)) return -1;
+  index_row_layout_rows(rows, n, format, off, words);
+  return 0;
 }
 
 void fr_index_rows(fr_engine* e) {
@@ -660,4 +688,10 @@ fr_status frk_shard_wait(fr_engine* e, int slot, cudaStream_t st) {
   e->launches++;
   FR_CUDA(e, cudaGetLastError());
   return FR_OK;
+}
+
+// Host-side evaluation of the lookup kernels' index decode (same inline function), for the CPU tests of the packed
+// index rows: index of item b / descriptor offset idx_off out of rows of row_words int32 words.
+extern "C" int64_t frdbg_index_at(const int32_t* rows, int64_t b, int row_words, int idx_off) {
+  return fr_index_at(rows + b * (int64_t)row_words, idx_off);
 }

@@ -115,3 +115,53 @@ def test_release_library_has_no_experiments_and_reads_two_env_hooks(L):
     assert {f for f, _ in sites} == {"fr_api.cu"}, sites                 # one translation unit reads the environment
     release = src[src.index("static void fr_read_knobs"):src.index("#ifdef FR_EXPERIMENTS", src.index("static void fr_read_knobs"))]
     assert sorted(re.findall(r'getenv\("(\w+)"\)', release)) == ["FR_TC_MAX_CLUSTERS", "FR_TC_TILES"]
+
+
+def _layout(L, rows, fmt):
+    raw = C.CDLL(_capi.LIB_PATH)
+    raw.frdbg_index_layout.argtypes = [C.POINTER(C.c_int64), C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int)]
+    n = len(rows)
+    off, words = (C.c_int32 * max(n, 1))(), C.c_int(0)
+    assert raw.frdbg_index_layout((C.c_int64 * max(n, 1))(*rows), n, fmt, off, C.byref(words)) == 0
+    return [int(off[i]) for i in range(n)], words.value
+
+
+def test_packed_index_rows_layout_and_decode(L):
+    """FR_IDX_PACKED on the host: the layout rule (int32 columns of the tables above 65536 rows first, then uint16
+    columns, row padded to 4 bytes), fleetrec.pack_indices, and the lookup kernels' index decode (fr_index_at, the
+    same inline function compiled for the host) agree for every column of ragged rows."""
+    import numpy as np
+    raw = C.CDLL(_capi.LIB_PATH)
+    raw.frdbg_index_at.restype = C.c_int64
+    raw.frdbg_index_at.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int]
+    rng = np.random.default_rng(7)
+    cases = [[1], [65536], [65537], [65536, 65537, 3, 10 ** 8, 65536], [5] * 7, [10 ** 7] * 3, [],
+             [int(r) for r in rng.choice([4, 1000, 65535, 65536, 65537, 10 ** 6, 10 ** 8], size=47)]]
+    cases.append([t.rows for t in catalogue.load("small").tables])
+    for rows in cases:
+        for fmt in (fleetrec.FR_IDX_I32, fleetrec.FR_IDX_PACKED):
+            off, words = _layout(L, rows, fmt)
+            wid = [2 if o < 0 else 4 for o in off]
+            byte = [o & 0x7FFFFFFF for o in off]
+            if fmt == fleetrec.FR_IDX_I32:
+                assert byte == [4 * i for i in range(len(rows))] and all(w == 4 for w in wid) and words == len(rows)
+            else:
+                assert wid == [4 if r > 65536 else 2 for r in rows]
+                wide = [b for b, w in zip(byte, wid) if w == 4]
+                narrow = [b for b, w in zip(byte, wid) if w == 2]
+                assert wide == [4 * i for i in range(len(wide))]                       # table order, first
+                assert narrow == [4 * len(wide) + 2 * i for i in range(len(narrow))]   # then the uint16 columns
+                assert words == (4 * len(wide) + 2 * len(narrow) + 3) // 4
+            B = 9
+            idx = np.stack([rng.integers(0, r, size=B) for r in rows], axis=1).astype(np.int32) if rows else np.zeros((B, 0), np.int32)
+            if rows:
+                idx[0] = [r - 1 for r in rows]      # the largest index of every table
+                idx[1] = 0
+            packed = fleetrec.pack_indices(idx, (byte, wid, 4 * words))
+            assert packed.dtype == np.int32 and packed.shape == (B, words)
+            packed = np.ascontiguousarray(packed)
+            for b in range(B):
+                for c in range(len(rows)):
+                    assert raw.frdbg_index_at(packed.ctypes.data, b, words, off[c]) == idx[b, c], (rows, fmt, b, c)
+    small = [t.rows for t in catalogue.load("small").tables]
+    assert 4 * _layout(L, small, fleetrec.FR_IDX_PACKED)[1] == 120 and 4 * _layout(L, small, fleetrec.FR_IDX_I32)[1] == 188
