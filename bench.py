@@ -511,7 +511,9 @@ def run_ours(args):
         trace("per-kernel times")
         kms = eng.time_kernels(idx_dev[1], B, reps=args.kernel_reps, worker=workers[0])
         names = ["gather_concat", "mlp_layer1", "mlp_layer2", "mlp_layer3+out", "mlp_out"]
-        gather_bytes = B * cat.gather_bytes_per_item(materialised=True)
+        # SURVEY 8(d)'s per-item figure with the index bytes this run actually reads (packed rows are shorter than T*4)
+        item_bytes = cat.gather_bytes_per_item(materialised=True) - 4 * T + lay_full[2]
+        gather_bytes = B * item_bytes
         # SMs every MLP launch occupies (one CTA per SM): a 2048-item batch is 8..32 tiles, so a kernel timed ALONE runs
         # on 8..32 of the 148 SMs -- `frac` (the contract's definition, against the whole device) is small by
         # construction; `frac_of_occupied_sms` relates it to the tensor peak of the SMs it actually held, and
@@ -614,10 +616,10 @@ def run_ours(args):
             eng.gather_only_async(gidx, gout, GB, workers[0])
         eng.mark(1, workers[0])
         gms = eng.elapsed_ms(workers[0]) / 20
-        g_alg = GB * cat.gather_bytes_per_item(materialised=True)
+        g_alg = GB * item_bytes
         gather = dict(batch=GB, indices="uniform", ms=gms, achieved=g_alg / (gms * 1e-3) / 1e9, peak=pk["hbm"],
                       unit="GB/s", frac=g_alg / (gms * 1e-3) / 1e9 / pk["hbm"],
-                      bytes_per_item=cat.gather_bytes_per_item(True))
+                      bytes_per_item=item_bytes)
         del gidx, gout
 
         # ---- the same timed stream on fp16 operands, where the engine's range analysis allows them
