@@ -171,15 +171,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// 16 consecutive fp32 columns of this thread's TMEM lane.
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // fp32 -> tf32, round to nearest with ties away from zero (what cvt.rna.tf32.f32 computes for finite
 // values): add half an ulp of the 10-bit mantissa to the magnitude and clear the 13 low bits.  Two
@@ -414,7 +405,6 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -1099,7 +1089,6 @@ tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===== epilogue warps: TMEM lane quarter q = warp % 4, two warps per quarter on alternate chunks =====
     const int q = warp % 4, half = (warp - kEpiWarp0) / 4;
     const uint32_t empty_remote = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);   // the leader's tmem_empty_bar[0]
-    constexpr int CH = 128 / ELT;   // columns per chunk: 128 bytes of this thread's output row
     uint32_t it = 0;
     long long pf_acc = 0;
     FR_PROF_T0(pf_start);
