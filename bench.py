@@ -469,8 +469,7 @@ def run_ours(args):
     # bytes uploaded per step, all ranks together, counted from the tensors copied
     if sharded:   # (every rank's blocks, from the plan: no collective here -- the other ranks have already left)
         def row_bytes(tabs):
-            wide = args.index_format == "i32"
-            return (sum(4 if wide or cat.tables[t].rows > 65536 else 2 for t in tabs) + 3) // 4 * 4
+            return shard.index_layout([cat.tables[t].rows for t in tabs], packed=args.index_format == "packed")[2]
         per_rank = [Bg * row_bytes(shard.rank_tables(owner, r)[0]) + B * row_bytes(shard.rank_tables(owner, r)[1]) for r in range(world)]
         per_rank[rank] = Bg * lay_own[2] + B * lay_rep[2]     # this rank's: what fr_index_layout reported
     else:

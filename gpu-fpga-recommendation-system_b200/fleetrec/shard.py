@@ -90,6 +90,21 @@ def rank_tables(owner, rank):
     return ([t for t, o in enumerate(owner) if o == rank], [t for t, o in enumerate(owner) if o == -1])
 
 
+def index_layout(rows, packed=True):
+    """(byte_offsets, widths, row_bytes) of one index row over tables of `rows` rows each, in the engine's transport
+    formats -- what fr_index_layout reports for the same column list (include/fleetrec.h, FR_OPT_INDEX_FORMAT).
+    packed: int32 columns of the tables above 65536 rows first, in list order, then uint16 columns, row padded to 4."""
+    rows = list(rows)
+    if not packed:
+        return [4 * i for i in range(len(rows))], [4] * len(rows), 4 * len(rows)
+    off, wid, pos = [0] * len(rows), [4 if r > 65536 else 2 for r in rows], 0
+    for w in (4, 2):
+        for i, wi in enumerate(wid):
+            if wi == w:
+                off[i], pos = pos, pos + w
+    return off, wid, (pos + 3) // 4 * 4
+
+
 def slice_indices(idx, owner, world, rank):
     """Column-slice a global index batch [B][T] for one rank, as the reference's index source does per FPGA
     (each device is sent only its own tables' indices): returns (idx_owned [B][n_owned] over ALL items,

@@ -8,7 +8,7 @@ import re
 import pytest
 
 import fleetrec
-from fleetrec import _capi, catalogue
+from fleetrec import _capi, catalogue, shard
 from fleetrec.engine import model_desc
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -143,6 +143,7 @@ def test_packed_index_rows_layout_and_decode(L):
             off, words = _layout(L, rows, fmt)
             wid = [2 if o < 0 else 4 for o in off]
             byte = [o & 0x7FFFFFFF for o in off]
+            assert shard.index_layout(rows, packed=fmt == fleetrec.FR_IDX_PACKED) == (byte, wid, 4 * words)   # the host-side mirror
             if fmt == fleetrec.FR_IDX_I32:
                 assert byte == [4 * i for i in range(len(rows))] and all(w == 4 for w in wid) and words == len(rows)
             else:

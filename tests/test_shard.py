@@ -76,6 +76,15 @@ def test_column_sliced_index_blocks_cover_the_batch(model, world):
         assert np.array_equal(io, idx[:, owned]) and np.array_equal(ir, idx[b0:b1, repl])
         seen[owned] += 1
         assert io.size + ir.size < idx.size
+        # the same blocks in the packed transport format: every column decodes to the int32 block's
+        capped = cat.with_row_cap(1000)
+        for blk, tabs in ((io, owned), (ir, repl)):
+            off, wid, rb = shard.index_layout([capped.tables[t].rows if t % 3 else 10 ** 6 for t in tabs])
+            pk = fleetrec.pack_indices(blk, (off, wid, rb)).view(np.uint8).reshape(blk.shape[0], rb)
+            assert rb % 4 == 0 and rb <= 4 * len(tabs)
+            for c, (o, w) in enumerate(zip(off, wid)):
+                col = pk[:, o:o + w].copy().view("<u2" if w == 2 else "<i4").reshape(-1)
+                assert np.array_equal(col.astype(np.int64), blk[:, c].astype(np.int64))
     assert all(seen[t] == (0 if owner[t] == -1 else 1) for t in range(cat.n_tables))
 
 
