@@ -22,6 +22,7 @@
 #include <cuda_fp8.h>
 
 #include <stddef.h>
+#include <string.h>
 
 #include "fr_common.h"
 
@@ -95,8 +96,7 @@ __device__ __forceinline__ int64_t ld_index(const int32_t* __restrict__ idx, siz
 // A piece descriptor in two 128-bit loads (the compiler splits the struct copy into three or four).
 static_assert(offsetof(FrChunk, table) == 8 && offsetof(FrChunk, stride4) == 12 && offsetof(FrChunk, col4) == 16 &&
               offsetof(FrChunk, rows) == 20 && offsetof(FrChunk, idx_off) == 24, "ld_chunk unpacks this layout");
-__device__ __forceinline__ FrChunk ld_chunk(const FrChunk* __restrict__ p) {
-  const uint4 lo = __ldg(reinterpret_cast<const uint4*>(p)), hi = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+__host__ __device__ __forceinline__ FrChunk unpack_chunk(const uint4 lo, const uint4 hi) {
   FrChunk ch;
   ch.base = reinterpret_cast<const float4*>((uint64_t)lo.x | ((uint64_t)lo.y << 32));
   ch.table = (int)lo.z;
@@ -106,6 +106,9 @@ __device__ __forceinline__ FrChunk ld_chunk(const FrChunk* __restrict__ p) {
   ch.idx_off = (int)hi.z;
   ch.pad_ = 0;
   return ch;
+}
+__device__ __forceinline__ FrChunk ld_chunk(const FrChunk* __restrict__ p) {
+  return unpack_chunk(__ldg(reinterpret_cast<const uint4*>(p)), __ldg(reinterpret_cast<const uint4*>(p) + 1));
 }
 
 // PUSH = false: out4 is the local [B][C] buffer.
@@ -694,4 +697,12 @@ fr_status frk_shard_wait(fr_engine* e, int slot, cudaStream_t st) {
 // index rows: index of item b / descriptor offset idx_off out of rows of row_words int32 words.
 extern "C" int64_t frdbg_index_at(const int32_t* rows, int64_t b, int row_words, int idx_off) {
   return fr_index_at(rows + b * (int64_t)row_words, idx_off);
+}
+
+// The lookup kernels' descriptor unpack evaluated on the host (CPU test: out == in for any descriptor).
+extern "C" void frdbg_chunk_roundtrip(const void* chunk32, void* out32) {
+  uint4 w[2];
+  memcpy(w, chunk32, 32);
+  const FrChunk ch = unpack_chunk(w[0], w[1]);
+  memcpy(out32, &ch, 32);
 }

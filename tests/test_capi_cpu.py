@@ -166,3 +166,18 @@ def test_packed_index_rows_layout_and_decode(L):
                     assert raw.frdbg_index_at(packed.ctypes.data, b, words, off[c]) == idx[b, c], (rows, fmt, b, c)
     small = [t.rows for t in catalogue.load("small").tables]
     assert 4 * _layout(L, small, fleetrec.FR_IDX_PACKED)[1] == 120 and 4 * _layout(L, small, fleetrec.FR_IDX_I32)[1] == 188
+
+
+def test_lookup_descriptor_unpack_is_the_struct_layout(L):
+    """The lookup kernels fetch a 32-byte piece descriptor as two 128-bit words and unpack the fields by hand
+    (fr_gather.cu: unpack_chunk); the same function on the host reproduces any descriptor bit for bit."""
+    import numpy as np
+    raw = C.CDLL(_capi.LIB_PATH)
+    raw.frdbg_chunk_roundtrip.argtypes = [C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(3)
+    for _ in range(64):
+        src = rng.integers(0, 2 ** 32, size=8, dtype=np.uint64).astype(np.uint32)
+        src[7] = 0                                   # pad_
+        out = np.full(8, 0xFFFFFFFF, np.uint32)
+        raw.frdbg_chunk_roundtrip(src.ctypes.data, out.ctypes.data)
+        assert np.array_equal(src, out)
