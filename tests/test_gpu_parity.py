@@ -738,30 +738,18 @@ def test_reduced_precision_tables_bit_exact_after_stated_dequant(dt):
 
 # ---------------------------------------------------------------- B2-compatible TCP ingest (8f-3)
 def _send_blocks(port, blocks):
-    """What multiple_connections_network_client_sender.c:55-100 does: connect, then send() raw
-    little-endian bytes block after block, no header."""
-    import socket
-    with socket.create_connection(("127.0.0.1", port), timeout=30) as s:
-        for blk in blocks:
-            s.sendall(blk.tobytes())
+    """What multiple_connections_network_client_sender.c:55-100 does: connect, then send() raw little-endian bytes block
+    after block, no header (tests/wire.py; tests/test_wire_format.py checks it against the reference's own sender)."""
+    import wire
+    wire.send_blocks(port, blocks)
 
 
 def _free_base_port(n):
-    import socket
-    for base in range(18080, 28080, 97):
-        try:
-            socks = []
-            for i in range(n):
-                s = socket.socket()
-                s.bind(("127.0.0.1", base + i))
-                socks.append(s)
-            for s in socks:
-                s.close()
-            return base
-        except OSError:
-            for s in socks:
-                s.close()
-    pytest.skip("no free port range")
+    import wire
+    base = wire.free_base_port(n)
+    if base is None:
+        pytest.skip("no free port range")
+    return base
 
 
 @pytest.mark.parametrize("payload", ("concat", "indices"))
